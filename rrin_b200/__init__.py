@@ -1,0 +1,8 @@
+"""rrin_b200 -- B200-native (sm_100a) forward pass of RRIN frame interpolation.
+
+Public API mirrors the reference's ``model.py``: ``from rrin_b200 import Net``.
+"""
+from .model import Net  # noqa: F401
+
+__all__ = ["Net"]
+__version__ = "0.1.0"
