@@ -1,0 +1,109 @@
+/* rrin_b200 -- C-ABI of the B200-native (sm_100a) RRIN forward pass.
+ *
+ * This is the drop-in boundary beneath the Python `Net` module.
+ * The reference (Thomasedv/RRIN) has no FFI of its own: its hot path is the Python
+ * `Net.forward` (/root/reference/model.py:59-65) calling PyTorch operators.  Each entry
+ * point below therefore cites the reference *call site(s)* whose work it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
+ *   - functions return 0 on success, non-zero otherwise (rrin_last_error() gives the text);
+ *     they never throw, never allocate device memory, never synchronise the device;
+ *   - frames / results: fp32 NCHW [N,3,H,W] in [0,1]   (dataloader.py:116-118, convert.py:133)
+ *   - U-Net activations: bf16 NHWC; U-Net outputs (flow, residues, mask logits): fp32 NHWC4;
+ *   - H and W must be multiples of 16 (four 2x2 pools in the Flow U-Net, unet.py:46).
+ */
+#ifndef RRIN_B200_H_
+#define RRIN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RRIN_API __attribute__((visibility("default")))
+#else
+#define RRIN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRIN_OK 0
+#define RRIN_ERR_BAD_SHAPE 1
+#define RRIN_ERR_UNSUPPORTED 2
+#define RRIN_ERR_CUDA 3
+#define RRIN_ERR_BAD_ARG 4
+
+/* library version (major*10000 + minor*100 + patch) and last error text of this thread */
+RRIN_API int rrin_version(void);
+RRIN_API const char* rrin_last_error(void);
+
+/* ---- static description of the 81 convolutions, in execution order ----------------------
+ * Mirrors Net.__init__ (model.py:27-30) and UNet.__init__/forward (unet.py:10-51):
+ * U-Nets run in the order Flow, refine_flow, Mask, final (model.py:35,42,52,62).
+ * `key` receives the state_dict prefix of the conv, e.g. "Flow.down_path.0.block.0"
+ * (append ".weight" / ".bias"); src_mode: 0 plain, 1 cat(up,skip), 2 avg-pool, 3 bilinear x2,
+ * 4 packed head input. */
+RRIN_API int rrin_num_convs(void);
+RRIN_API int rrin_conv_info(int idx, char* key, int key_cap, int* cin, int* cout, int* level, int* src_mode, int* act);
+
+/* ---- K7: one-time weight repack (replaces nothing in the reference; cost of load_state_dict,
+ * convert.py:100-104).  w: fp32 OIHW [cout,cin,3,3], b: fp32 [cout] -> this conv's slice of the
+ * packed blob (bf16, per-tap K-major UMMA core-matrix order).  blob must be 256-byte aligned. */
+RRIN_API size_t rrin_packed_weights_bytes(void);
+RRIN_API int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* stream);
+
+/* ---- the engine: Net.forward (model.py:59-65) for a fixed problem shape -------------------
+ * n_pairs frame pairs and n_samples interpolated frames: either n_samples == n_pairs (sample i
+ * uses pair i: a batch, model.py:59) or n_pairs == 1 (all samples interpolate the same pair at
+ * different t; the t-independent Flow U-Net, model.py:33-35, then runs once). */
+typedef struct rrin_engine rrin_engine;
+RRIN_API int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** out);
+RRIN_API void rrin_engine_destroy(rrin_engine* e);
+RRIN_API size_t rrin_engine_workspace_bytes(const rrin_engine* e);   /* caller-provided scratch, 256-B aligned */
+RRIN_API int rrin_engine_num_launches(const rrin_engine* e);         /* kernels enqueued by one forward */
+/* coef: fp32 [n_samples][6] = {-(1-t)t, t*t, (1-t)(1-t), t(1-t), 1-t, t} (model.py:38-39,54).
+ * in0,in1: fp32 NCHW [n_pairs,3,H,W]; out: fp32 NCHW [n_samples,3,H,W]. */
+RRIN_API int rrin_engine_forward(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
+                        const float* coef, float* out, void* stream);
+/* debug/test taps: copy out intermediate fp32 NHWC4 tensors of the last forward.
+ * which: 0 flow (n_pairs), 1 blend output (n_samples).  dst is a device pointer of n*H*W*4 floats. */
+RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, float* dst, void* stream);
+
+/* ---- unit-level entry points (used by tests and micro-benchmarks) -------------------------
+ * K1: conv3x3(pad 1) + bias + optional LeakyReLU(0.1) on tcgen05 tensor cores.
+ * Replaces nn.Conv2d (unet.py:29,38,59,62,78) + LeakyReLU (unet.py:47,60,63), with the input
+ * transform folded into the operand loads: src_mode 0 plain, 1 cat(src0,src1) (unet.py:93),
+ * 2 avg_pool2d(src0,2) (unet.py:46), 3 bilinear x2 upsample of src0 (unet.py:77).
+ * src*: bf16 NHWC; N,H,W: output size; wpack/bias_pack from rrin_pack_conv_raw;
+ * out: bf16 NHWC [N,H,W,cout], or fp32 NHWC4 when out_f32 (cout <= 4 of 16 padded). */
+RRIN_API int rrin_conv_select_config(int cin, int cout, int out_f32);           /* -> config id or -1 */
+RRIN_API size_t rrin_conv_packed_weight_bytes(int cout, int cin_pad, int cfg);
+RRIN_API int rrin_conv_packed_bias_count(int cout, int cfg);
+RRIN_API int rrin_pack_conv_raw(const float* w, const float* b, int cout, int cin, int cin_pad, int cfg,
+                       void* wpack, float* bias_pack, void* stream);
+RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int N, int H, int W, int cout,
+                 const void* wpack, const float* bias_pack, void* out, int out_f32, int act, int cfg, void* stream);
+
+/* K6: torch.cat((x0,x1),1) (model.py:33) -> packed 16-channel bf16 NHWC head input. */
+RRIN_API int rrin_pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, void* stream);
+/* K2: flow t-scaling (model.py:37-39) + cat((F_t0,F_t1,x),1) (model.py:41) -> refine head input. */
+RRIN_API int rrin_flow_tscale_pack(const float* flow4, const float* in0, const float* in1, const float* coef, int n_samples,
+                          int pair_mul, int H, int W, void* r16, void* stream);
+/* K3: residue add (model.py:44-45) + warp x2 (model.py:8-21,47-48: grid build + F.grid_sample)
+ * + cat((F_t0,F_t1,x,xt1,xt2),1) (model.py:50) -> Mask head input m16 and fp32 xt8 = [xt1,xt2,0,0]. */
+RRIN_API int rrin_warp_pack(const float* flow4, const float* res4, const float* in0, const float* in1, const float* coef,
+                   int n_samples, int pair_mul, int H, int W, void* m16, float* xt8, void* stream);
+/* K4: sigmoid (model.py:52) + weights (model.py:54) + blend (model.py:55) + cat((in0,in1,output),1)
+ * (model.py:61) -> out4 (fp32 NHWC4) and the `final` head input f16. */
+RRIN_API int rrin_blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef,
+                    int n_samples, int pair_mul, int H, int W, float* out4, void* f16, void* stream);
+/* K5: final residue add + clamp(0,1) (model.py:62-63) -> fp32 NCHW result. */
+RRIN_API int rrin_residue_clamp(const float* res4, const float* out4, int n_samples, int H, int W, float* out_nchw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRIN_B200_H_ */

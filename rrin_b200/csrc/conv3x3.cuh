@@ -1,0 +1,412 @@
+// K1: 3x3 convolution (pad 1) + bias + optional LeakyReLU(0.1) as an implicit GEMM on the
+// 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM), NHWC bf16 activations.
+//
+// Replaces, for one conv of the reference U-Net, the torch ops of unet.py:
+//   nn.Conv2d(k=3,padding=1) (:29,38,59,62,78) + LeakyReLU(0.1) (:47,60,63), and -- folded into
+//   the operand loads so they are never materialised -- F.avg_pool2d(x,2) (:46),
+//   nn.Upsample(bilinear, x2) (:77) and torch.cat((up, bridge), 1) (:93).
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} A_tap[pixel, cin] * W[tap][cout, cin]
+//   M = 128 pixels = a 16(rows) x 8(cols) sub-tile of the image, MSUB sub-tiles side by side
+//   N = NT output channels (one n-tile), K = 9 taps x Cin, consumed KC channels per stage.
+//
+// Operand A is a *halo tile* ((16+2) x (8*MSUB+2) pixels x KC channels) staged once per
+// K-chunk and reused by all 9 taps: the tap (dy,dx) is just a different start address of
+// the UMMA shared-memory descriptor (K-major, SWIZZLE_NONE canonical layout: 8 pixels x
+// 16 bytes per core matrix; LBO = plane stride between 8-channel groups, SBO = one halo row).
+// That cuts L2->SMEM operand traffic ~7x versus per-tap im2col tiles.
+//
+// Warp roles (320 threads, 1 CTA / SM, persistent over a static tile schedule):
+//   warps 0-3  epilogue : TMEM -> regs (tcgen05.ld) -> +bias, LeakyReLU -> bf16 NHWC stores
+//   warp  4    MMA      : one lane issues tcgen05.mma / tcgen05.commit
+//   warp  5    weights  : one lane streams packed weight blocks with cp.async.bulk (TMA unit)
+//   warps 6-9  producer : build halo tiles (cp.async zero-fill for plain/cat; 2x2 mean or
+//                         bilinear x2 computed in registers for pool/up)
+// Pipelines: A ring (SA stages), B ring (SB weight blocks; fully resident when the layer's
+// 9*Cin/KC blocks fit), double-buffered TMEM accumulators (MMA <-> epilogue).
+#pragma once
+#include "common.cuh"
+#include "rrin_internal.h"
+
+namespace rrin {
+
+struct ConvParams {
+    const __nv_bfloat16* src0;   // NHWC bf16; plain/cat: [N,H,W,c0]; pool: [N,2H,2W,c0]; up: [N,H/2,W/2,c0]
+    const __nv_bfloat16* src1;   // cat only: [N,H,W,c1] (the skip), channels follow src0's
+    int c0, c1;
+    int mode;                    // ConvSrcMode
+    int N, H, W;                 // conv grid (== output) size
+    int cin;                     // c0 (+ c1 for cat); multiple of KC
+    int cout;                    // channels stored per pixel: bf16 -> n_ntiles*NT, f32 -> 4
+    const __nv_bfloat16* wpack;  // [n_ntiles][cin/KC][9][KC/8][NT][8] bf16 (pack_weights)
+    const float* bias;           // [n_ntiles*NT] fp32, zero padded
+    void* out;                   // bf16 NHWC [N,H,W,cout]  or  fp32 NHWC [N,H,W,4]
+    int out_f32;
+    int act;                     // 1 -> LeakyReLU(0.1)
+    int n_ntiles;
+    int tiles_x, tiles_y;
+    int total_work;              // n_ntiles * N * tiles_y * tiles_x
+    int b_resident;              // all 9*cin/KC weight blocks stay in SMEM (requires n_ntiles == 1)
+};
+
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 4;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kConvThreads = (kEpiWarps + 2 + kProdWarps) * 32;
+constexpr int kTileH = 16;
+
+template <int KC, int NT, int MSUB, int SA, int SB>
+struct ConvCfg {
+    static constexpr int CH8 = KC / 8;                 // 16-byte channel groups per stage
+    static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
+    static constexpr int HALO_PX = (kTileH + 2) * PW;
+    static constexpr int PLANE_PX = HALO_PX | 1;       // odd -> conflict-free plane-strided stores
+    static constexpr int PS = PLANE_PX * 16;           // bytes per 8-channel plane
+    static constexpr int A_STAGE = CH8 * PS;
+    static constexpr int B_BLOCK = NT * KC * 2;
+    static constexpr int TMEM_COLS = 2 * MSUB * NT;
+    static constexpr int BIAS_MAX = 512;
+    static constexpr int OFF_B = SA * A_STAGE;
+    static constexpr int OFF_BIAS = OFF_B + SB * B_BLOCK;
+    static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
+    static constexpr int NBAR = 2 * SA + 2 * SB + 4;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+    static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+    static_assert(KC % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+    static_assert(kProdThreads % CH8 == 0, "producer mapping");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// mean of four 8-channel bf16 vectors: ((a+b)+c)+d then *0.25 (ATen avg_pool2d sums h-major, then divides)
+__device__ __forceinline__ uint4 avg4_bf16x8(uint4 a, uint4 b, uint4 c, uint4 d) {
+    uint4 o;
+    const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+    uint32_t* po = &o.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 fa = unpack_bf16x2(pa[i]), fb = unpack_bf16x2(pb[i]), fc = unpack_bf16x2(pc[i]), fd = unpack_bf16x2(pd[i]);
+        po[i] = pack_bf16x2((((fa.x + fb.x) + fc.x) + fd.x) * 0.25f, (((fa.y + fb.y) + fc.y) + fd.y) * 0.25f);
+    }
+    return o;
+}
+// bilinear: wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11)   (ATen upsample_bilinear2d order)
+__device__ __forceinline__ uint4 bilerp_bf16x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11,
+                                               float wx1, float wy1) {
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    uint4 o;
+    const uint32_t* p00 = &v00.x; const uint32_t* p01 = &v01.x; const uint32_t* p10 = &v10.x; const uint32_t* p11 = &v11.x;
+    uint32_t* po = &o.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 a = unpack_bf16x2(p00[i]), b = unpack_bf16x2(p01[i]), c = unpack_bf16x2(p10[i]), d = unpack_bf16x2(p11[i]);
+        float rx = wy0 * (wx0 * a.x + wx1 * b.x) + wy1 * (wx0 * c.x + wx1 * d.x);
+        float ry = wy0 * (wx0 * a.y + wx1 * b.y) + wy1 * (wx0 * c.y + wx1 * d.y);
+        po[i] = pack_bf16x2(rx, ry);
+    }
+    return o;
+}
+// source index / weight of nn.Upsample(bilinear, x2, align_corners=False) for output index o
+// (ATen/native/UpSample.h:289-314,443-476): src = max((o+0.5)/2-0.5, 0); i1 = i0 + (i0 < size-1)
+__device__ __forceinline__ void up2_taps(int o, int size_in, int& i0, int& i1, float& w1) {
+    float src = fmaxf((o + 0.5f) * 0.5f - 0.5f, 0.f);
+    i0 = min((int)src, size_in - 1);
+    w1 = fminf(fmaxf(src - (float)i0, 0.f), 1.f);
+    i1 = i0 + (i0 < size_in - 1 ? 1 : 0);
+}
+
+template <int KC, int NT, int MSUB, int SA, int SB>
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const ConvParams p) {
+    using C = ConvCfg<KC, NT, MSUB, SA, SB>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_a = s_base;
+    const uint32_t s_b = s_base + C::OFF_B;
+    float* bias_s = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+    const uint32_t s_bar = s_base + C::OFF_BAR;
+    // barrier addresses
+    auto a_full = [&](int i) { return s_bar + 8u * i; };
+    auto a_empty = [&](int i) { return s_bar + 8u * (SA + i); };
+    auto b_full = [&](int i) { return s_bar + 8u * (2 * SA + i); };
+    auto b_empty = [&](int i) { return s_bar + 8u * (2 * SA + SB + i); };
+    auto acc_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + i); };
+    auto acc_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nch = p.cin / KC;          // K chunks (A stages) per tile
+    const int nblk = nch * 9;            // weight blocks per tile
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int tiles_per_nt = tiles_per_img * p.N;
+
+    // ---------------- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), kProdThreads); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps * 32); }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
+    if (warp == 4) {
+        tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 6) {
+        // =========================================================== producers: halo tiles
+        const int ptid = threadIdx.x - 6 * 32;
+        const int c8 = ptid % C::CH8;                      // this thread's 8-channel group
+        const int px0 = ptid / C::CH8;
+        constexpr int PXSTEP = kProdThreads / C::CH8;
+        constexpr int LAG = (SA >= 3) ? 2 : 1;             // cp.async groups kept in flight
+        const bool async_mode = (p.mode == SRC_PLAIN || p.mode == SRC_CAT);
+        int it = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+            int r = w % tiles_per_nt;
+            const int n = r / tiles_per_img; r -= n * tiles_per_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int y0 = ty * kTileH - 1, x0 = tx * (8 * MSUB) - 1;   // halo origin
+            for (int ch = 0; ch < nch; ++ch, ++it) {
+                const int stage = it % SA;
+                mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
+                const uint32_t dst0 = s_a + stage * C::A_STAGE + c8 * C::PS;
+                if (async_mode) {
+                    const __nv_bfloat16* src; int cs, coff;
+                    if (p.mode == SRC_CAT && ch * KC >= p.c0) { src = p.src1; cs = p.c1; coff = ch * KC - p.c0; }
+                    else { src = p.src0; cs = p.c0; coff = ch * KC; }
+                    src += coff + c8 * 8;
+                    for (int px = px0; px < C::HALO_PX; px += PXSTEP) {
+                        const int hy = px / C::PW, hx = px - hy * C::PW;
+                        const int gy = y0 + hy, gx = x0 + hx;
+                        const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                        const size_t off = ok ? ((size_t)(n * p.H + gy) * p.W + gx) * cs : 0;
+                        cp_async16_zfill(dst0 + px * 16, src + off, ok);
+                    }
+                    cp_async_commit();
+                    if (it >= LAG) {
+                        cp_async_wait<LAG>();
+                        fence_proxy_async_smem();
+                        mbar_arrive(a_full((it - LAG) % SA));
+                    }
+                } else if (p.mode == SRC_POOL) {
+                    const int H2 = 2 * p.H, W2 = 2 * p.W, cs = p.c0;
+                    const __nv_bfloat16* src = p.src0 + ch * KC + c8 * 8;
+                    const size_t rowb = (size_t)W2 * cs;
+                    for (int px = px0; px < C::HALO_PX; px += 2 * PXSTEP) {
+                        uint4 v[2][4]; bool okk[2]; int pxs[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int q = px + u * PXSTEP; pxs[u] = q;
+                            const int hy = q / C::PW, hx = q - hy * C::PW;
+                            const int gy = y0 + hy, gx = x0 + hx;
+                            okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                            if (okk[u]) {
+                                const __nv_bfloat16* s = src + ((size_t)(n * H2 + 2 * gy) * W2 + 2 * gx) * cs;
+                                v[u][0] = ldg_nc16(s); v[u][1] = ldg_nc16(s + cs);
+                                v[u][2] = ldg_nc16(s + rowb); v[u][3] = ldg_nc16(s + rowb + cs);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (pxs[u] < C::HALO_PX) {
+                                uint4 o = okk[u] ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3]) : make_uint4(0, 0, 0, 0);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + pxs[u] * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(a_full(stage));
+                } else {  // SRC_UP
+                    const int h2 = p.H >> 1, w2 = p.W >> 1, cs = p.c0;
+                    const __nv_bfloat16* src = p.src0 + ch * KC + c8 * 8;
+                    for (int px = px0; px < C::HALO_PX; px += 2 * PXSTEP) {
+                        uint4 v[2][4]; bool okk[2]; int pxs[2]; float wx[2], wy[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int q = px + u * PXSTEP; pxs[u] = q;
+                            const int hy = q / C::PW, hx = q - hy * C::PW;
+                            const int gy = y0 + hy, gx = x0 + hx;
+                            okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                            if (okk[u]) {
+                                int iy0, iy1, ix0, ix1;
+                                up2_taps(gy, h2, iy0, iy1, wy[u]);
+                                up2_taps(gx, w2, ix0, ix1, wx[u]);
+                                const __nv_bfloat16* r0 = src + (size_t)(n * h2 + iy0) * w2 * cs;
+                                const __nv_bfloat16* r1 = src + (size_t)(n * h2 + iy1) * w2 * cs;
+                                v[u][0] = ldg_nc16(r0 + (size_t)ix0 * cs); v[u][1] = ldg_nc16(r0 + (size_t)ix1 * cs);
+                                v[u][2] = ldg_nc16(r1 + (size_t)ix0 * cs); v[u][3] = ldg_nc16(r1 + (size_t)ix1 * cs);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (pxs[u] < C::HALO_PX) {
+                                uint4 o = okk[u] ? bilerp_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], wx[u], wy[u]) : make_uint4(0, 0, 0, 0);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + pxs[u] * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(a_full(stage));
+                }
+            }
+        }
+        if (async_mode) {   // drain the cp.async groups still in flight
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            for (int k = (it > LAG ? it - LAG : 0); k < it; ++k) mbar_arrive(a_full(k % SA));
+        }
+    } else if (warp == 5) {
+        // =========================================================== weight blocks (bulk copies)
+        if (lane == 0) {
+            if (p.b_resident) {
+                for (int b = 0; b < nblk; ++b) {
+                    mbar_arrive_expect_tx(b_full(b), C::B_BLOCK);
+                    bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KC), C::B_BLOCK, b_full(b));
+                }
+            } else {
+                int cnt = 0;
+                for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+                    const int nt = w / tiles_per_nt;
+                    const __nv_bfloat16* wsrc = p.wpack + (size_t)nt * nblk * (NT * KC);
+                    for (int b = 0; b < nblk; ++b, ++cnt) {
+                        const int slot = cnt % SB;
+                        mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_full(slot), C::B_BLOCK);
+                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KC), C::B_BLOCK, b_full(slot));
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            int it = 0, cnt = 0, tcount = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+                const int buf = tcount & 1;
+                mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * (MSUB * NT);
+                for (int ch = 0; ch < nch; ++ch, ++it) {
+                    const int stage = it % SA;
+                    mbar_wait(a_full(stage), (it / SA) & 1);
+                    tc_fence_after();
+                    const uint32_t a_stage = s_a + stage * C::A_STAGE;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap, ++cnt) {
+                        int slot;
+                        if (p.b_resident) { slot = ch * 9 + tap; mbar_wait(b_full(slot), 0); }
+                        else { slot = cnt % SB; mbar_wait(b_full(slot), (cnt / SB) & 1); }
+                        tc_fence_after();
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint32_t a_tap = a_stage + (dy * C::PW + dx) * 16;
+                        const uint32_t b_blk = s_b + slot * C::B_BLOCK;
+#pragma unroll
+                        for (int j = 0; j < MSUB; ++j) {
+#pragma unroll
+                            for (int s = 0; s < KC / 16; ++s) {
+                                const uint64_t ad = make_smem_desc(a_tap + j * 128 + 2 * s * C::PS, C::PS, C::PW * 16);
+                                const uint64_t bd = make_smem_desc(b_blk + 2 * s * (NT * 16), NT * 16, 128);
+                                umma_bf16(d0 + j * NT, ad, bd, idesc, (ch | tap | s) != 0);
+                            }
+                        }
+                        if (!p.b_resident) umma_commit(b_empty(slot));
+                    }
+                    umma_commit(a_empty(stage));
+                }
+                umma_commit(acc_full(buf));
+            }
+        }
+    } else {
+        // =========================================================== epilogue (warps 0-3)
+        const int m = warp * 32 + lane;                 // accumulator row == TMEM lane
+        const int ly = m >> 3, lx = m & 7;
+        int tcount = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+            const int nt = w / tiles_per_nt;
+            int r = w - nt * tiles_per_nt;
+            const int n = r / tiles_per_img; r -= n * tiles_per_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int buf = tcount & 1;
+            mbar_wait(acc_full(buf), (tcount >> 1) & 1);
+            tc_fence_after();
+            const int gy = ty * kTileH + ly;
+            const float* bsrc = bias_s + nt * NT;
+#pragma unroll 1
+            for (int j = 0; j < MSUB; ++j) {
+                const int gx = tx * (8 * MSUB) + 8 * j + lx;
+                const bool ok = (gy < p.H) && (gx < p.W);
+                const size_t pix = (size_t)(n * p.H + gy) * p.W + gx;
+                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * MSUB + j) * NT;
+                if (p.out_f32) {
+                    uint32_t r16[16];
+                    tmem_ld16(t0, r16);
+                    tmem_ld_wait();
+                    if (ok) {
+                        float4 o;
+                        o.x = __uint_as_float(r16[0]) + bsrc[0]; o.y = __uint_as_float(r16[1]) + bsrc[1];
+                        o.z = __uint_as_float(r16[2]) + bsrc[2]; o.w = __uint_as_float(r16[3]) + bsrc[3];
+                        reinterpret_cast<float4*>(p.out)[pix] = o;
+                    }
+                } else {
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nt * NT;
+#pragma unroll 1
+                    for (int c = 0; c < NT; c += 32) {
+                        uint32_t ra[16], rb[16];
+                        tmem_ld16(t0 + c, ra);
+                        if (NT >= 32) tmem_ld16(t0 + c + 16, rb);
+                        tmem_ld_wait();
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float v0 = __uint_as_float(ra[2 * i]) + bsrc[c + 2 * i];
+                            float v1 = __uint_as_float(ra[2 * i + 1]) + bsrc[c + 2 * i + 1];
+                            if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
+                            o[i] = pack_bf16x2(v0, v1);
+                        }
+                        if (NT >= 32) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float v0 = __uint_as_float(rb[2 * i]) + bsrc[c + 16 + 2 * i];
+                                float v1 = __uint_as_float(rb[2 * i + 1]) + bsrc[c + 16 + 2 * i + 1];
+                                if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
+                                o[8 + i] = pack_bf16x2(v0, v1);
+                            }
+                        }
+                        if (ok) {
+                            uint4* o4 = reinterpret_cast<uint4*>(op + c);
+                            o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                            if (NT >= 32) {
+                                o4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                                o4[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty(buf));
+        }
+    }
+
+    // ---------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+}  // namespace rrin

@@ -1,0 +1,124 @@
+"""Host side of the engine: packed weights, workspace and the forward call.
+
+PyTorch is used only as plumbing here -- device allocations (weights blob, workspace, output)
+and the current CUDA stream.  All arithmetic happens inside ``librrin_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Union
+
+import torch
+
+from ._lib import check, lib
+
+
+def conv_table():
+    """[(key, cin, cout, level, src_mode, act)] for the 81 convs in execution order."""
+    l = lib()
+    out = []
+    buf = C.create_string_buffer(128)
+    for i in range(l.rrin_num_convs()):
+        v = [C.c_int() for _ in range(5)]
+        check(l.rrin_conv_info(i, buf, 128, *[C.byref(x) for x in v]), "rrin_conv_info")
+        out.append((buf.value.decode(), *[x.value for x in v]))
+    return out
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class PackedWeights:
+    """bf16 UMMA-ordered copy of all 81 conv weights + fp32 biases in one device blob (K7)."""
+
+    def __init__(self, net: torch.nn.Module, device: torch.device, fingerprint=None):
+        l = lib()
+        self.device, self.fingerprint = device, fingerprint
+        sd = net.state_dict()
+        with torch.cuda.device(device):
+            self.blob = torch.zeros(l.rrin_packed_weights_bytes(), dtype=torch.uint8, device=device)
+            keep = []
+            for i, (key, cin, cout, *_rest) in enumerate(conv_table()):
+                w = sd[key + ".weight"].detach().to(device=device, dtype=torch.float32).contiguous()
+                b = sd[key + ".bias"].detach().to(device=device, dtype=torch.float32).contiguous()
+                if tuple(w.shape) != (cout, cin, 3, 3) or tuple(b.shape) != (cout,):
+                    raise RuntimeError(f"size mismatch for {key}: {tuple(w.shape)} vs {(cout, cin, 3, 3)}")
+                keep += [w, b]
+                check(l.rrin_pack_conv(i, _ptr(w), _ptr(b), _ptr(self.blob), _stream()), f"rrin_pack_conv({key})")
+            torch.cuda.current_stream().synchronize()   # w/b temporaries may be freed after this
+
+
+def time_coefficients(t: Union[float, torch.Tensor, Sequence[float]], n: int, device) -> torch.Tensor:
+    """fp32 [n,6] = {-(1-t)t, t*t, (1-t)(1-t), t(1-t), 1-t, t} as model.py:38-39,54 evaluates them:
+    Python-float t -> products in double, rounded once to fp32 (scalar * tensor semantics);
+    tensor t -> the same expressions in fp32 tensor arithmetic."""
+    if isinstance(t, torch.Tensor):
+        tt = t.detach().to(dtype=torch.float32, device="cpu").reshape(-1)
+        if tt.numel() == 1:
+            tt = tt.expand(n)
+        if tt.numel() != n:
+            raise RuntimeError("tensor-valued t must be a scalar or broadcast per sample ([N,1,1,1]); "
+                               f"got {tuple(t.shape)} for batch {n}")
+        c = torch.stack([-(1 - tt) * tt, tt * tt, (1 - tt) * (1 - tt), tt * (1 - tt), 1 - tt, tt], 1)
+        return c.contiguous().to(device)
+    ts = [float(t)] * n if not isinstance(t, (list, tuple)) else [float(x) for x in t]
+    if len(ts) != n:
+        raise RuntimeError(f"expected {n} timesteps, got {len(ts)}")
+    rows = [[-(1 - x) * x, x * x, (1 - x) * (1 - x), x * (1 - x), 1 - x, x] for x in ts]
+    return torch.tensor(rows, dtype=torch.float64).to(torch.float32).to(device)
+
+
+class Engine:
+    """One problem shape (n_pairs, n_samples, H, W) on one device."""
+
+    def __init__(self, device: torch.device, n: int, h: int, w: int, n_pairs: int | None = None):
+        l = lib()
+        self.device, self.n, self.h, self.w = device, n, h, w
+        self.n_pairs = n if n_pairs is None else n_pairs
+        hnd = C.c_void_p()
+        check(l.rrin_engine_create(self.n_pairs, n, h, w, C.byref(hnd)), "rrin_engine_create")
+        self._h = hnd
+        with torch.cuda.device(device):
+            self.workspace = torch.empty(l.rrin_engine_workspace_bytes(hnd), dtype=torch.uint8, device=device)
+        self.num_launches = l.rrin_engine_num_launches(hnd)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().rrin_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def invalidate_graph(self):
+        pass
+
+    def run(self, weights: "PackedWeights", in0: torch.Tensor, in1: torch.Tensor, coef: torch.Tensor,
+            out: torch.Tensor | None = None) -> torch.Tensor:
+        in0 = in0.detach().to(torch.float32).contiguous()
+        in1 = in1.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((self.n, 3, self.h, self.w), dtype=torch.float32, device=self.device)
+            check(lib().rrin_engine_forward(self._h, _ptr(weights.blob), _ptr(self.workspace), _ptr(in0), _ptr(in1),
+                                            _ptr(coef), _ptr(out), _stream()), "rrin_engine_forward")
+        return out
+
+    def forward(self, weights, in0, in1, t) -> torch.Tensor:
+        return self.run(weights, in0, in1, time_coefficients(t, self.n, self.device))
+
+    def forward_multi(self, weights, in0, in1, ts: List[float]) -> torch.Tensor:
+        if self.n_pairs != 1:
+            raise RuntimeError("forward_multi needs an engine created with n_pairs=1")
+        return self.run(weights, in0, in1, time_coefficients(list(ts), self.n, self.device))
+
+    def tap(self, which: int) -> torch.Tensor:
+        n = self.n_pairs if which == 0 else self.n
+        dst = torch.empty((n, self.h, self.w, 4), dtype=torch.float32, device=self.device)
+        check(lib().rrin_engine_tap(self._h, _ptr(self.workspace), which, _ptr(dst), _stream()), "rrin_engine_tap")
+        return dst
