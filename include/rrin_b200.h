@@ -68,6 +68,13 @@ RRIN_API int rrin_engine_num_launches(const rrin_engine* e);         /* kernels 
  * in0,in1: fp32 NCHW [n_pairs,3,H,W]; out: fp32 NCHW [n_samples,3,H,W]. */
 RRIN_API int rrin_engine_forward(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
                         const float* coef, float* out, void* stream);
+/* Profiling aids (bench.py): description of launch i of one forward (kernel class, reference layer,
+ * algorithmic FLOPs and HBM bytes), and a forward that records a CUDA event after every launch and
+ * returns per-launch device milliseconds in the HOST array ms_host[num_launches] (synchronises). */
+RRIN_API int rrin_engine_launch_info(const rrin_engine* e, int i, char* name, int name_cap, char* layer, int layer_cap,
+                            double* flops, double* bytes);
+RRIN_API int rrin_engine_forward_profiled(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
+                                 const float* coef, float* out, void* stream, float* ms_host);
 /* debug/test taps: copy out intermediate fp32 NHWC4 tensors of the last forward.
  * which: 0 flow (n_pairs), 1 blend output (n_samples).  dst is a device pointer of n*H*W*4 floats. */
 RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, float* dst, void* stream);

@@ -111,7 +111,13 @@ struct rrin_engine {
     // workspace offsets (bytes)
     size_t off_tmp[3], off_skip[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
     int launches;
+    std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every launch
+    int prof_n = 0;
 };
+
+static inline void mark(const rrin_engine* e, cudaStream_t st) {
+    if (e->prof && e->prof_n < (int)e->prof->size()) cudaEventRecord((*e->prof)[const_cast<rrin_engine*>(e)->prof_n++], st);
+}
 
 static size_t lvl_bytes(int B, int H, int W, int lvl) {   // bf16 NHWC tensor of level lvl
     return (size_t)B * (H >> lvl) * (W >> lvl) * (32 << lvl) * 2;
@@ -194,7 +200,9 @@ static int run_unet(const rrin_engine* e, int u, int B, const uint8_t* blob, uin
         cd.N = B; cd.H = e->H >> lvl; cd.W = e->W >> lvl;
         cd.cout = L.cout; cd.wpack = blob + L.w_off; cd.bias = reinterpret_cast<const float*>(blob + L.b_off);
         cd.out = out; cd.out_f32 = L.out_f32; cd.act = L.act; cd.cfg = L.cfg;
-        return conv_launch(cd, st);
+        const int r = conv_launch(cd, st);
+        mark(e, st);
+        return r;
     };
     const void* x = head16;
     int xc = 16;
@@ -230,15 +238,86 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
     float* xt8 = reinterpret_cast<float*>(ws + e->off_xt8);
     const int H = e->H, W = e->W, Np = e->Np, Nt = e->Nt, pm = e->pair_mul;
     int r;
+    mark(e, st);                                                                                  // t0
     if ((r = pack_pair(in0, in1, Np, H, W, h16, st))) return r;                                   // model.py:33
+    mark(e, st);
     if ((r = run_unet(e, 0, Np, blob, ws, h16, flow4, st))) return r;                             // model.py:35
     if ((r = flow_tscale_pack(flow4, in0, in1, coef, Nt, pm, H, W, h16, st))) return r;           // model.py:37-41
+    mark(e, st);
     if ((r = run_unet(e, 1, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:42
     if ((r = warp_pack(flow4, u4, in0, in1, coef, Nt, pm, H, W, h16, xt8, st))) return r;         // model.py:44-50
+    mark(e, st);
     if ((r = run_unet(e, 2, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:52
     if ((r = blend_pack(u4, xt8, in0, in1, coef, Nt, pm, H, W, out4, h16, st))) return r;         // model.py:52-55,61
+    mark(e, st);
     if ((r = run_unet(e, 3, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:62
-    return residue_clamp(u4, out4, Nt, H, W, out, st);                                            // model.py:62-63
+    r = residue_clamp(u4, out4, Nt, H, W, out, st);                                               // model.py:62-63
+    mark(e, st);
+    return r;
+}
+
+// Launch i of one forward, in stream order: kernel class name, the reference layer it computes,
+// algorithmic FLOPs and algorithmic HBM bytes (each operand/result tensor crossing once).
+int rrin_engine_launch_info(const rrin_engine* e, int i, char* name, int name_cap, char* layer, int layer_cap,
+                            double* flops, double* bytes) {
+    if (!e || i < 0 || i >= e->launches) { set_error("rrin_engine_launch_info: bad index %d", i); return RRIN_ERR_BAD_ARG; }
+    const Schedule& s = schedule();
+    const double px = (double)e->H * e->W;
+    std::string nm, ly; double fl = 0, by = 0;
+    // glue launches sit before U-Net 0, between U-Nets, and at the end
+    int pos = i, li = -1;
+    const char* glue_names[5] = {"pack_pair", "flow_tscale_pack", "warp_pack", "blend_pack", "residue_clamp"};
+    const double glue_bytes[5] = {56, 72, 120, 120, 44};          // per pixel, see DESIGN.md
+    int g = -1;
+    for (int u = 0; u < 4 && g < 0 && li < 0; ++u) {
+        if (pos == 0) { g = u; break; }
+        pos -= 1;
+        const int nl = s.first[u + 1] - s.first[u];
+        if (pos < nl) { li = s.first[u] + pos; break; }
+        pos -= nl;
+    }
+    if (g < 0 && li < 0) g = 4;
+    if (g >= 0) {
+        nm = glue_names[g]; ly = std::string("model.py glue: ") + glue_names[g];
+        by = glue_bytes[g] * px * (g == 0 ? e->Np : e->Nt);
+    } else {
+        const Layer& L = s.layers[li];
+        int kc, nt, msub; conv_config_info(L.cfg, &kc, &nt, &msub);
+        char b[96]; snprintf(b, sizeof b, "conv3x3_umma<KC%d,NT%d,MSUB%d>", kc, nt, msub);
+        nm = b; ly = L.key;
+        const int B = (L.unet == 0) ? e->Np : e->Nt;
+        const double lp = px * B / (double)(1 << (2 * L.level));
+        fl = 2.0 * 9 * L.cin * L.cout * lp;
+        double in_b = 2.0 * L.cin_pad * lp;                       // bf16 operand tensor(s) at this level
+        if (L.src == K_POOL) in_b *= 4; else if (L.src == K_UP) in_b /= 4;
+        const double out_b = L.out_f32 ? 16.0 * lp : 2.0 * L.cout * lp;
+        by = in_b + out_b + (double)conv_packed_weight_bytes(L.cout, L.cin_pad, L.cfg);
+    }
+    if (name && name_cap > 0) { strncpy(name, nm.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (layer && layer_cap > 0) { strncpy(layer, ly.c_str(), layer_cap - 1); layer[layer_cap - 1] = 0; }
+    if (flops) *flops = fl;
+    if (bytes) *bytes = by;
+    return RRIN_OK;
+}
+
+// One forward with a CUDA event after every launch; ms[i] = device time of launch i.
+// Synchronises the stream (profiling aid for bench.py, not part of the product path).
+int rrin_engine_forward_profiled(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
+                                 const float* coef, float* out, void* stream, float* ms_host) {
+    if (!e || !ms_host) { set_error("rrin_engine_forward_profiled: null argument"); return RRIN_ERR_BAD_ARG; }
+    std::vector<cudaEvent_t> ev(e->launches + 1);
+    for (auto& x : ev) RRIN_CUDA_CHECK(cudaEventCreate(&x));
+    e->prof = &ev; e->prof_n = 0;
+    int r = rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
+    e->prof = nullptr;
+    if (r == RRIN_OK) {
+        cudaError_t ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        if (ce != cudaSuccess) { set_error("profiled forward failed: %s", cudaGetErrorString(ce)); r = RRIN_ERR_CUDA; }
+    }
+    if (r == RRIN_OK)
+        for (int i = 0; i < e->launches; ++i) cudaEventElapsedTime(&ms_host[i], ev[i], ev[i + 1]);
+    for (auto& x : ev) cudaEventDestroy(x);
+    return r;
 }
 
 int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, float* dst, void* stream) {

@@ -86,6 +86,7 @@ class Engine:
         with torch.cuda.device(device):
             self.workspace = torch.empty(l.rrin_engine_workspace_bytes(hnd), dtype=torch.uint8, device=device)
         self.num_launches = l.rrin_engine_num_launches(hnd)
+        self._coef_cache = {}
 
     def __del__(self):
         try:
@@ -109,13 +110,46 @@ class Engine:
                                             _ptr(coef), _ptr(out), _stream()), "rrin_engine_forward")
         return out
 
+    def _coef(self, t):
+        if isinstance(t, torch.Tensor):
+            return time_coefficients(t, self.n, self.device)
+        key = tuple(t) if isinstance(t, (list, tuple)) else float(t)
+        c = self._coef_cache.get(key)
+        if c is None:
+            if len(self._coef_cache) > 64:
+                self._coef_cache.clear()
+            c = self._coef_cache[key] = time_coefficients(t, self.n, self.device)
+        return c
+
     def forward(self, weights, in0, in1, t) -> torch.Tensor:
-        return self.run(weights, in0, in1, time_coefficients(t, self.n, self.device))
+        return self.run(weights, in0, in1, self._coef(t))
 
     def forward_multi(self, weights, in0, in1, ts: List[float]) -> torch.Tensor:
         if self.n_pairs != 1:
             raise RuntimeError("forward_multi needs an engine created with n_pairs=1")
-        return self.run(weights, in0, in1, time_coefficients(list(ts), self.n, self.device))
+        return self.run(weights, in0, in1, self._coef(list(ts)))
+
+    def launch_table(self):
+        """[(kernel_class, layer, flops, bytes)] for the launches of one forward, in stream order."""
+        l, out = lib(), []
+        nm, ly = C.create_string_buffer(128), C.create_string_buffer(128)
+        for i in range(self.num_launches):
+            fl, by = C.c_double(), C.c_double()
+            check(l.rrin_engine_launch_info(self._h, i, nm, 128, ly, 128, C.byref(fl), C.byref(by)))
+            out.append((nm.value.decode(), ly.value.decode(), fl.value, by.value))
+        return out
+
+    def profile(self, weights, in0, in1, t) -> List[float]:
+        """Per-launch device milliseconds of one forward (CUDA events on the launching stream)."""
+        coef = time_coefficients(t, self.n, self.device)
+        in0 = in0.detach().float().contiguous()
+        in1 = in1.detach().float().contiguous()
+        ms = (C.c_float * self.num_launches)()
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.n, 3, self.h, self.w), dtype=torch.float32, device=self.device)
+            check(lib().rrin_engine_forward_profiled(self._h, _ptr(weights.blob), _ptr(self.workspace), _ptr(in0), _ptr(in1),
+                                                     _ptr(coef), _ptr(out), _stream(), ms), "rrin_engine_forward_profiled")
+        return list(ms)
 
     def tap(self, which: int) -> torch.Tensor:
         n = self.n_pairs if which == 0 else self.n

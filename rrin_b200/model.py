@@ -34,7 +34,7 @@ class Net(nn.Module):
         self.Flow = UNet(6, 4, 5)
         self.refine_flow = UNet(10, 4, 4)
         self.final = UNet(9, 3, 4)
-        self._engines = {}        # (device, N, H, W) -> engine.Engine
+        self._engines = {}        # (device, n_pairs, N, H, W) -> engine.Engine
         self._packed = None       # engine.PackedWeights, rebuilt when parameters change
         self.precision = "bf16"   # operand format of the tensor-core path (fp32 accumulate)
 
@@ -51,14 +51,15 @@ class Net(nn.Module):
                 e.invalidate_graph()
         return self._packed
 
-    def _engine(self, device, n, h, w):
+    def _engine(self, device, n, h, w, n_pairs=None):
         from . import engine
-        key = (device, n, h, w)
+        n_pairs = n if n_pairs is None else n_pairs
+        key = (device, n_pairs, n, h, w)
         e = self._engines.get(key)
         if e is None:
             if len(self._engines) >= 4:           # bound workspace memory: keep few shapes alive
                 self._engines.pop(next(iter(self._engines)))
-            e = self._engines[key] = engine.Engine(device, n, h, w)
+            e = self._engines[key] = engine.Engine(device, n, h, w, n_pairs)
         return e
 
     # ------------------------------------------------------------------ forward
@@ -100,5 +101,5 @@ class Net(nn.Module):
         dev = input0.device
         _, _, h, w = input0.shape
         with torch.no_grad():
-            eng = self._engine(dev, len(ts), h, w)
+            eng = self._engine(dev, len(ts), h, w, n_pairs=1)
             return eng.forward_multi(self._weights(dev), input0, input1, list(ts))

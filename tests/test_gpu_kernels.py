@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
-    from tests import gpu_util as G
+    import gpu_util as G
     from oracle import rrin_oracle as O
 
 
@@ -97,6 +97,7 @@ def test_glue_kernels_match_oracle_ops():
         return o.cuda().contiguous()
 
     ad, bd, coef = a.cuda(), b.cuda(), _coef(ts)
+    flow4, res4, logit4, fres4 = nhwc4(flow), nhwc4(res), nhwc4(logit), nhwc4(fres)   # keep alive: raw pointers below
     s = G.stream()
     # K6
     x16 = torch.empty(n, h, w, 16, dtype=torch.bfloat16, device="cuda")
@@ -108,7 +109,7 @@ def test_glue_kernels_match_oracle_ops():
     ft0 = -(1 - tt) * tt * f01 + tt * tt * f10
     ft1 = (1 - tt) * (1 - tt) * f01 - tt * (1 - tt) * f10
     r16 = torch.empty_like(x16)
-    check(l.rrin_flow_tscale_pack(nhwc4(flow).data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w, r16.data_ptr(), s))
+    check(l.rrin_flow_tscale_pack(flow4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w, r16.data_ptr(), s))
     ref = torch.cat((ft0, ft1, a, b), 1).permute(0, 2, 3, 1)
     assert (r16[..., :10].float().cpu() - ref).abs().max() <= 2 ** -8 * ref.abs().max() and (r16[..., 10:] == 0).all()
     # K3
@@ -116,7 +117,7 @@ def test_glue_kernels_match_oracle_ops():
     xt1, xt2 = O.warp(a, ft0r), O.warp(b, ft1r)
     m16 = torch.empty_like(x16)
     xt8 = torch.empty(n, h, w, 8, device="cuda")
-    check(l.rrin_warp_pack(nhwc4(flow).data_ptr(), nhwc4(res).data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
+    check(l.rrin_warp_pack(flow4.data_ptr(), res4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
                            m16.data_ptr(), xt8.data_ptr(), s))
     xt_ref = torch.cat((xt1, xt2), 1).permute(0, 2, 3, 1)
     assert (xt8[..., :6].cpu() - xt_ref).abs().max() <= 2e-5, (xt8[..., :6].cpu() - xt_ref).abs().max()
@@ -129,14 +130,14 @@ def test_glue_kernels_match_oracle_ops():
     blend = (w1 * xt1 + w2 * xt2) / (w1 + w2 + 1e-8)
     out4 = torch.empty(n, h, w, 4, device="cuda")
     f16 = torch.empty_like(x16)
-    check(l.rrin_blend_pack(nhwc4(logit).data_ptr(), xt8.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
+    check(l.rrin_blend_pack(logit4.data_ptr(), xt8.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
                             out4.data_ptr(), f16.data_ptr(), s))
     assert (out4[..., :3].cpu() - blend.permute(0, 2, 3, 1)).abs().max() <= 3e-5
     ref = torch.cat((a, b, blend), 1).permute(0, 2, 3, 1)
     assert (f16[..., :9].float().cpu() - ref).abs().max() <= 2 ** -8 and (f16[..., 9:] == 0).all()
     # K5
     y = torch.empty(n, 3, h, w, device="cuda")
-    check(l.rrin_residue_clamp(nhwc4(fres).data_ptr(), out4.data_ptr(), n, h, w, y.data_ptr(), s))
+    check(l.rrin_residue_clamp(fres4.data_ptr(), out4.data_ptr(), n, h, w, y.data_ptr(), s))
     ref = (fres + out4[..., :3].cpu().permute(0, 3, 1, 2)).clamp(0, 1)
     assert (y.cpu() - ref).abs().max() <= 1e-6
     assert ((y == 0) | (y == 1)).float().mean() > 0.05      # the clamp is exercised
@@ -150,8 +151,9 @@ def test_glue_multi_t_shares_pair():
     a, b = O.seeded_frames(1, h, w, seed=9)
     flow = torch.randn(1, h, w, 4, generator=torch.Generator().manual_seed(1)).cuda()
     coef = _coef(ts)
+    ad, bd = a.cuda(), b.cuda()
     r16 = torch.empty(3, h, w, 16, dtype=torch.bfloat16, device="cuda")
-    check(l.rrin_flow_tscale_pack(flow.data_ptr(), a.cuda().data_ptr(), b.cuda().data_ptr(), coef.data_ptr(), 3, 0, h, w, r16.data_ptr(), G.stream()))
+    check(l.rrin_flow_tscale_pack(flow.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), 3, 0, h, w, r16.data_ptr(), G.stream()))
     torch.cuda.synchronize()
     for i, t in enumerate(ts):
         f = flow[0].cpu()
