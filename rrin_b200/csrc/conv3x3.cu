@@ -8,21 +8,19 @@ namespace rrin {
 
 // ------------------------------------------------------------------ configuration table
 // id : <KC, NT, MSUB, SA, SB>      used for
-//  0 : <16, 32, 4, 3,  9>   head convs   Cin in {6,9,10,16} (stored as 16 ch) -> 32
-//  1 : <32, 32, 4, 3, 18>   level 0      32->32, up 64->32, cat(32+32)->32 (weights resident)
-//  2 : <32, 16, 4, 3,  9>   `last`       32 -> {2,3,4} (N padded to 16), fp32 NHWC4 output
-//  3 : <32, 64, 4, 3,  9>   level 1      pool(32) -> 64
-//  4 : <64, 64, 2, 3,  9>   level 1      64 -> 64 (weights resident)
-//  5 : <64, 64, 4, 2,  4>   level 1      up 128->64, cat(64+64)->64 (weights streamed)
-//  6 : <64,128, 2, 3,  4>   levels >= 2  Cout in {128,256,512} as n-tiles of 128
+//  0 : <16, 32, 4, 4,  9>   head convs   Cin in {6,9,10,16} (stored as 16 ch) -> 32
+//  1 : <32, 32, 4, 4, 18>   level 0      32->32, up 64->32, cat(32+32)->32 (weights resident)
+//  2 : <32, 16, 4, 4,  9>   `last`       32 -> {2,3,4} (N padded to 16), fp32 NHWC4 output
+//  3 : <32, 64, 4, 4,  9>   level 1      pool(32) -> 64
+//  4 : <64, 64, 2, 3,  9>   level 1      64->64 (weights resident); up 128->64, cat(64+64)->64 (streamed)
+//  5 : <64,128, 2, 3,  4>   levels >= 2  Cout in {128,256,512} as n-tiles of 128
 #define RRIN_CONV_CONFIGS(X) \
-    X(0, 16, 32, 4, 3, 9)    \
-    X(1, 32, 32, 4, 3, 18)   \
-    X(2, 32, 16, 4, 3, 9)    \
-    X(3, 32, 64, 4, 3, 9)    \
+    X(0, 16, 32, 4, 4, 9)    \
+    X(1, 32, 32, 4, 4, 18)   \
+    X(2, 32, 16, 4, 4, 9)    \
+    X(3, 32, 64, 4, 4, 9)    \
     X(4, 64, 64, 2, 3, 9)    \
-    X(5, 64, 64, 4, 2, 4)    \
-    X(6, 64, 128, 2, 3, 4)
+    X(5, 64, 128, 2, 3, 4)
 
 struct CfgInfo { int kc, nt, msub, sa, sb, smem; };
 static const CfgInfo kCfg[] = {
@@ -36,8 +34,8 @@ int conv_select_config(int cin, int cout, int out_f32) {
     if (out_f32) return (cin == 32 && cout <= 16) ? 2 : -1;
     if (cin == 16) return cout == 32 ? 0 : -1;
     if (cout == 32) return (cin == 32 || cin == 64) ? 1 : -1;
-    if (cout == 64) return cin == 32 ? 3 : cin == 64 ? 4 : cin == 128 ? 5 : -1;
-    if (cout % 128 == 0 && cin % 64 == 0) return 6;
+    if (cout == 64) return cin == 32 ? 3 : (cin == 64 || cin == 128) ? 4 : -1;
+    if (cout % 128 == 0 && cin % 64 == 0) return 5;
     return -1;
 }
 
@@ -128,7 +126,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (d.mode < 0 || d.mode > 3 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
     p.n_ntiles = (d.cout + c.nt - 1) / c.nt;
     if (!d.out_f32 && d.cout % c.nt) { set_error("conv3x3: Cout %d not a multiple of NT=%d", d.cout, c.nt); return RRIN_ERR_BAD_SHAPE; }
-    if (p.n_ntiles * c.nt > ConvCfg<16, 32, 4, 3, 9>::BIAS_MAX) { set_error("conv3x3: Cout %d too large", d.cout); return RRIN_ERR_BAD_SHAPE; }
+    if (p.n_ntiles * c.nt > ConvCfg<16, 32, 4, 4, 9>::BIAS_MAX) { set_error("conv3x3: Cout %d too large", d.cout); return RRIN_ERR_BAD_SHAPE; }
     p.cout = d.out_f32 ? 4 : d.cout;
     p.wpack = reinterpret_cast<const __nv_bfloat16*>(d.wpack);
     p.bias = d.bias;

@@ -16,11 +16,11 @@
 // 16 bytes per core matrix; LBO = plane stride between 8-channel groups, SBO = one halo row).
 // That cuts L2->SMEM operand traffic ~7x versus per-tap im2col tiles.
 //
-// Warp roles (320 threads, 1 CTA / SM, persistent over a static tile schedule):
+// Warp roles (448 threads, 1 CTA / SM, persistent over a static tile schedule):
 //   warps 0-3  epilogue : TMEM -> regs (tcgen05.ld) -> +bias, LeakyReLU -> bf16 NHWC stores
 //   warp  4    MMA      : one lane issues tcgen05.mma / tcgen05.commit
 //   warp  5    weights  : one lane streams packed weight blocks with cp.async.bulk (TMA unit)
-//   warps 6-9  producer : build halo tiles (cp.async zero-fill for plain/cat; 2x2 mean or
+//   warps 6-13 producer : build halo tiles (cp.async zero-fill for plain/cat; 2x2 mean or
 //                         bilinear x2 computed in registers for pool/up)
 // Pipelines: A ring (SA stages), B ring (SB weight blocks; fully resident when the layer's
 // 9*Cin/KC blocks fit), double-buffered TMEM accumulators (MMA <-> epilogue).
@@ -50,7 +50,7 @@ struct ConvParams {
 };
 
 constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 4;
+constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kConvThreads = (kEpiWarps + 2 + kProdWarps) * 32;
 constexpr int kTileH = 16;
@@ -168,7 +168,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
         const int c8 = ptid % C::CH8;                      // this thread's 8-channel group
         const int px0 = ptid / C::CH8;
         constexpr int PXSTEP = kProdThreads / C::CH8;
-        constexpr int LAG = (SA >= 3) ? 2 : 1;             // cp.async groups kept in flight
+        // cp.async groups kept in flight.  SA >= LAG + 2 keeps the a_empty wait of a *later* stage off
+        // the critical path of signalling an earlier one (otherwise MMA and producer ping-pong).
+        constexpr int LAG = (SA >= 4) ? 2 : (SA >= 3 ? 1 : 0);
+        constexpr int U = 4;                               // transform modes: pixels batched per thread (16 LDG.128 in flight)
         const bool async_mode = (p.mode == SRC_PLAIN || p.mode == SRC_CAT);
         int it = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -198,60 +201,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
                         fence_proxy_async_smem();
                         mbar_arrive(a_full((it - LAG) % SA));
                     }
-                } else if (p.mode == SRC_POOL) {
-                    const int H2 = 2 * p.H, W2 = 2 * p.W, cs = p.c0;
-                    const __nv_bfloat16* src = p.src0 + ch * KC + c8 * 8;
-                    const size_t rowb = (size_t)W2 * cs;
-                    for (int px = px0; px < C::HALO_PX; px += 2 * PXSTEP) {
-                        uint4 v[2][4]; bool okk[2]; int pxs[2];
+                } else {
+                    // pool: 2x2 mean of the finer tensor; up: bilinear x2 of the coarser tensor.
+                    const bool pool = (p.mode == SRC_POOL);
+                    const int cs = p.c0;
+                    const int sh = pool ? 2 * p.H : p.H >> 1, sw = pool ? 2 * p.W : p.W >> 1;   // source size
+                    const __nv_bfloat16* src = p.src0 + (size_t)n * sh * sw * cs + ch * KC + c8 * 8;
+                    for (int px = px0; px < C::HALO_PX; px += U * PXSTEP) {
+                        uint4 v[U][4]; bool okk[U]; float wx[U], wy[U];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int q = px + u * PXSTEP; pxs[u] = q;
+                        for (int u = 0; u < U; ++u) {
+                            const int q = px + u * PXSTEP;
                             const int hy = q / C::PW, hx = q - hy * C::PW;
                             const int gy = y0 + hy, gx = x0 + hx;
                             okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                            int iy0 = 0, iy1 = 0, ix0 = 0, ix1 = 0;
+                            wx[u] = wy[u] = 0.f;
                             if (okk[u]) {
-                                const __nv_bfloat16* s = src + ((size_t)(n * H2 + 2 * gy) * W2 + 2 * gx) * cs;
-                                v[u][0] = ldg_nc16(s); v[u][1] = ldg_nc16(s + cs);
-                                v[u][2] = ldg_nc16(s + rowb); v[u][3] = ldg_nc16(s + rowb + cs);
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            if (pxs[u] < C::HALO_PX) {
-                                uint4 o = okk[u] ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3]) : make_uint4(0, 0, 0, 0);
-                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + pxs[u] * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-                            }
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    mbar_arrive(a_full(stage));
-                } else {  // SRC_UP
-                    const int h2 = p.H >> 1, w2 = p.W >> 1, cs = p.c0;
-                    const __nv_bfloat16* src = p.src0 + ch * KC + c8 * 8;
-                    for (int px = px0; px < C::HALO_PX; px += 2 * PXSTEP) {
-                        uint4 v[2][4]; bool okk[2]; int pxs[2]; float wx[2], wy[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int q = px + u * PXSTEP; pxs[u] = q;
-                            const int hy = q / C::PW, hx = q - hy * C::PW;
-                            const int gy = y0 + hy, gx = x0 + hx;
-                            okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
-                            if (okk[u]) {
-                                int iy0, iy1, ix0, ix1;
-                                up2_taps(gy, h2, iy0, iy1, wy[u]);
-                                up2_taps(gx, w2, ix0, ix1, wx[u]);
-                                const __nv_bfloat16* r0 = src + (size_t)(n * h2 + iy0) * w2 * cs;
-                                const __nv_bfloat16* r1 = src + (size_t)(n * h2 + iy1) * w2 * cs;
+                                if (pool) { iy0 = 2 * gy; iy1 = iy0 + 1; ix0 = 2 * gx; ix1 = ix0 + 1; }
+                                else { up2_taps(gy, sh, iy0, iy1, wy[u]); up2_taps(gx, sw, ix0, ix1, wx[u]); }
+                                const __nv_bfloat16* r0 = src + (size_t)iy0 * sw * cs;
+                                const __nv_bfloat16* r1 = src + (size_t)iy1 * sw * cs;
                                 v[u][0] = ldg_nc16(r0 + (size_t)ix0 * cs); v[u][1] = ldg_nc16(r0 + (size_t)ix1 * cs);
                                 v[u][2] = ldg_nc16(r1 + (size_t)ix0 * cs); v[u][3] = ldg_nc16(r1 + (size_t)ix1 * cs);
                             }
                         }
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            if (pxs[u] < C::HALO_PX) {
-                                uint4 o = okk[u] ? bilerp_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], wx[u], wy[u]) : make_uint4(0, 0, 0, 0);
-                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + pxs[u] * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                        for (int u = 0; u < U; ++u) {
+                            const int q = px + u * PXSTEP;
+                            if (q < C::HALO_PX) {
+                                uint4 o = make_uint4(0, 0, 0, 0);
+                                if (okk[u]) o = pool ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3])
+                                                     : bilerp_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], wx[u], wy[u]);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + q * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                             }
                         }
                     }
@@ -289,42 +271,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
         }
     } else if (warp == 4) {
         // =========================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
-            int it = 0, cnt = 0, tcount = 0;
-            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-                const int buf = tcount & 1;
-                mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + buf * (MSUB * NT);
-                for (int ch = 0; ch < nch; ++ch, ++it) {
-                    const int stage = it % SA;
-                    mbar_wait(a_full(stage), (it / SA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_stage = s_a + stage * C::A_STAGE;
+        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform
+        // registers); one elected lane issues the tcgen05 instructions.
+        constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+        const uint64_t a_desc0 = make_smem_desc(0, C::PS, C::PW * 16);
+        const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
+        int it = 0, cnt = 0, tcount = 0;
+        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+            const int buf = tcount & 1;
+            mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
+            const uint32_t d0 = tmem_base + buf * (MSUB * NT);
+            for (int ch = 0; ch < nch; ++ch, ++it) {
+                const int stage = it % SA;
+                mbar_wait(a_full(stage), (it / SA) & 1);
+                const uint32_t a_stage = s_a + stage * C::A_STAGE;
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap, ++cnt) {
-                        int slot;
-                        if (p.b_resident) { slot = ch * 9 + tap; mbar_wait(b_full(slot), 0); }
-                        else { slot = cnt % SB; mbar_wait(b_full(slot), (cnt / SB) & 1); }
-                        tc_fence_after();
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint32_t a_tap = a_stage + (dy * C::PW + dx) * 16;
-                        const uint32_t b_blk = s_b + slot * C::B_BLOCK;
+                for (int tap = 0; tap < 9; ++tap, ++cnt) {
+                    int slot;
+                    if (p.b_resident) { slot = ch * 9 + tap; if (tcount == 0) mbar_wait(b_full(slot), 0); }
+                    else { slot = cnt % SB; mbar_wait(b_full(slot), (cnt / SB) & 1); }
+                    tc_fence_after();
+                    const int dy = tap / 3, dx = tap - dy * 3;
+                    const uint64_t a_tap = a_desc0 + ((a_stage + (dy * C::PW + dx) * 16) >> 4);
+                    const uint64_t b_blk = b_desc0 + ((s_b + slot * C::B_BLOCK) >> 4);
+                    if (elect_one()) {
 #pragma unroll
                         for (int j = 0; j < MSUB; ++j) {
 #pragma unroll
-                            for (int s = 0; s < KC / 16; ++s) {
-                                const uint64_t ad = make_smem_desc(a_tap + j * 128 + 2 * s * C::PS, C::PS, C::PW * 16);
-                                const uint64_t bd = make_smem_desc(b_blk + 2 * s * (NT * 16), NT * 16, 128);
-                                umma_bf16(d0 + j * NT, ad, bd, idesc, (ch | tap | s) != 0);
-                            }
+                            for (int s = 0; s < KC / 16; ++s)
+                                umma_bf16(d0 + j * NT, a_tap + ((j * 128 + 2 * s * C::PS) >> 4), b_blk + ((2 * s * (NT * 16)) >> 4),
+                                          idesc, (ch | tap | s) != 0);
                         }
                         if (!p.b_resident) umma_commit(b_empty(slot));
+                        if (tap == 8) {
+                            umma_commit(a_empty(stage));
+                            if (ch == nch - 1) umma_commit(acc_full(buf));
+                        }
                     }
-                    umma_commit(a_empty(stage));
+                    __syncwarp();
                 }
-                umma_commit(acc_full(buf));
             }
         }
     } else {

@@ -1,0 +1,23 @@
+"""Minimal program for ncu: W warm-up forwards + 1 forward of the 1080p step (no timing, no CPU work).
+Usage: python tools/profile_step.py [H W [warmups]]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from oracle import rrin_oracle as O
+from rrin_b200 import Net
+
+h = int(sys.argv[1]) if len(sys.argv) > 1 else 1088
+w = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+net = Net()
+net.load_state_dict(O.seeded_state_dict(), strict=True)
+net = net.cuda().eval()
+a, b = O.seeded_frames(1, h, w, seed=2, smooth=True)
+a, b = a.cuda(), b.cuda()
+for _ in range(warm + 1):
+    y = net(a, b, t=0.5)
+torch.cuda.synchronize()
+print("ok", float(y.mean()))
