@@ -11,7 +11,7 @@
  *   - functions return 0 on success, non-zero otherwise (rrin_last_error() gives the text);
  *     they never throw, never allocate device memory, never synchronise the device;
  *   - frames / results: fp32 NCHW [N,3,H,W] in [0,1]   (dataloader.py:116-118, convert.py:133)
- *   - U-Net activations: bf16 NHWC; U-Net outputs (flow, residues, mask logits): fp32 NHWC4;
+ *   - U-Net activations: bf16 NHWC (level 0: space-to-depth, see K1); U-Net outputs: fp32 [N,H/2,W/2,4,4];
  *   - H and W must be multiples of 16 (four 2x2 pools in the Flow U-Net, unet.py:46).
  */
 #ifndef RRIN_B200_H_
@@ -76,24 +76,33 @@ RRIN_API int rrin_engine_launch_info(const rrin_engine* e, int i, char* name, in
 RRIN_API int rrin_engine_forward_profiled(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
                                  const float* coef, float* out, void* stream, float* ms_host);
 /* debug/test taps: copy out intermediate fp32 NHWC4 tensors of the last forward.
- * which: 0 flow (n_pairs), 1 blend output (n_samples).  dst is a device pointer of n*H*W*4 floats. */
+ * which: 0 flow (n_pairs), 1 blend output (n_samples); layout fp32 [n,H/2,W/2,4 phases,4].  dst: n*H*W*4 floats. */
 RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, float* dst, void* stream);
 
 /* ---- unit-level entry points (used by tests and micro-benchmarks) -------------------------
  * K1: conv3x3(pad 1) + bias + optional LeakyReLU(0.1) on tcgen05 tensor cores.
  * Replaces nn.Conv2d (unet.py:29,38,59,62,78) + LeakyReLU (unet.py:47,60,63), with the input
- * transform folded into the operand loads: src_mode 0 plain, 1 cat(src0,src1) (unet.py:93),
- * 2 avg_pool2d(src0,2) (unet.py:46), 3 bilinear x2 upsample of src0 (unet.py:77).
- * src*: bf16 NHWC; N,H,W: output size; wpack/bias_pack from rrin_pack_conv_raw;
- * out: bf16 NHWC [N,H,W,cout], or fp32 NHWC4 when out_f32 (cout <= 4 of 16 padded). */
-RRIN_API int rrin_conv_select_config(int cin, int cout, int out_f32);           /* -> config id or -1 */
-RRIN_API size_t rrin_conv_packed_weight_bytes(int cout, int cin_pad, int cfg);
-RRIN_API int rrin_conv_packed_bias_count(int cout, int cfg);
-RRIN_API int rrin_pack_conv_raw(const float* w, const float* b, int cout, int cin, int cin_pad, int cfg,
+ * transform folded into the operand loads or the weights.
+ *   src_mode : 0 plain [N,H,W,c0] | 1 cat(src0,src1) (unet.py:93) | 2 avg_pool2d of [N,2H,2W,c0] (unet.py:46)
+ *              | 3 bilinear x2 of [N,H/2,W/2,c0] (unet.py:77) | 4 mean over the 4 phases of a space-to-depth
+ *              source [N,H,W,c0] | 5 space-to-depth grid: phase (a,b) = bilinear x2 of [N,H,W,c0] at (2y+a,2x+b)
+ *   sched    : 0 nine 3x3 taps | 1 space-to-depth (16 (block shift, phase) entries; level-0 tensors are stored
+ *              [N,H/2,W/2,4 phases,C] and the conv runs on the half-resolution grid with 4*Cout columns)
+ *   epi      : 0 bf16 NHWC [N,H,W,cout_stride] | 1 fp32 [N,H,W,16] | 2 folded-upsample scatter into bf16
+ *              [N,2H,2W,cout_stride]
+ *   pack kind: 0 plain | 1 space-to-depth | 2 bilinear-x2-folded weights (4*cout columns, pad_clamp=1 input)
+ *   cfg      : tile configuration 0..rrin-internal (rrin_conv_config_info gives KCS, KB, NT, MSUB). */
+RRIN_API int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
+RRIN_API size_t rrin_conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);
+RRIN_API int rrin_conv_packed_bias_count(int cfg, int n_cols);
+RRIN_API int rrin_pack_conv_raw(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
                        void* wpack, float* bias_pack, void* stream);
-RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int N, int H, int W, int cout,
-                 const void* wpack, const float* bias_pack, void* out, int out_f32, int act, int cfg, void* stream);
+RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
+                 int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
+                 int act, int ring_only, int cfg, void* stream);
 
+/* Glue kernels.  Frames are fp32 NCHW; tensors exchanged with the U-Nets are space-to-depth on the half-res
+ * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8]. */
 /* K6: torch.cat((x0,x1),1) (model.py:33) -> packed 16-channel bf16 NHWC head input. */
 RRIN_API int rrin_pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, void* stream);
 /* K2: flow t-scaling (model.py:37-39) + cat((F_t0,F_t1,x),1) (model.py:41) -> refine head input. */

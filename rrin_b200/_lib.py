@@ -30,11 +30,11 @@ _SIGNATURES = {
     "rrin_engine_tap": (ci, [vp, vp, ci, vp, vp]),
     "rrin_engine_launch_info": (ci, [vp, ci, C.c_char_p, ci, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rrin_engine_forward_profiled": (ci, [vp] * 8 + [C.POINTER(C.c_float)]),
-    "rrin_conv_select_config": (ci, [ci, ci, ci]),
-    "rrin_conv_packed_weight_bytes": (cs, [ci, ci, ci]),
+    "rrin_conv_config_info": (ci, [ci] + [C.POINTER(ci)] * 4),
+    "rrin_conv_packed_weight_bytes": (cs, [ci, ci, ci, ci]),
     "rrin_conv_packed_bias_count": (ci, [ci, ci]),
-    "rrin_pack_conv_raw": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp]),
-    "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp]),
+    "rrin_pack_conv_raw": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
+    "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
     "rrin_pack_pair": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "rrin_flow_tscale_pack": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_warp_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),

@@ -1,106 +1,141 @@
-// Host side of K1: configuration table, weight repack (K7) and launcher for the tcgen05
-// implicit-GEMM 3x3 convolution (conv3x3.cuh).  C-ABI entry points are declared in
-// include/rrin_b200.h.
+// Host side of K1: configuration table, weight repack (K7: plain / space-to-depth / folded
+// upsample) and launcher for the tcgen05 implicit-GEMM 3x3 convolution (conv3x3.cuh).
 #include "conv3x3.cuh"
 #include "rrin_internal.h"
 
 namespace rrin {
 
 // ------------------------------------------------------------------ configuration table
-// id : <KC, NT, MSUB, SA, SB>      used for
-//  0 : <16, 32, 4, 4,  9>   head convs   Cin in {6,9,10,16} (stored as 16 ch) -> 32
-//  1 : <32, 32, 4, 4, 18>   level 0      32->32, up 64->32, cat(32+32)->32 (weights resident)
-//  2 : <32, 16, 4, 4,  9>   `last`       32 -> {2,3,4} (N padded to 16), fp32 NHWC4 output
-//  3 : <32, 64, 4, 4,  9>   level 1      pool(32) -> 64
-//  4 : <64, 64, 2, 3,  9>   level 1      64->64 (weights resident); up 128->64, cat(64+64)->64 (streamed)
-//  5 : <64,128, 2, 3,  4>   levels >= 2  Cout in {128,256,512} as n-tiles of 128
-#define RRIN_CONV_CONFIGS(X) \
-    X(0, 16, 32, 4, 4, 9)    \
-    X(1, 32, 32, 4, 4, 18)   \
-    X(2, 32, 16, 4, 4, 9)    \
-    X(3, 32, 64, 4, 4, 9)    \
-    X(4, 64, 64, 2, 3, 9)    \
-    X(5, 64, 128, 2, 3, 4)
+// id : <KCS, KB, NT, MSUB, SA, SB>    used for
+//  0 : < 64, 16, 128, 2, 3, 16>  level-0 head convs, space-to-depth (4 phases x 16 stored ch) -> 4x32
+//  1 : <128, 32, 128, 2, 2,  5>  level-0 32->32, cat(32+32)->32 and the exact-upsample ring, space-to-depth
+//  2 : <128, 32,  16, 2, 2, 16>  level-0 `last` 32 -> {2,3,4}, space-to-depth, fp32 output (4 phases x 4)
+//  3 : < 32, 32,  64, 4, 4,  9>  level-1 pool(32) -> 64 (reads the level-0 space-to-depth skip)
+//  4 : < 64, 64,  64, 2, 3,  9>  level-1 64->64 (weights resident), cat(64+64)->64, exact-upsample ring
+//  5 : < 64, 64, 128, 2, 3,  4>  levels >= 2 (Cout in {128,256,512} as n-tiles of 128) and every
+//                                folded-upsample conv (N = 4*Cout)
+#define RRIN_CONV_CONFIGS(X)   \
+    X(0, 64, 16, 128, 2, 3, 16) \
+    X(1, 128, 32, 128, 2, 2, 5) \
+    X(2, 128, 32, 16, 2, 2, 16) \
+    X(3, 32, 32, 64, 4, 4, 9)   \
+    X(4, 64, 64, 64, 2, 3, 9)   \
+    X(5, 64, 64, 128, 2, 3, 4)
 
-struct CfgInfo { int kc, nt, msub, sa, sb, smem; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw; };
 static const CfgInfo kCfg[] = {
-#define X(id, KC, NT, MSUB, SA, SB) {KC, NT, MSUB, SA, SB, ConvCfg<KC, NT, MSUB, SA, SB>::SMEM_BYTES},
+#define X(id, KCS, KB, NT, MSUB, SA, SB) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 constexpr int kNumCfg = sizeof(kCfg) / sizeof(kCfg[0]);
 
-int conv_select_config(int cin, int cout, int out_f32) {
-    if (out_f32) return (cin == 32 && cout <= 16) ? 2 : -1;
-    if (cin == 16) return cout == 32 ? 0 : -1;
-    if (cout == 32) return (cin == 32 || cin == 64) ? 1 : -1;
-    if (cout == 64) return cin == 32 ? 3 : (cin == 64 || cin == 128) ? 4 : -1;
-    if (cout % 128 == 0 && cin % 64 == 0) return 5;
-    return -1;
-}
-
-int conv_config_info(int cfg, int* kc, int* nt, int* msub) {
+int conv_num_configs() { return kNumCfg; }
+int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub) {
     if (cfg < 0 || cfg >= kNumCfg) return RRIN_ERR_BAD_ARG;
-    if (kc) *kc = kCfg[cfg].kc;
+    if (kcs) *kcs = kCfg[cfg].kcs;
+    if (kb) *kb = kCfg[cfg].kb;
     if (nt) *nt = kCfg[cfg].nt;
     if (msub) *msub = kCfg[cfg].msub;
     return RRIN_OK;
 }
 
-// ------------------------------------------------------------------ K7: weight repack
-// OIHW fp32 [cout][cin][3][3] -> bf16 [n_ntiles][cin_pad/KC][9][KC/8][NT][8], zero padded in
-// both channel dims; bias -> fp32 [n_ntiles*NT] zero padded.  Runs once per load_state_dict.
-__global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ b, int cout, int cin,
-                                    int cin_pad, int kc, int nt, int n_ntiles,
-                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
-    const int nch = cin_pad / kc;
-    const long total = (long)n_ntiles * nch * 9 * kc * nt;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        long r = i;
-        const int e = r % 8; r /= 8;
-        const int n = r % nt; r /= nt;
-        const int k8 = r % (kc / 8); r /= (kc / 8);
-        const int tap = r % 9; r /= 9;
-        const int ch = r % nch; r /= nch;
-        const int t = (int)r;
-        const int ci = ch * kc + k8 * 8 + e, co = t * nt + n;
-        float v = (ci < cin && co < cout) ? w[((long)co * cin + ci) * 9 + tap] : 0.f;
-        wp[i] = __float2bfloat16_rn(v);
-    }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ntiles * nt; i += gridDim.x * blockDim.x)
-        bp[i] = i < cout ? b[i] : 0.f;
+// Space-to-depth entry e -> block shift (u,v) in {-1,0,1} and input phase (r,c).  Along one axis the
+// hi-res taps {-1,0,1} of output phase a touch (block shift, input phase) in {(-1,1),(0,0),(0,1),(1,0)}.
+__host__ __device__ inline void s2d_entry(int e, int& u, int& r, int& v, int& c) {
+    const int us[4] = {-1, 0, 0, 1}, ps[4] = {1, 0, 1, 0};
+    u = us[e >> 2]; r = ps[e >> 2];
+    v = us[e & 3]; c = ps[e & 3];
 }
 
-int conv_pack_weights(const float* w, const float* b, int cout, int cin, int cin_pad, int cfg,
+// ------------------------------------------------------------------ K7: weight repack
+// -> bf16 [n_ntiles][n_stages][n_ent][KB/8][NT][8] (+ fp32 bias [n_ntiles*NT]); once per load_state_dict.
+__global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const float* __restrict__ b, int cout, int cin,
+                                    int kcs, int kb, int nt, int n_ntiles, int n_stages, int n_ent,
+                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
+    // bilinear x2 (align_corners=False) coefficient of coarse sample (i+u) in hi-res sample 2i+a+d:  al[a][d+1][u+1]
+    const float al[2][3][3] = {{{.75f, .25f, 0.f}, {.25f, .75f, 0.f}, {0.f, .75f, .25f}},
+                               {{.25f, .75f, 0.f}, {0.f, .75f, .25f}, {0.f, .25f, .75f}}};
+    const long total = (long)n_ntiles * n_stages * n_ent * kb * nt;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        long r = i;
+        const int e8 = r % 8; r /= 8;
+        const int n = r % nt; r /= nt;
+        const int k8 = r % (kb / 8); r /= (kb / 8);
+        const int ent = r % n_ent; r /= n_ent;
+        const int st = r % n_stages; r /= n_stages;
+        const int t = (int)r;
+        const int k = k8 * 8 + e8, col = t * nt + n;
+        float v = 0.f;
+        if (kind == PACK_NORMAL) {
+            const int ci = st * kcs + k;
+            if (ci < cin && col < cout) v = w[((long)col * cin + ci) * 9 + ent];
+        } else if (kind == PACK_S2D) {
+            const int cpp = nt / 4, ph = n / cpp, co = n - ph * cpp, ci = st * kb + k;
+            int u, rr, vv, cc;
+            s2d_entry(ent, u, rr, vv, cc);
+            const int dy = 2 * u + rr - (ph >> 1), dx = 2 * vv + cc - (ph & 1);
+            if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1 && co < cout && ci < cin)
+                v = w[((long)co * cin + ci) * 9 + (dy + 1) * 3 + (dx + 1)];
+        } else {  // PACK_FOLD
+            const int ph = col / cout, co = col - ph * cout, ci = st * kcs + k;
+            if (ph < 4 && ci < cin) {
+                const int u = ent / 3, vv = ent % 3, a = ph >> 1, bb = ph & 1;
+                const float* wk = w + ((long)co * cin + ci) * 9;
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) v += al[a][dy][u] * al[bb][dx][vv] * wk[dy * 3 + dx];
+            }
+        }
+        wp[i] = __float2bfloat16_rn(v);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ntiles * nt; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (kind == PACK_NORMAL) { if (i < cout) v = b[i]; }
+        else if (kind == PACK_S2D) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
+        else { if (i < 4 * cout) v = b[i % cout]; }
+        bp[i] = v;
+    }
+}
+
+static int n_ent_of(int sched) { return sched == SCHED_S2D16 ? 16 : 9; }
+
+size_t conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched) {
+    const CfgInfo& c = kCfg[cfg];
+    const int n_ntiles = (n_cols + c.nt - 1) / c.nt;
+    return (size_t)n_ntiles * n_stages * n_ent_of(sched) * c.kb * c.nt * 2;
+}
+int conv_packed_bias_count(int cfg, int n_cols) {
+    const CfgInfo& c = kCfg[cfg];
+    return ((n_cols + c.nt - 1) / c.nt) * c.nt;
+}
+
+int conv_pack_weights(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
                       void* wpack, float* bias_pack, cudaStream_t stream) {
     if (cfg < 0 || cfg >= kNumCfg) { set_error("conv_pack_weights: bad config %d", cfg); return RRIN_ERR_BAD_ARG; }
     const CfgInfo& c = kCfg[cfg];
-    if (cin_pad % c.kc != 0 || cin > cin_pad) { set_error("conv_pack_weights: cin_pad %d not a multiple of KC %d", cin_pad, c.kc); return RRIN_ERR_BAD_SHAPE; }
-    const int n_ntiles = (cout + c.nt - 1) / c.nt;
-    pack_weights_kernel<<<256, 256, 0, stream>>>(w, b, cout, cin, cin_pad, c.kc, c.nt, n_ntiles,
+    int n_cols, n_ent;
+    if (kind == PACK_NORMAL) { n_cols = cout; n_ent = 9; if (c.kb != c.kcs) { set_error("pack: config %d is space-to-depth only", cfg); return RRIN_ERR_BAD_ARG; } }
+    else if (kind == PACK_S2D) { n_cols = c.nt; n_ent = 16; if (cout > c.nt / 4) { set_error("pack(s2d): cout %d > %d", cout, c.nt / 4); return RRIN_ERR_BAD_SHAPE; } }
+    else if (kind == PACK_FOLD) { n_cols = 4 * cout; n_ent = 9; if (c.kb != c.kcs || (4 * cout) % c.nt) { set_error("pack(fold): bad shape"); return RRIN_ERR_BAD_SHAPE; } }
+    else { set_error("conv_pack_weights: bad kind %d", kind); return RRIN_ERR_BAD_ARG; }
+    const int kspan = (kind == PACK_S2D) ? c.kb : c.kcs;
+    if (n_stages < 1 || cin > n_stages * kspan) { set_error("pack: cin %d does not fit %d stage(s) of %d", cin, n_stages, kspan); return RRIN_ERR_BAD_SHAPE; }
+    const int n_ntiles = (n_cols + c.nt - 1) / c.nt;
+    pack_weights_kernel<<<256, 256, 0, stream>>>(kind, w, b, cout, cin, c.kcs, c.kb, c.nt, n_ntiles, n_stages, n_ent,
                                                  reinterpret_cast<__nv_bfloat16*>(wpack), bias_pack);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
-}
-
-size_t conv_packed_weight_bytes(int cout, int cin_pad, int cfg) {
-    const CfgInfo& c = kCfg[cfg];
-    const int n_ntiles = (cout + c.nt - 1) / c.nt;
-    return (size_t)n_ntiles * c.nt * cin_pad * 9 * 2;
-}
-int conv_packed_bias_count(int cout, int cfg) {
-    const CfgInfo& c = kCfg[cfg];
-    return ((cout + c.nt - 1) / c.nt) * c.nt;
 }
 
 // ------------------------------------------------------------------ launcher
 static int g_num_sms = 0;
 static bool g_attr_set[kNumCfg] = {};
 
-template <int KC, int NT, int MSUB, int SA, int SB>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
 static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream) {
-    using C = ConvCfg<KC, NT, MSUB, SA, SB>;
-    auto kern = conv3x3_umma_kernel<KC, NT, MSUB, SA, SB>;
+    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB>;
+    auto kern = conv3x3_umma_kernel<KCS, KB, NT, MSUB, SA, SB>;
     if (!g_attr_set[id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
@@ -114,29 +149,55 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     const int cfg = d.cfg;
     if (cfg < 0 || cfg >= kNumCfg) { set_error("conv3x3: bad config id %d", cfg); return RRIN_ERR_BAD_ARG; }
     const CfgInfo& c = kCfg[cfg];
+    if (d.N <= 0 || d.H <= 0 || d.W <= 0) { set_error("conv3x3: empty shape %dx%dx%d", d.N, d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
+    if (d.mode < 0 || d.mode > SRC_UP_S2D || !d.src0 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
+    if (d.sched == SCHED_TAPS9 && c.kb != c.kcs) { set_error("conv3x3: config %d needs the space-to-depth schedule", cfg); return RRIN_ERR_BAD_ARG; }
     ConvParams p{};
     p.src0 = reinterpret_cast<const __nv_bfloat16*>(d.src0);
     p.src1 = reinterpret_cast<const __nv_bfloat16*>(d.src1);
-    p.c0 = d.c0; p.c1 = d.c1; p.mode = d.mode;
+    p.c0 = d.c0; p.c1 = d.c1; p.mode = d.mode; p.pad_clamp = d.pad_clamp;
     p.N = d.N; p.H = d.H; p.W = d.W;
-    p.cin = d.c0 + (d.mode == SRC_CAT ? d.c1 : 0);
-    if (d.N <= 0 || d.H <= 0 || d.W <= 0) { set_error("conv3x3: empty shape %dx%dx%d", d.N, d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
-    if (p.cin % c.kc || d.c0 % c.kc) { set_error("conv3x3: Cin %d (+%d) not a multiple of KC=%d", d.c0, d.c1, c.kc); return RRIN_ERR_BAD_SHAPE; }
+    // stages per tile
+    int span = 0;
+    switch (d.mode) {
+        case SRC_PLAIN: case SRC_POOL: case SRC_UP: span = d.c0; break;
+        case SRC_CAT: span = d.c0 + d.c1; if (d.c0 % c.kcs) span = -1; break;
+        case SRC_POOL_S2D: span = d.c0 / 4; break;
+        case SRC_UP_S2D: span = d.c0 * 4; break;     // each source channel feeds 4 phases
+    }
+    if (span <= 0 || span % c.kcs) { set_error("conv3x3: %d input channels (mode %d) not a multiple of the stage width %d", span, d.mode, c.kcs); return RRIN_ERR_BAD_SHAPE; }
+    p.n_stages = span / c.kcs;
     if (d.mode == SRC_UP && ((d.H | d.W) & 1)) { set_error("conv3x3(up): odd output size %dx%d", d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
-    if (d.mode < 0 || d.mode > 3 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
-    p.n_ntiles = (d.cout + c.nt - 1) / c.nt;
-    if (!d.out_f32 && d.cout % c.nt) { set_error("conv3x3: Cout %d not a multiple of NT=%d", d.cout, c.nt); return RRIN_ERR_BAD_SHAPE; }
-    if (p.n_ntiles * c.nt > ConvCfg<16, 32, 4, 4, 9>::BIAS_MAX) { set_error("conv3x3: Cout %d too large", d.cout); return RRIN_ERR_BAD_SHAPE; }
-    p.cout = d.out_f32 ? 4 : d.cout;
+    if (d.mode == SRC_UP_S2D && d.sched != SCHED_S2D16) { set_error("conv3x3: SRC_UP_S2D needs the space-to-depth schedule"); return RRIN_ERR_BAD_ARG; }
+    // entry table (descriptor start offsets in 16-byte units)
+    p.n_ent = n_ent_of(d.sched);
+    if (d.sched == SCHED_TAPS9) {
+        for (int t = 0; t < 9; ++t) p.ent_off[t] = (t / 3) * c.pw + (t % 3);
+    } else {
+        for (int e = 0; e < 16; ++e) {
+            int u, r, v, cc;
+            s2d_entry(e, u, r, v, cc);
+            p.ent_off[e] = (u + 1) * c.pw + (v + 1) + (r * 2 + cc) * (c.kb / 8) * (c.ps / 16);
+        }
+    }
+    if (d.n_cols <= 0 || d.n_cols % c.nt) { set_error("conv3x3: %d GEMM columns not a multiple of NT=%d", d.n_cols, c.nt); return RRIN_ERR_BAD_SHAPE; }
+    p.n_ntiles = d.n_cols / c.nt;
+    if (d.n_cols > ConvCfg<64, 64, 128, 2, 3, 4>::BIAS_MAX) { set_error("conv3x3: too many columns %d", d.n_cols); return RRIN_ERR_BAD_SHAPE; }
     p.wpack = reinterpret_cast<const __nv_bfloat16*>(d.wpack);
     p.bias = d.bias;
-    p.out = d.out; p.out_f32 = d.out_f32; p.act = d.act;
+    p.out = d.out; p.epi = d.epi; p.cout_stride = d.cout_stride; p.act = d.act;
+    if (d.epi == EPI_F32X16 && c.nt != 16) { set_error("conv3x3: fp32 epilogue needs NT=16"); return RRIN_ERR_BAD_ARG; }
+    if (d.epi == EPI_SCATTER && (d.cout_stride % 32 || d.n_cols != 4 * d.cout_stride)) { set_error("conv3x3: bad scatter epilogue shape"); return RRIN_ERR_BAD_SHAPE; }
+    if (d.epi == EPI_BF16 && d.cout_stride < d.n_cols) { set_error("conv3x3: cout_stride %d < columns %d", d.cout_stride, d.n_cols); return RRIN_ERR_BAD_SHAPE; }
     p.tiles_x = (d.W + 8 * c.msub - 1) / (8 * c.msub);
     p.tiles_y = (d.H + kTileH - 1) / kTileH;
-    const long work = (long)p.n_ntiles * d.N * p.tiles_x * p.tiles_y;
+    p.ring_only = d.ring_only && p.tiles_x > 2 && p.tiles_y > 2;
+    if (d.ring_only && !p.ring_only) { set_error("conv3x3: ring_only needs more than 2x2 tiles (the caller should run the full exact path)"); return RRIN_ERR_BAD_SHAPE; }
+    p.tiles_per_img = p.ring_only ? 2 * p.tiles_x + 2 * (p.tiles_y - 2) : p.tiles_x * p.tiles_y;
+    const long work = (long)p.n_ntiles * d.N * p.tiles_per_img;
     if (work > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
     p.total_work = (int)work;
-    p.b_resident = (p.n_ntiles == 1 && 9 * (p.cin / c.kc) <= c.sb) ? 1 : 0;
+    p.b_resident = (p.n_ntiles == 1 && p.n_stages * p.n_ent <= c.sb) ? 1 : 0;
     if (g_num_sms == 0) {
         int dev = 0;
         RRIN_CUDA_CHECK(cudaGetDevice(&dev));
@@ -144,7 +205,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     }
     const int grid = p.total_work < g_num_sms ? p.total_work : g_num_sms;
     switch (cfg) {
-#define X(id, KC, NT, MSUB, SA, SB) case id: return launch_cfg<KC, NT, MSUB, SA, SB>(id, p, grid, stream);
+#define X(id, KCS, KB, NT, MSUB, SA, SB) case id: return launch_cfg<KCS, KB, NT, MSUB, SA, SB>(id, p, grid, stream);
         RRIN_CONV_CONFIGS(X)
 #undef X
     }

@@ -3,50 +3,68 @@
 //
 // Replaces, for one conv of the reference U-Net, the torch ops of unet.py:
 //   nn.Conv2d(k=3,padding=1) (:29,38,59,62,78) + LeakyReLU(0.1) (:47,60,63), and -- folded into
-//   the operand loads so they are never materialised -- F.avg_pool2d(x,2) (:46),
+//   the operand loads / weights so they are never materialised -- F.avg_pool2d(x,2) (:46),
 //   nn.Upsample(bilinear, x2) (:77) and torch.cat((up, bridge), 1) (:93).
 //
-// GEMM view:  D[pixel, cout] = sum_{tap, cin} A_tap[pixel, cin] * W[tap][cout, cin]
-//   M = 128 pixels = a 16(rows) x 8(cols) sub-tile of the image, MSUB sub-tiles side by side
-//   N = NT output channels (one n-tile), K = 9 taps x Cin, consumed KC channels per stage.
+// GEMM view:  D[pixel, n] = sum_{entry, k} A_entry[pixel, k] * Wpack[entry][n, k]
+//   M = 128 pixels = a 16(rows) x 8(cols) sub-tile of the conv grid, MSUB sub-tiles side by side
+//   N = NT output columns (one n-tile); K is consumed in "entries" of KB channels.
 //
-// Operand A is a *halo tile* ((16+2) x (8*MSUB+2) pixels x KC channels) staged once per
-// K-chunk and reused by all 9 taps: the tap (dy,dx) is just a different start address of
-// the UMMA shared-memory descriptor (K-major, SWIZZLE_NONE canonical layout: 8 pixels x
-// 16 bytes per core matrix; LBO = plane stride between 8-channel groups, SBO = one halo row).
-// That cuts L2->SMEM operand traffic ~7x versus per-tap im2col tiles.
+// Operand A is a *halo tile* ((16+2) x (8*MSUB+2) pixels x KCS channels) staged once per stage
+// and reused by every entry of the stage: an entry is just a different start address of the UMMA
+// shared-memory descriptor (K-major, SWIZZLE_NONE canonical layout: 8 pixels x 16 bytes per core
+// matrix; LBO = plane stride between 8-channel groups, SBO = one halo row).
+//
+// Two K schedules share the kernel (the host passes the entry table):
+//   * TAPS9 : 9 entries per stage = the 3x3 taps (dy*PW+dx pixel shift), KB == KCS.
+//   * S2D16 : level-0 tensors are stored space-to-depth ([H/2][W/2][2x2 phase][C], i.e. NHWC at
+//             half resolution with 4C channels); the conv runs on the half-res grid with
+//             N = 4 phases x Cout and 16 entries per stage = (block shift, input phase) pairs,
+//             KB == C.  This lifts N from 32 to 128: a 128xNx16 MMA costs ~max(N/2, 50) cycles
+//             (the A operand is re-read from SMEM for every MMA), so N=32 caps at 32% of peak.
+//   The bilinear x2 upsample in front of `up.1` is folded into the weights (4 output phases,
+//   N = 4*Cout, input = the coarse tensor with replicate padding); only the outermost ring of
+//   tiles is recomputed with the exact transform path (SRC_UP / SRC_UP_S2D), because there the
+//   conv's zero padding and the fold's implicit replicate padding differ.
 //
 // Warp roles (448 threads, 1 CTA / SM, persistent over a static tile schedule):
-//   warps 0-3  epilogue : TMEM -> regs (tcgen05.ld) -> +bias, LeakyReLU -> bf16 NHWC stores
-//   warp  4    MMA      : one lane issues tcgen05.mma / tcgen05.commit
+//   warps 0-3  epilogue : TMEM -> regs (tcgen05.ld) -> +bias, LeakyReLU -> stores
+//   warp  4    MMA      : warp-uniform loop, one elected lane issues tcgen05.mma / commit
 //   warp  5    weights  : one lane streams packed weight blocks with cp.async.bulk (TMA unit)
-//   warps 6-13 producer : build halo tiles (cp.async zero-fill for plain/cat; 2x2 mean or
+//   warps 6-13 producer : build halo tiles (cp.async zero-fill/clamp for plain/cat; 2x2 mean or
 //                         bilinear x2 computed in registers for pool/up)
 // Pipelines: A ring (SA stages), B ring (SB weight blocks; fully resident when the layer's
-// 9*Cin/KC blocks fit), double-buffered TMEM accumulators (MMA <-> epilogue).
+// blocks fit), double-buffered TMEM accumulators (MMA <-> epilogue).
 #pragma once
 #include "common.cuh"
 #include "rrin_internal.h"
 
 namespace rrin {
 
+constexpr int kMaxEntries = 16;
+
 struct ConvParams {
-    const __nv_bfloat16* src0;   // NHWC bf16; plain/cat: [N,H,W,c0]; pool: [N,2H,2W,c0]; up: [N,H/2,W/2,c0]
-    const __nv_bfloat16* src1;   // cat only: [N,H,W,c1] (the skip), channels follow src0's
-    int c0, c1;
+    const __nv_bfloat16* src0;   // bf16 NHWC (see ConvSrcMode for the geometry of each mode)
+    const __nv_bfloat16* src1;   // cat only
+    int c0, c1;                  // channels per stored pixel of src0 / src1
     int mode;                    // ConvSrcMode
-    int N, H, W;                 // conv grid (== output) size
-    int cin;                     // c0 (+ c1 for cat); multiple of KC
-    int cout;                    // channels stored per pixel: bf16 -> n_ntiles*NT, f32 -> 4
-    const __nv_bfloat16* wpack;  // [n_ntiles][cin/KC][9][KC/8][NT][8] bf16 (pack_weights)
-    const float* bias;           // [n_ntiles*NT] fp32, zero padded
-    void* out;                   // bf16 NHWC [N,H,W,cout]  or  fp32 NHWC [N,H,W,4]
-    int out_f32;
+    int pad_clamp;               // plain/cat: replicate padding instead of zero fill (folded upsample)
+    int N, H, W;                 // conv grid (== accumulator pixel grid)
+    int n_stages;                // A stages per tile
+    int n_ent;                   // entries (weight blocks) per stage: 9 or 16
+    uint32_t ent_off[kMaxEntries];   // descriptor start offset of each entry, in 16-byte units
+    const __nv_bfloat16* wpack;  // [n_ntiles][n_stages][n_ent][KB/8][NT][8] bf16
+    const float* bias;           // [n_ntiles*NT] fp32
+    void* out;
+    int epi;                     // ConvEpilogue
+    int cout_stride;             // EPI_BF16: channels per output pixel; EPI_SCATTER: channels per hi-res pixel
     int act;                     // 1 -> LeakyReLU(0.1)
     int n_ntiles;
     int tiles_x, tiles_y;
-    int total_work;              // n_ntiles * N * tiles_y * tiles_x
-    int b_resident;              // all 9*cin/KC weight blocks stay in SMEM (requires n_ntiles == 1)
+    int ring_only;               // work items enumerate only the outermost ring of tiles
+    int tiles_per_img;           // tiles_x*tiles_y, or the ring count
+    int total_work;              // n_ntiles * N * tiles_per_img
+    int b_resident;              // all n_stages*n_ent weight blocks stay in SMEM (requires n_ntiles == 1)
 };
 
 constexpr int kEpiWarps = 4;
@@ -55,24 +73,24 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kConvThreads = (kEpiWarps + 2 + kProdWarps) * 32;
 constexpr int kTileH = 16;
 
-template <int KC, int NT, int MSUB, int SA, int SB>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
 struct ConvCfg {
-    static constexpr int CH8 = KC / 8;                 // 16-byte channel groups per stage
+    static constexpr int CH8 = KCS / 8;                // 16-byte channel groups (planes) per stage
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
     static constexpr int HALO_PX = (kTileH + 2) * PW;
     static constexpr int PLANE_PX = HALO_PX | 1;       // odd -> conflict-free plane-strided stores
     static constexpr int PS = PLANE_PX * 16;           // bytes per 8-channel plane
     static constexpr int A_STAGE = CH8 * PS;
-    static constexpr int B_BLOCK = NT * KC * 2;
-    static constexpr int TMEM_COLS = 2 * MSUB * NT;
+    static constexpr int B_BLOCK = NT * KB * 2;
+    static constexpr int TMEM_COLS = (2 * MSUB * NT) < 32 ? 32 : (2 * MSUB * NT);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int OFF_BIAS = OFF_B + SB * B_BLOCK;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
     static constexpr int NBAR = 2 * SA + 2 * SB + 4;
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
-    static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
-    static_assert(KC % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+    static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+    static_assert(KB % 16 == 0 && KCS % KB == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert(kProdThreads % CH8 == 0, "producer mapping");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -96,8 +114,7 @@ __device__ __forceinline__ uint4 avg4_bf16x8(uint4 a, uint4 b, uint4 c, uint4 d)
     return o;
 }
 // bilinear: wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11)   (ATen upsample_bilinear2d order)
-__device__ __forceinline__ uint4 bilerp_bf16x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11,
-                                               float wx1, float wy1) {
+__device__ __forceinline__ uint4 bilerp_bf16x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11, float wx1, float wy1) {
     const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
     uint4 o;
     const uint32_t* p00 = &v00.x; const uint32_t* p01 = &v01.x; const uint32_t* p10 = &v10.x; const uint32_t* p11 = &v11.x;
@@ -120,16 +137,40 @@ __device__ __forceinline__ void up2_taps(int o, int size_in, int& i0, int& i1, f
     i1 = i0 + (i0 < size_in - 1 ? 1 : 0);
 }
 
-template <int KC, int NT, int MSUB, int SA, int SB>
-__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const ConvParams p) {
-    using C = ConvCfg<KC, NT, MSUB, SA, SB>;
+// work item -> (n-tile, image, tile row, tile col); ring mode enumerates top row, bottom row,
+// then the left/right tiles of the rows in between.
+struct TileCoord { int nt, n, ty, tx; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int w) {
+    TileCoord t;
+    const int per_nt = p.tiles_per_img * p.N;
+    t.nt = w / per_nt;
+    int r = w - t.nt * per_nt;
+    t.n = r / p.tiles_per_img;
+    r -= t.n * p.tiles_per_img;
+    if (!p.ring_only) {
+        t.ty = r / p.tiles_x;
+        t.tx = r - t.ty * p.tiles_x;
+    } else if (r < p.tiles_x) {
+        t.ty = 0; t.tx = r;
+    } else if (r < 2 * p.tiles_x) {
+        t.ty = p.tiles_y - 1; t.tx = r - p.tiles_x;
+    } else {
+        r -= 2 * p.tiles_x;
+        t.ty = 1 + (r >> 1);
+        t.tx = (r & 1) ? p.tiles_x - 1 : 0;
+    }
+    return t;
+}
+
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
+__global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
+    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB>;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_a = s_base;
     const uint32_t s_b = s_base + C::OFF_B;
     float* bias_s = reinterpret_cast<float*>(smem + C::OFF_BIAS);
     const uint32_t s_bar = s_base + C::OFF_BAR;
-    // barrier addresses
     auto a_full = [&](int i) { return s_bar + 8u * i; };
     auto a_empty = [&](int i) { return s_bar + 8u * (SA + i); };
     auto b_full = [&](int i) { return s_bar + 8u * (2 * SA + i); };
@@ -140,10 +181,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nch = p.cin / KC;          // K chunks (A stages) per tile
-    const int nblk = nch * 9;            // weight blocks per tile
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int tiles_per_nt = tiles_per_img * p.N;
+    const int nst = p.n_stages;
+    const int nblk = nst * p.n_ent;      // weight blocks per tile
 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
@@ -165,33 +204,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
     if (warp >= 6) {
         // =========================================================== producers: halo tiles
         const int ptid = threadIdx.x - 6 * 32;
-        const int c8 = ptid % C::CH8;                      // this thread's 8-channel group
+        const int c8 = ptid % C::CH8;                      // this thread's 8-channel group (plane)
         const int px0 = ptid / C::CH8;
         constexpr int PXSTEP = kProdThreads / C::CH8;
         // cp.async groups kept in flight.  SA >= LAG + 2 keeps the a_empty wait of a *later* stage off
         // the critical path of signalling an earlier one (otherwise MMA and producer ping-pong).
         constexpr int LAG = (SA >= 4) ? 2 : (SA >= 3 ? 1 : 0);
-        constexpr int U = 4;                               // transform modes: pixels batched per thread (16 LDG.128 in flight)
+        constexpr int U = 2;                               // transform modes: pixels batched per thread (8 LDG.128 in flight)
         const bool async_mode = (p.mode == SRC_PLAIN || p.mode == SRC_CAT);
         int it = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-            int r = w % tiles_per_nt;
-            const int n = r / tiles_per_img; r -= n * tiles_per_img;
-            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int y0 = ty * kTileH - 1, x0 = tx * (8 * MSUB) - 1;   // halo origin
-            for (int ch = 0; ch < nch; ++ch, ++it) {
+            const TileCoord tc = decode_tile(p, w);
+            const int n = tc.n;
+            const int y0 = tc.ty * kTileH - 1, x0 = tc.tx * (8 * MSUB) - 1;   // halo origin
+            for (int st = 0; st < nst; ++st, ++it) {
                 const int stage = it % SA;
                 mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
                 const uint32_t dst0 = s_a + stage * C::A_STAGE + c8 * C::PS;
                 if (async_mode) {
                     const __nv_bfloat16* src; int cs, coff;
-                    if (p.mode == SRC_CAT && ch * KC >= p.c0) { src = p.src1; cs = p.c1; coff = ch * KC - p.c0; }
-                    else { src = p.src0; cs = p.c0; coff = ch * KC; }
+                    if (p.mode == SRC_CAT && st * KCS >= p.c0) { src = p.src1; cs = p.c1; coff = st * KCS - p.c0; }
+                    else { src = p.src0; cs = p.c0; coff = st * KCS; }
                     src += coff + c8 * 8;
                     for (int px = px0; px < C::HALO_PX; px += PXSTEP) {
                         const int hy = px / C::PW, hx = px - hy * C::PW;
-                        const int gy = y0 + hy, gx = x0 + hx;
-                        const bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                        int gy = y0 + hy, gx = x0 + hx;
+                        bool ok = ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                        if (p.pad_clamp) { gy = min(max(gy, 0), p.H - 1); gx = min(max(gx, 0), p.W - 1); ok = true; }
                         const size_t off = ok ? ((size_t)(n * p.H + gy) * p.W + gx) * cs : 0;
                         cp_async16_zfill(dst0 + px * 16, src + off, ok);
                     }
@@ -201,12 +240,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
                         fence_proxy_async_smem();
                         mbar_arrive(a_full((it - LAG) % SA));
                     }
+                } else if (p.mode == SRC_POOL_S2D) {
+                    // source is a space-to-depth tensor on THIS grid: the 2x2 block is 4 phase slices of one pixel
+                    const int cph = p.c0 >> 2;             // channels per phase
+                    const __nv_bfloat16* src = p.src0 + st * KCS + c8 * 8;
+                    for (int px = px0; px < C::HALO_PX; px += U * PXSTEP) {
+                        uint4 v[U][4]; bool okk[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int q = px + u * PXSTEP;
+                            const int hy = q / C::PW, hx = q - hy * C::PW;
+                            const int gy = y0 + hy, gx = x0 + hx;
+                            okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
+                            if (okk[u]) {
+                                const __nv_bfloat16* s = src + ((size_t)(n * p.H + gy) * p.W + gx) * p.c0;
+                                v[u][0] = ldg_nc16(s); v[u][1] = ldg_nc16(s + cph);
+                                v[u][2] = ldg_nc16(s + 2 * cph); v[u][3] = ldg_nc16(s + 3 * cph);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int q = px + u * PXSTEP;
+                            if (q < C::HALO_PX) {
+                                uint4 o = okk[u] ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3]) : make_uint4(0, 0, 0, 0);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + q * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(a_full(stage));
                 } else {
-                    // pool: 2x2 mean of the finer tensor; up: bilinear x2 of the coarser tensor.
+                    // SRC_POOL   : 2x2 mean of the finer NHWC tensor [2H,2W]
+                    // SRC_UP     : bilinear x2 of the coarser NHWC tensor [H/2,W/2]
+                    // SRC_UP_S2D : this grid is space-to-depth (pixel = 2x2 block, plane = phase*KB/8 + k8):
+                    //              bilinear x2 of the NHWC tensor [H,W] evaluated at hi-res (2y+a, 2x+b)
                     const bool pool = (p.mode == SRC_POOL);
+                    const bool s2d = (p.mode == SRC_UP_S2D);
                     const int cs = p.c0;
-                    const int sh = pool ? 2 * p.H : p.H >> 1, sw = pool ? 2 * p.W : p.W >> 1;   // source size
-                    const __nv_bfloat16* src = p.src0 + (size_t)n * sh * sw * cs + ch * KC + c8 * 8;
+                    const int sh = pool ? 2 * p.H : (s2d ? p.H : p.H >> 1), sw = pool ? 2 * p.W : (s2d ? p.W : p.W >> 1);
+                    constexpr int PPH = KB / 8;            // planes per phase (s2d)
+                    const int pa = s2d ? (c8 / PPH) >> 1 : 0, pb = s2d ? (c8 / PPH) & 1 : 0;
+                    const int coff = s2d ? st * KB + (c8 % PPH) * 8 : st * KCS + c8 * 8;
+                    const __nv_bfloat16* src = p.src0 + (size_t)n * sh * sw * cs + coff;
                     for (int px = px0; px < C::HALO_PX; px += U * PXSTEP) {
                         uint4 v[U][4]; bool okk[U]; float wx[U], wy[U];
 #pragma unroll
@@ -219,6 +294,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
                             wx[u] = wy[u] = 0.f;
                             if (okk[u]) {
                                 if (pool) { iy0 = 2 * gy; iy1 = iy0 + 1; ix0 = 2 * gx; ix1 = ix0 + 1; }
+                                else if (s2d) { up2_taps(2 * gy + pa, sh, iy0, iy1, wy[u]); up2_taps(2 * gx + pb, sw, ix0, ix1, wx[u]); }
                                 else { up2_taps(gy, sh, iy0, iy1, wy[u]); up2_taps(gx, sw, ix0, ix1, wx[u]); }
                                 const __nv_bfloat16* r0 = src + (size_t)iy0 * sw * cs;
                                 const __nv_bfloat16* r1 = src + (size_t)iy1 * sw * cs;
@@ -253,18 +329,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
             if (p.b_resident) {
                 for (int b = 0; b < nblk; ++b) {
                     mbar_arrive_expect_tx(b_full(b), C::B_BLOCK);
-                    bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KC), C::B_BLOCK, b_full(b));
+                    bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KB), C::B_BLOCK, b_full(b));
                 }
             } else {
                 int cnt = 0;
+                const int per_nt = p.tiles_per_img * p.N;
                 for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-                    const int nt = w / tiles_per_nt;
-                    const __nv_bfloat16* wsrc = p.wpack + (size_t)nt * nblk * (NT * KC);
+                    const int nt = w / per_nt;
+                    const __nv_bfloat16* wsrc = p.wpack + (size_t)nt * nblk * (NT * KB);
                     for (int b = 0; b < nblk; ++b, ++cnt) {
                         const int slot = cnt % SB;
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
                         mbar_arrive_expect_tx(b_full(slot), C::B_BLOCK);
-                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KC), C::B_BLOCK, b_full(slot));
+                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), C::B_BLOCK, b_full(slot));
                     }
                 }
             }
@@ -276,36 +353,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
         constexpr uint32_t idesc = make_idesc_bf16(128, NT);
         const uint64_t a_desc0 = make_smem_desc(0, C::PS, C::PW * 16);
         const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
+        const int n_ent = p.n_ent;
         int it = 0, cnt = 0, tcount = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
             mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
             const uint32_t d0 = tmem_base + buf * (MSUB * NT);
-            for (int ch = 0; ch < nch; ++ch, ++it) {
+            for (int st = 0; st < nst; ++st, ++it) {
                 const int stage = it % SA;
                 mbar_wait(a_full(stage), (it / SA) & 1);
                 const uint32_t a_stage = s_a + stage * C::A_STAGE;
 #pragma unroll 1
-                for (int tap = 0; tap < 9; ++tap, ++cnt) {
+                for (int e = 0; e < n_ent; ++e, ++cnt) {
                     int slot;
-                    if (p.b_resident) { slot = ch * 9 + tap; if (tcount == 0) mbar_wait(b_full(slot), 0); }
+                    if (p.b_resident) { slot = st * n_ent + e; if (tcount == 0) mbar_wait(b_full(slot), 0); }
                     else { slot = cnt % SB; mbar_wait(b_full(slot), (cnt / SB) & 1); }
                     tc_fence_after();
-                    const int dy = tap / 3, dx = tap - dy * 3;
-                    const uint64_t a_tap = a_desc0 + ((a_stage + (dy * C::PW + dx) * 16) >> 4);
+                    const uint64_t a_ent = a_desc0 + ((a_stage >> 4) + p.ent_off[e]);
                     const uint64_t b_blk = b_desc0 + ((s_b + slot * C::B_BLOCK) >> 4);
                     if (elect_one()) {
 #pragma unroll
                         for (int j = 0; j < MSUB; ++j) {
 #pragma unroll
-                            for (int s = 0; s < KC / 16; ++s)
-                                umma_bf16(d0 + j * NT, a_tap + ((j * 128 + 2 * s * C::PS) >> 4), b_blk + ((2 * s * (NT * 16)) >> 4),
-                                          idesc, (ch | tap | s) != 0);
+                            for (int s = 0; s < KB / 16; ++s)
+                                umma_bf16(d0 + j * NT, a_ent + ((j * 128 + 2 * s * C::PS) >> 4), b_blk + ((2 * s * (NT * 16)) >> 4),
+                                          idesc, (st | e | s) != 0);
                         }
                         if (!p.b_resident) umma_commit(b_empty(slot));
-                        if (tap == 8) {
+                        if (e == n_ent - 1) {
                             umma_commit(a_empty(stage));
-                            if (ch == nch - 1) umma_commit(acc_full(buf));
+                            if (st == nst - 1) umma_commit(acc_full(buf));
                         }
                     }
                     __syncwarp();
@@ -318,33 +395,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
         const int ly = m >> 3, lx = m & 7;
         int tcount = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-            const int nt = w / tiles_per_nt;
-            int r = w - nt * tiles_per_nt;
-            const int n = r / tiles_per_img; r -= n * tiles_per_img;
-            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const TileCoord tc = decode_tile(p, w);
+            const int nt = tc.nt, n = tc.n;
             const int buf = tcount & 1;
             mbar_wait(acc_full(buf), (tcount >> 1) & 1);
             tc_fence_after();
-            const int gy = ty * kTileH + ly;
+            const int gy = tc.ty * kTileH + ly;
             const float* bsrc = bias_s + nt * NT;
 #pragma unroll 1
             for (int j = 0; j < MSUB; ++j) {
-                const int gx = tx * (8 * MSUB) + 8 * j + lx;
+                const int gx = tc.tx * (8 * MSUB) + 8 * j + lx;
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * MSUB + j) * NT;
-                if (p.out_f32) {
+                if (p.epi == EPI_F32X16) {
                     uint32_t r16[16];
                     tmem_ld16(t0, r16);
                     tmem_ld_wait();
                     if (ok) {
-                        float4 o;
-                        o.x = __uint_as_float(r16[0]) + bsrc[0]; o.y = __uint_as_float(r16[1]) + bsrc[1];
-                        o.z = __uint_as_float(r16[2]) + bsrc[2]; o.w = __uint_as_float(r16[3]) + bsrc[3];
-                        reinterpret_cast<float4*>(p.out)[pix] = o;
+                        float4* o4 = reinterpret_cast<float4*>(p.out) + pix * 4;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            o4[q] = make_float4(__uint_as_float(r16[4 * q]) + bsrc[4 * q], __uint_as_float(r16[4 * q + 1]) + bsrc[4 * q + 1],
+                                                __uint_as_float(r16[4 * q + 2]) + bsrc[4 * q + 2], __uint_as_float(r16[4 * q + 3]) + bsrc[4 * q + 3]);
                     }
                 } else {
-                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout + nt * NT;
 #pragma unroll 1
                     for (int c = 0; c < NT; c += 32) {
                         uint32_t ra[16], rb[16];
@@ -369,7 +444,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const Con
                             }
                         }
                         if (ok) {
-                            uint4* o4 = reinterpret_cast<uint4*>(op + c);
+                            __nv_bfloat16* op;
+                            if (p.epi == EPI_SCATTER) {
+                                // folded upsample: global column g = (a, b, co); pixel (2y+a, 2x+b) of the hi-res NHWC tensor
+                                const int g = nt * NT + c, cs = p.cout_stride;
+                                const int ph = g / cs, co = g - ph * cs;
+                                const size_t hp = ((size_t)(n * 2 * p.H + 2 * gy + (ph >> 1)) * (2 * p.W) + 2 * gx + (ph & 1));
+                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + hp * cs + co;
+                            } else {
+                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout_stride + nt * NT + c;
+                            }
+                            uint4* o4 = reinterpret_cast<uint4*>(op);
                             o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
                             o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
                             if (NT >= 32) {

@@ -1,6 +1,11 @@
 // The forward-pass engine: static layer schedule of the four U-Nets, packed-weight blob
 // layout, workspace plan and the launch sequence of Net.forward (model.py:59-65) -- plus the
 // extern "C" surface declared in include/rrin_b200.h.
+//
+// Tensor layouts inside a U-Net:
+//   level 0 (full resolution, 32 channels): space-to-depth on the half-res grid, i.e. bf16
+//           [N, H/2, W/2, 4 phases, 32] == NHWC with 128 channels at half resolution;
+//   level l >= 1 (32*2^l channels): bf16 NHWC [N, H/2^l, W/2^l, C].
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -8,7 +13,6 @@
 #include <string>
 #include <vector>
 
-#include "../../include/rrin_b200.h"
 #include "common.cuh"
 #include "rrin_internal.h"
 
@@ -26,13 +30,19 @@ void set_error(const char* fmt, ...) {
 // ------------------------------------------------------------------ static schedule
 enum SrcKind { K_PLAIN = 0, K_CAT = 1, K_POOL = 2, K_UP = 3, K_HEAD = 4 };
 
+// One packed copy of a conv's weights (a layer has a second one when its upsample is folded:
+// the folded weights for the interior plus the plain weights for the exact border ring).
+struct Pack {
+    int kind = -1, cfg = -1, n_stages = 0, sched = SCHED_TAPS9, n_cols = 0;
+    size_t w_off = 0, b_off = 0;
+};
+
 struct Layer {
     std::string key;
     int unet;        // 0 Flow, 1 refine_flow, 2 Mask, 3 final   (execution order)
     int cin, cout;   // true channel counts (unet.py)
-    int cin_pad;     // channels of the stored input tensor(s) (heads: 16)
-    int level, src, act, out_f32, cfg;
-    size_t w_off, b_off;   // byte offsets into the packed blob
+    int level, src, act, is_last;
+    Pack main, fold; // `fold` only for up.1 convs writing level 0 or 1
 };
 
 struct UNetDef { const char* name; int cin, ncls, depth; };
@@ -43,7 +53,6 @@ struct Schedule {
     std::vector<Layer> layers;
     int first[5];          // first layer index of each U-Net, first[4] = total
     size_t blob_bytes;
-    std::string error;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -51,17 +60,33 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
-    auto add = [&](int u, const std::string& key, int cin, int cout, int level, int src, int act, int out_f32) {
+    auto place = [&](Pack& p) {
+        p.w_off = off;
+        off = align_up(off + conv_packed_weight_bytes(p.cfg, p.n_cols, p.n_stages, p.sched), 256);
+        p.b_off = off;
+        off = align_up(off + (size_t)conv_packed_bias_count(p.cfg, p.n_cols) * 4, 256);
+    };
+    auto add = [&](int u, const std::string& key, int cin, int cout, int level, int src, int act, int is_last) {
         Layer L;
         L.key = std::string(kUNets[u].name) + "." + key;
-        L.unet = u; L.cin = cin; L.cout = cout; L.level = level; L.src = src; L.act = act; L.out_f32 = out_f32;
-        L.cin_pad = (src == K_HEAD) ? 16 : cin;
-        L.cfg = conv_select_config(L.cin_pad, out_f32 ? 16 : cout, out_f32);
-        if (L.cfg < 0) s.error = "no conv configuration for " + L.key;
-        L.w_off = off;
-        off = align_up(off + (L.cfg < 0 ? 0 : conv_packed_weight_bytes(cout, L.cin_pad, L.cfg)), 256);
-        L.b_off = off;
-        off = align_up(off + (L.cfg < 0 ? 0 : (size_t)conv_packed_bias_count(cout, L.cfg) * 4), 256);
+        L.unet = u; L.cin = cin; L.cout = cout; L.level = level; L.src = src; L.act = act; L.is_last = is_last;
+        Pack& m = L.main;
+        if (level == 0) {                       // space-to-depth schedule, 4 phases x cout columns
+            m.kind = PACK_S2D; m.sched = SCHED_S2D16;
+            if (src == K_HEAD) { m.cfg = 0; m.n_stages = 1; m.n_cols = 128; }
+            else if (is_last) { m.cfg = 2; m.n_stages = 1; m.n_cols = 16; }
+            else { m.cfg = 1; m.n_stages = cin / 32; m.n_cols = 128; }          // 32->32, cat(32+32), exact up 64->32
+        } else {
+            m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
+            if (level == 1) { m.cfg = (cin == 32) ? 3 : 4; m.n_stages = (cin == 32) ? 1 : cin / 64; }
+            else { m.cfg = 5; m.n_stages = cin / 64; }
+        }
+        place(m);
+        if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns
+            Pack& f = L.fold;
+            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = 5; f.n_stages = cin / 64; f.n_cols = 4 * cout;
+            place(f);
+        }
         s.layers.push_back(L);
     };
     for (int u = 0; u < 4; ++u) {
@@ -100,6 +125,16 @@ static const Schedule& schedule() {
     return s;
 }
 
+// One kernel launch of a forward pass, resolved against the workspace at run time.
+struct Launch {
+    int glue = -1;           // >= 0: glue kernel id (0 pack_pair .. 4 residue_clamp)
+    int layer = -1;          // conv: index into schedule().layers
+    int use_fold = 0;        // conv: which Pack
+    ConvDesc cd;             // pointers hold workspace OFFSETS (+1 so that 0 stays "null") until launch
+    std::string name;
+    double flops = 0, bytes = 0;
+};
+
 }  // namespace rrin
 
 using namespace rrin;
@@ -108,24 +143,140 @@ using namespace rrin;
 struct rrin_engine {
     int Np, Nt, H, W, pair_mul;
     size_t ws_bytes;
-    // workspace offsets (bytes)
     size_t off_tmp[3], off_skip[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
-    int launches;
+    std::vector<Launch> launches;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every launch
     int prof_n = 0;
 };
 
-static inline void mark(const rrin_engine* e, cudaStream_t st) {
-    if (e->prof && e->prof_n < (int)e->prof->size()) cudaEventRecord((*e->prof)[const_cast<rrin_engine*>(e)->prof_n++], st);
+static inline void mark(rrin_engine* e, cudaStream_t st) {
+    if (e->prof && e->prof_n < (int)e->prof->size()) cudaEventRecord((*e->prof)[e->prof_n++], st);
 }
 
-static size_t lvl_bytes(int B, int H, int W, int lvl) {   // bf16 NHWC tensor of level lvl
+static size_t lvl_bytes(int B, int H, int W, int lvl) {   // bf16 activation tensor of level lvl (either layout)
     return (size_t)B * (H >> lvl) * (W >> lvl) * (32 << lvl) * 2;
+}
+
+static void* enc(size_t off) { return reinterpret_cast<void*>(off + 1); }   // workspace offset as a tagged pointer
+
+// Builds the conv launches of one U-Net at batch B: head16 -> fp32 out4.
+static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_off) {
+    const Schedule& s = schedule();
+    const int d = kUNets[u].depth;
+    const int H = e->H, W = e->W;
+    int li = s.first[u];
+    const bool fold_ok = (H > 64 && W > 64);     // the exact border ring needs more than 2x2 tiles of 32x32 pixels
+    auto base = [&](int layer, int use_fold, int grid_lvl) {
+        const Layer& L = s.layers[layer];
+        const Pack& pk = use_fold ? L.fold : L.main;
+        Launch ln;
+        ln.layer = layer; ln.use_fold = use_fold;
+        ln.cd.N = B; ln.cd.H = H >> grid_lvl; ln.cd.W = W >> grid_lvl;
+        ln.cd.sched = pk.sched; ln.cd.n_cols = pk.n_cols; ln.cd.cfg = pk.cfg; ln.cd.act = L.act;
+        return ln;
+    };
+    auto finish = [&](Launch& ln, const char* tag, bool counts_flops) {
+        const Layer& L = s.layers[ln.layer];
+        int kcs, kb, nt, msub;
+        conv_config_info(ln.cd.cfg, &kcs, &kb, &nt, &msub);
+        char b[128];
+        snprintf(b, sizeof b, "conv3x3_umma<KCS%d,KB%d,NT%d,MSUB%d>%s", kcs, kb, nt, msub, tag);
+        ln.name = b;
+        const double lp = (double)B * (H >> L.level) * (W >> L.level);      // output pixels of the reference conv
+        if (counts_flops) {
+            ln.flops = 2.0 * 9 * L.cin * L.cout * lp;
+            double in_b = 2.0 * (L.src == K_HEAD ? 16 : L.cin) * lp;
+            if (L.src == K_POOL) in_b *= 4; else if (L.src == K_UP) in_b /= 4;
+            const Pack& pk = ln.use_fold ? L.fold : L.main;
+            ln.bytes = in_b + (L.is_last ? 16.0 * lp : 2.0 * L.cout * lp) + (double)conv_packed_weight_bytes(pk.cfg, pk.n_cols, pk.n_stages, pk.sched);
+        }
+        e->launches.push_back(ln);
+    };
+    const size_t tmp[3] = {e->off_tmp[0], e->off_tmp[1], e->off_tmp[2]};
+    // ---- encoder
+    size_t x = head_off;
+    for (int i = 0; i < d; ++i) {
+        const int c = 32 << i;
+        {   // block.0
+            Launch ln = base(li, 0, i == 0 ? 1 : i);
+            if (i == 0) { ln.cd.mode = SRC_PLAIN; ln.cd.c0 = 64; ln.cd.cout_stride = 128; }
+            else if (i == 1) { ln.cd.mode = SRC_POOL_S2D; ln.cd.c0 = 128; ln.cd.cout_stride = c; }
+            else { ln.cd.mode = SRC_POOL; ln.cd.c0 = c / 2; ln.cd.cout_stride = c; }
+            ln.cd.src0 = enc(x); ln.cd.out = enc(tmp[0]); ln.cd.epi = EPI_BF16;
+            finish(ln, "", true); ++li;
+        }
+        {   // block.2
+            Launch ln = base(li, 0, i == 0 ? 1 : i);
+            ln.cd.mode = SRC_PLAIN; ln.cd.c0 = (i == 0) ? 128 : c; ln.cd.cout_stride = (i == 0) ? 128 : c;
+            const size_t o = (i < d - 1) ? e->off_skip[i] : tmp[1];
+            ln.cd.src0 = enc(tmp[0]); ln.cd.out = enc(o); ln.cd.epi = EPI_BF16;
+            finish(ln, "", true); ++li;
+            x = o;
+        }
+    }
+    {   // midconv at level d-1 (>= 3)
+        Launch ln = base(li, 0, d - 1);
+        ln.cd.mode = SRC_PLAIN; ln.cd.c0 = 32 << (d - 1); ln.cd.cout_stride = ln.cd.c0;
+        ln.cd.src0 = enc(x); ln.cd.out = enc(tmp[0]); ln.cd.epi = EPI_BF16;
+        finish(ln, "", true); ++li;
+    }
+    // ---- decoder
+    int cur = 0;
+    for (int j = 0; j < d - 1; ++j) {
+        const int lvl = d - 2 - j, c = 32 << lvl;
+        const int ui = (cur + 1) % 3, vi = (cur + 2) % 3;
+        // up.1 (no activation): input tmp[cur] is the level lvl+1 tensor with 2c channels
+        if (lvl <= 1 && fold_ok) {
+            Launch f = base(li, 1, lvl + 1);          // folded: runs on the coarse grid, replicate padding
+            f.cd.mode = SRC_PLAIN; f.cd.pad_clamp = 1; f.cd.c0 = 2 * c;
+            f.cd.src0 = enc(tmp[cur]); f.cd.out = enc(tmp[ui]);
+            if (lvl == 1) { f.cd.epi = EPI_SCATTER; f.cd.cout_stride = c; }
+            else { f.cd.epi = EPI_BF16; f.cd.cout_stride = 128; }     // (phase, co) columns == space-to-depth pixel
+            finish(f, " fold", true);
+            Launch r = base(li, 0, 1);                // exact transform path on the outermost ring of tiles
+            r.cd.mode = (lvl == 0) ? SRC_UP_S2D : SRC_UP; r.cd.c0 = 2 * c; r.cd.ring_only = 1;
+            r.cd.src0 = enc(tmp[cur]); r.cd.out = enc(tmp[ui]); r.cd.epi = EPI_BF16; r.cd.cout_stride = (lvl == 0) ? 128 : c;
+            finish(r, " ring", false);
+        } else {
+            Launch r = base(li, 0, lvl == 0 ? 1 : lvl);
+            r.cd.mode = (lvl == 0) ? SRC_UP_S2D : SRC_UP; r.cd.c0 = 2 * c;
+            r.cd.src0 = enc(tmp[cur]); r.cd.out = enc(tmp[ui]); r.cd.epi = EPI_BF16; r.cd.cout_stride = (lvl == 0) ? 128 : c;
+            finish(r, " up", true);
+        }
+        ++li;
+        {   // conv_block.block.0 on cat(up, skip)
+            Launch ln = base(li, 0, lvl == 0 ? 1 : lvl);
+            ln.cd.mode = SRC_CAT; ln.cd.c0 = ln.cd.c1 = (lvl == 0) ? 128 : c; ln.cd.cout_stride = (lvl == 0) ? 128 : c;
+            ln.cd.src0 = enc(tmp[ui]); ln.cd.src1 = enc(e->off_skip[lvl]); ln.cd.out = enc(tmp[vi]); ln.cd.epi = EPI_BF16;
+            finish(ln, "", true); ++li;
+        }
+        {   // conv_block.block.2
+            Launch ln = base(li, 0, lvl == 0 ? 1 : lvl);
+            ln.cd.mode = SRC_PLAIN; ln.cd.c0 = (lvl == 0) ? 128 : c; ln.cd.cout_stride = ln.cd.c0;
+            ln.cd.src0 = enc(tmp[vi]); ln.cd.out = enc(tmp[cur]); ln.cd.epi = EPI_BF16;
+            finish(ln, "", true); ++li;
+        }
+    }
+    {   // last (level 0, fp32 space-to-depth output)
+        Launch ln = base(li, 0, 1);
+        ln.cd.mode = SRC_PLAIN; ln.cd.c0 = 128; ln.cd.epi = EPI_F32X16; ln.cd.cout_stride = 16;
+        ln.cd.src0 = enc(tmp[cur]); ln.cd.out = enc(out_off);
+        finish(ln, "", true); ++li;
+    }
+}
+
+static void plan_glue(rrin_engine* e, int id) {
+    static const char* names[5] = {"pack_pair", "flow_tscale_pack", "warp_pack", "blend_pack", "residue_clamp"};
+    static const double bytes_px[5] = {56, 72, 120, 120, 44};          // per pixel, see DESIGN.md
+    Launch ln;
+    ln.glue = id; ln.name = names[id];
+    ln.bytes = bytes_px[id] * (double)e->H * e->W * (id == 0 ? e->Np : e->Nt);
+    e->launches.push_back(ln);
 }
 
 extern "C" {
 
-int rrin_version(void) { return 100; }
+int rrin_version(void) { return 200; }
 const char* rrin_last_error(void) { return g_err; }
 
 int rrin_num_convs(void) { return (int)schedule().layers.size(); }
@@ -147,12 +298,16 @@ size_t rrin_packed_weights_bytes(void) { return schedule().blob_bytes; }
 
 int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* stream) {
     const Schedule& s = schedule();
-    if (!s.error.empty()) { set_error("%s", s.error.c_str()); return RRIN_ERR_UNSUPPORTED; }
     if (idx < 0 || idx >= (int)s.layers.size() || !w || !b || !blob) { set_error("rrin_pack_conv: bad argument"); return RRIN_ERR_BAD_ARG; }
     const Layer& L = s.layers[idx];
     uint8_t* base = static_cast<uint8_t*>(blob);
-    return conv_pack_weights(w, b, L.cout, L.cin, L.cin_pad, L.cfg, base + L.w_off, reinterpret_cast<float*>(base + L.b_off),
-                             static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int r = conv_pack_weights(L.main.kind, w, b, L.cout, L.cin, L.main.n_stages, L.main.cfg, base + L.main.w_off,
+                              reinterpret_cast<float*>(base + L.main.b_off), st);
+    if (r == RRIN_OK && L.fold.kind >= 0)
+        r = conv_pack_weights(L.fold.kind, w, b, L.cout, L.cin, L.fold.n_stages, L.fold.cfg, base + L.fold.w_off,
+                              reinterpret_cast<float*>(base + L.fold.b_off), st);
+    return r;
 }
 
 int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** out) {
@@ -161,7 +316,6 @@ int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** o
     if (n_pairs <= 0 || n_samples <= 0 || H <= 0 || W <= 0) { set_error("rrin_engine_create: empty shape"); return RRIN_ERR_BAD_SHAPE; }
     if (H % 16 || W % 16) { set_error("H and W must be multiples of 16 (got %dx%d)", H, W); return RRIN_ERR_BAD_SHAPE; }
     if (n_pairs != n_samples && n_pairs != 1) { set_error("n_pairs must equal n_samples or be 1 (got %d, %d)", n_pairs, n_samples); return RRIN_ERR_BAD_SHAPE; }
-    if (!schedule().error.empty()) { set_error("%s", schedule().error.c_str()); return RRIN_ERR_UNSUPPORTED; }
     rrin_engine* e = new rrin_engine();
     e->Np = n_pairs; e->Nt = n_samples; e->H = H; e->W = W;
     e->pair_mul = (n_pairs == n_samples) ? 1 : 0;
@@ -177,53 +331,23 @@ int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** o
     e->off_out4 = take((size_t)n_samples * px * 16);
     e->off_xt8 = take((size_t)n_samples * px * 32);
     e->ws_bytes = off;
-    e->launches = rrin_num_convs() + 5;
+    // launch sequence of Net.forward
+    plan_glue(e, 0);                                              // model.py:33
+    plan_unet(e, 0, n_pairs, e->off_h16, e->off_flow4);           // model.py:35
+    plan_glue(e, 1);                                              // model.py:37-41
+    plan_unet(e, 1, n_samples, e->off_h16, e->off_u4);            // model.py:42
+    plan_glue(e, 2);                                              // model.py:44-50
+    plan_unet(e, 2, n_samples, e->off_h16, e->off_u4);            // model.py:52
+    plan_glue(e, 3);                                              // model.py:52-55,61
+    plan_unet(e, 3, n_samples, e->off_h16, e->off_u4);            // model.py:62
+    plan_glue(e, 4);                                              // model.py:62-63
     *out = e;
     return RRIN_OK;
 }
 
 void rrin_engine_destroy(rrin_engine* e) { delete e; }
 size_t rrin_engine_workspace_bytes(const rrin_engine* e) { return e ? e->ws_bytes : 0; }
-int rrin_engine_num_launches(const rrin_engine* e) { return e ? e->launches : 0; }
-
-// One U-Net (unet.py:40-51) at batch B: head16 -> fp32 NHWC4 `out4`.
-static int run_unet(const rrin_engine* e, int u, int B, const uint8_t* blob, uint8_t* ws, const void* head16, float* out4,
-                    cudaStream_t st) {
-    const Schedule& s = schedule();
-    const int d = kUNets[u].depth;
-    void* tmp[3] = {ws + e->off_tmp[0], ws + e->off_tmp[1], ws + e->off_tmp[2]};
-    int li = s.first[u];
-    auto conv = [&](const void* src0, const void* src1, int c0, int c1, int mode, int lvl, void* out) -> int {
-        const Layer& L = s.layers[li++];
-        ConvDesc cd;
-        cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = mode;
-        cd.N = B; cd.H = e->H >> lvl; cd.W = e->W >> lvl;
-        cd.cout = L.cout; cd.wpack = blob + L.w_off; cd.bias = reinterpret_cast<const float*>(blob + L.b_off);
-        cd.out = out; cd.out_f32 = L.out_f32; cd.act = L.act; cd.cfg = L.cfg;
-        const int r = conv_launch(cd, st);
-        mark(e, st);
-        return r;
-    };
-    const void* x = head16;
-    int xc = 16;
-    for (int i = 0; i < d; ++i) {
-        const int c = 32 << i;
-        if (int r = conv(x, nullptr, xc, 0, i == 0 ? SRC_PLAIN : SRC_POOL, i, tmp[0])) return r;
-        void* o = (i < d - 1) ? (void*)(ws + e->off_skip[i]) : tmp[1];
-        if (int r = conv(tmp[0], nullptr, c, 0, SRC_PLAIN, i, o)) return r;
-        x = o; xc = c;
-    }
-    if (int r = conv(x, nullptr, xc, 0, SRC_PLAIN, d - 1, tmp[0])) return r;   // midconv
-    int cur = 0;                                                                // x lives in tmp[cur]
-    for (int j = 0; j < d - 1; ++j) {
-        const int lvl = d - 2 - j, c = 32 << lvl;
-        const int ui = (cur + 1) % 3, vi = (cur + 2) % 3;
-        if (int r = conv(tmp[cur], nullptr, 2 * c, 0, SRC_UP, lvl, tmp[ui])) return r;              // up.1
-        if (int r = conv(tmp[ui], ws + e->off_skip[lvl], c, c, SRC_CAT, lvl, tmp[vi])) return r;    // block.0 on cat(up, skip)
-        if (int r = conv(tmp[vi], nullptr, c, 0, SRC_PLAIN, lvl, tmp[cur])) return r;               // block.2
-    }
-    return conv(tmp[cur], nullptr, 32, 0, SRC_PLAIN, 0, out4);                                      // last
-}
+int rrin_engine_num_launches(const rrin_engine* e) { return e ? (int)e->launches.size() : 0; }
 
 int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, const float* in0, const float* in1,
                         const float* coef, float* out, void* stream) {
@@ -231,72 +355,51 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint8_t* blob = static_cast<const uint8_t*>(blob_);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const Schedule& s = schedule();
     void* h16 = ws + e->off_h16;
     float* flow4 = reinterpret_cast<float*>(ws + e->off_flow4);
     float* u4 = reinterpret_cast<float*>(ws + e->off_u4);
     float* out4 = reinterpret_cast<float*>(ws + e->off_out4);
     float* xt8 = reinterpret_cast<float*>(ws + e->off_xt8);
     const int H = e->H, W = e->W, Np = e->Np, Nt = e->Nt, pm = e->pair_mul;
-    int r;
-    mark(e, st);                                                                                  // t0
-    if ((r = pack_pair(in0, in1, Np, H, W, h16, st))) return r;                                   // model.py:33
-    mark(e, st);
-    if ((r = run_unet(e, 0, Np, blob, ws, h16, flow4, st))) return r;                             // model.py:35
-    if ((r = flow_tscale_pack(flow4, in0, in1, coef, Nt, pm, H, W, h16, st))) return r;           // model.py:37-41
-    mark(e, st);
-    if ((r = run_unet(e, 1, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:42
-    if ((r = warp_pack(flow4, u4, in0, in1, coef, Nt, pm, H, W, h16, xt8, st))) return r;         // model.py:44-50
-    mark(e, st);
-    if ((r = run_unet(e, 2, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:52
-    if ((r = blend_pack(u4, xt8, in0, in1, coef, Nt, pm, H, W, out4, h16, st))) return r;         // model.py:52-55,61
-    mark(e, st);
-    if ((r = run_unet(e, 3, Nt, blob, ws, h16, u4, st))) return r;                                // model.py:62
-    r = residue_clamp(u4, out4, Nt, H, W, out, st);                                               // model.py:62-63
-    mark(e, st);
-    return r;
+    auto dec = [&](const void* p) -> void* { return p ? ws + (reinterpret_cast<size_t>(p) - 1) : nullptr; };
+    mark(e, st);                                                  // t0
+    for (const Launch& ln : e->launches) {
+        int r = RRIN_OK;
+        if (ln.glue >= 0) {
+            switch (ln.glue) {
+                case 0: r = pack_pair(in0, in1, Np, H, W, h16, st); break;
+                case 1: r = flow_tscale_pack(flow4, in0, in1, coef, Nt, pm, H, W, h16, st); break;
+                case 2: r = warp_pack(flow4, u4, in0, in1, coef, Nt, pm, H, W, h16, xt8, st); break;
+                case 3: r = blend_pack(u4, xt8, in0, in1, coef, Nt, pm, H, W, out4, h16, st); break;
+                case 4: r = residue_clamp(u4, out4, Nt, H, W, out, st); break;
+            }
+        } else {
+            const Layer& L = s.layers[ln.layer];
+            const Pack& pk = ln.use_fold ? L.fold : L.main;
+            ConvDesc cd = ln.cd;
+            cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out);
+            cd.wpack = blob + pk.w_off;
+            cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
+            r = conv_launch(cd, st);
+        }
+        if (r != RRIN_OK) return r;
+        mark(e, st);
+    }
+    return RRIN_OK;
 }
 
 // Launch i of one forward, in stream order: kernel class name, the reference layer it computes,
 // algorithmic FLOPs and algorithmic HBM bytes (each operand/result tensor crossing once).
 int rrin_engine_launch_info(const rrin_engine* e, int i, char* name, int name_cap, char* layer, int layer_cap,
                             double* flops, double* bytes) {
-    if (!e || i < 0 || i >= e->launches) { set_error("rrin_engine_launch_info: bad index %d", i); return RRIN_ERR_BAD_ARG; }
-    const Schedule& s = schedule();
-    const double px = (double)e->H * e->W;
-    std::string nm, ly; double fl = 0, by = 0;
-    // glue launches sit before U-Net 0, between U-Nets, and at the end
-    int pos = i, li = -1;
-    const char* glue_names[5] = {"pack_pair", "flow_tscale_pack", "warp_pack", "blend_pack", "residue_clamp"};
-    const double glue_bytes[5] = {56, 72, 120, 120, 44};          // per pixel, see DESIGN.md
-    int g = -1;
-    for (int u = 0; u < 4 && g < 0 && li < 0; ++u) {
-        if (pos == 0) { g = u; break; }
-        pos -= 1;
-        const int nl = s.first[u + 1] - s.first[u];
-        if (pos < nl) { li = s.first[u] + pos; break; }
-        pos -= nl;
-    }
-    if (g < 0 && li < 0) g = 4;
-    if (g >= 0) {
-        nm = glue_names[g]; ly = std::string("model.py glue: ") + glue_names[g];
-        by = glue_bytes[g] * px * (g == 0 ? e->Np : e->Nt);
-    } else {
-        const Layer& L = s.layers[li];
-        int kc, nt, msub; conv_config_info(L.cfg, &kc, &nt, &msub);
-        char b[96]; snprintf(b, sizeof b, "conv3x3_umma<KC%d,NT%d,MSUB%d>", kc, nt, msub);
-        nm = b; ly = L.key;
-        const int B = (L.unet == 0) ? e->Np : e->Nt;
-        const double lp = px * B / (double)(1 << (2 * L.level));
-        fl = 2.0 * 9 * L.cin * L.cout * lp;
-        double in_b = 2.0 * L.cin_pad * lp;                       // bf16 operand tensor(s) at this level
-        if (L.src == K_POOL) in_b *= 4; else if (L.src == K_UP) in_b /= 4;
-        const double out_b = L.out_f32 ? 16.0 * lp : 2.0 * L.cout * lp;
-        by = in_b + out_b + (double)conv_packed_weight_bytes(L.cout, L.cin_pad, L.cfg);
-    }
-    if (name && name_cap > 0) { strncpy(name, nm.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (!e || i < 0 || i >= (int)e->launches.size()) { set_error("rrin_engine_launch_info: bad index %d", i); return RRIN_ERR_BAD_ARG; }
+    const Launch& ln = e->launches[i];
+    const std::string ly = ln.glue >= 0 ? std::string("model.py glue: ") + ln.name : schedule().layers[ln.layer].key;
+    if (name && name_cap > 0) { strncpy(name, ln.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
     if (layer && layer_cap > 0) { strncpy(layer, ly.c_str(), layer_cap - 1); layer[layer_cap - 1] = 0; }
-    if (flops) *flops = fl;
-    if (bytes) *bytes = by;
+    if (flops) *flops = ln.flops;
+    if (bytes) *bytes = ln.bytes;
     return RRIN_OK;
 }
 
@@ -305,7 +408,8 @@ int rrin_engine_launch_info(const rrin_engine* e, int i, char* name, int name_ca
 int rrin_engine_forward_profiled(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
                                  const float* coef, float* out, void* stream, float* ms_host) {
     if (!e || !ms_host) { set_error("rrin_engine_forward_profiled: null argument"); return RRIN_ERR_BAD_ARG; }
-    std::vector<cudaEvent_t> ev(e->launches + 1);
+    const int nl = (int)e->launches.size();
+    std::vector<cudaEvent_t> ev(nl + 1);
     for (auto& x : ev) RRIN_CUDA_CHECK(cudaEventCreate(&x));
     e->prof = &ev; e->prof_n = 0;
     int r = rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
@@ -315,7 +419,7 @@ int rrin_engine_forward_profiled(rrin_engine* e, const void* blob, void* workspa
         if (ce != cudaSuccess) { set_error("profiled forward failed: %s", cudaGetErrorString(ce)); r = RRIN_ERR_CUDA; }
     }
     if (r == RRIN_OK)
-        for (int i = 0; i < e->launches; ++i) cudaEventElapsedTime(&ms_host[i], ev[i], ev[i + 1]);
+        for (int i = 0; i < nl; ++i) cudaEventElapsedTime(&ms_host[i], ev[i], ev[i + 1]);
     for (auto& x : ev) cudaEventDestroy(x);
     return r;
 }
@@ -333,17 +437,26 @@ int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, floa
 }
 
 // ------------------------------------------------------------------ unit-level wrappers
-int rrin_conv_select_config(int cin, int cout, int out_f32) { return conv_select_config(cin, cout, out_f32); }
-size_t rrin_conv_packed_weight_bytes(int cout, int cin_pad, int cfg) { return conv_packed_weight_bytes(cout, cin_pad, cfg); }
-int rrin_conv_packed_bias_count(int cout, int cfg) { return conv_packed_bias_count(cout, cfg); }
-int rrin_pack_conv_raw(const float* w, const float* b, int cout, int cin, int cin_pad, int cfg, void* wpack, float* bias_pack, void* stream) {
-    return conv_pack_weights(w, b, cout, cin, cin_pad, cfg, wpack, bias_pack, static_cast<cudaStream_t>(stream));
+int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub) { return conv_config_info(cfg, kcs, kb, nt, msub); }
+size_t rrin_conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched) {
+    if (cfg < 0 || cfg >= conv_num_configs()) return 0;
+    return conv_packed_weight_bytes(cfg, n_cols, n_stages, sched);
 }
-int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int N, int H, int W, int cout,
-                 const void* wpack, const float* bias_pack, void* out, int out_f32, int act, int cfg, void* stream) {
+int rrin_conv_packed_bias_count(int cfg, int n_cols) {
+    if (cfg < 0 || cfg >= conv_num_configs()) return 0;
+    return conv_packed_bias_count(cfg, n_cols);
+}
+int rrin_pack_conv_raw(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg, void* wpack,
+                       float* bias_pack, void* stream) {
+    return conv_pack_weights(kind, w, b, cout, cin, n_stages, cfg, wpack, bias_pack, static_cast<cudaStream_t>(stream));
+}
+int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
+                 int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
+                 int act, int ring_only, int cfg, void* stream) {
     ConvDesc cd;
-    cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = src_mode; cd.N = N; cd.H = H; cd.W = W;
-    cd.cout = cout; cd.wpack = wpack; cd.bias = bias_pack; cd.out = out; cd.out_f32 = out_f32; cd.act = act; cd.cfg = cfg;
+    cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = src_mode; cd.pad_clamp = pad_clamp;
+    cd.N = N; cd.H = H; cd.W = W; cd.sched = sched; cd.n_cols = n_cols; cd.wpack = wpack; cd.bias = bias_pack;
+    cd.out = out; cd.epi = epi; cd.cout_stride = cout_stride; cd.act = act; cd.ring_only = ring_only; cd.cfg = cfg;
     return conv_launch(cd, static_cast<cudaStream_t>(stream));
 }
 int rrin_pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, void* stream) {

@@ -6,33 +6,59 @@
 
 namespace rrin {
 
-enum ConvSrcMode : int { SRC_PLAIN = 0, SRC_CAT = 1, SRC_POOL = 2, SRC_UP = 3 };
+// How the conv's A operand (halo tile on the conv grid [H,W]) is formed from stored tensors.
+enum ConvSrcMode : int {
+    SRC_PLAIN = 0,     // src0 NHWC [N,H,W,c0]
+    SRC_CAT = 1,       // channels of src0 [N,H,W,c0] then src1 [N,H,W,c1]            (unet.py:93)
+    SRC_POOL = 2,      // 2x2 mean of src0 NHWC [N,2H,2W,c0]                          (unet.py:46)
+    SRC_UP = 3,        // bilinear x2 of src0 NHWC [N,H/2,W/2,c0]                     (unet.py:77)
+    SRC_POOL_S2D = 4,  // mean over the 4 phases of src0 space-to-depth [N,H,W,4*(c0/4)]
+    SRC_UP_S2D = 5,    // grid is space-to-depth: phase (a,b) = bilinear x2 of src0 [N,H,W,c0] at (2y+a,2x+b)
+};
+enum ConvEpilogue : int {
+    EPI_BF16 = 0,      // bf16 NHWC [N,H,W,cout_stride]
+    EPI_F32X16 = 1,    // fp32 [N,H,W,16]   (space-to-depth `last` conv: 4 phases x 4 classes)
+    EPI_SCATTER = 2,   // folded upsample: column (a,b,co) -> bf16 NHWC [N,2H,2W,cout_stride] at (2y+a,2x+b)
+};
+enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1 };
+enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2 };
 
 // One 3x3 convolution launch (see conv3x3.cuh for the data layouts).
 struct ConvDesc {
-    const void* src0 = nullptr;   // bf16 NHWC
-    const void* src1 = nullptr;   // bf16 NHWC (cat only)
-    int c0 = 0, c1 = 0;
-    int mode = 0;                 // 0 plain, 1 cat, 2 pool, 3 up
-    int N = 0, H = 0, W = 0;      // output grid
-    int cout = 0;                 // true output channels (bf16: multiple of NT; f32: <= 16, 4 stored)
-    const void* wpack = nullptr;  // packed bf16 weights
-    const float* bias = nullptr;  // packed fp32 bias
+    const void* src0 = nullptr;
+    const void* src1 = nullptr;
+    int c0 = 0, c1 = 0;           // stored channels per pixel of each source
+    int mode = SRC_PLAIN;
+    int pad_clamp = 0;
+    int N = 0, H = 0, W = 0;      // conv grid
+    int sched = SCHED_TAPS9;
+    int n_cols = 0;               // GEMM N in total (multiple of the config's NT)
+    const void* wpack = nullptr;
+    const float* bias = nullptr;
     void* out = nullptr;
-    int out_f32 = 0;
+    int epi = EPI_BF16;
+    int cout_stride = 0;
     int act = 0;
-    int cfg = -1;                 // configuration id (conv_select_config)
+    int ring_only = 0;
+    int cfg = -1;
 };
 
-int conv_select_config(int cin, int cout, int out_f32);
-int conv_config_info(int cfg, int* kc, int* nt, int* msub);
-size_t conv_packed_weight_bytes(int cout, int cin_pad, int cfg);
-int conv_packed_bias_count(int cout, int cfg);
-int conv_pack_weights(const float* w, const float* b, int cout, int cin, int cin_pad, int cfg,
+int conv_num_configs();
+int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
+// packed sizes for a layer: n_cols GEMM columns, n_stages*n_ent weight blocks of KB x NT
+size_t conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);
+int conv_packed_bias_count(int cfg, int n_cols);
+// w: fp32 OIHW [cout][cin][3][3], b: fp32 [cout].
+//  PACK_NORMAL: columns = cout (zero padded to a multiple of NT), stage s covers input channels [s*KCS, +KCS)
+//  PACK_S2D   : columns = (phase, co) with NT/4 columns per phase; stage s covers input channels [s*KB, +KB)
+//  PACK_FOLD  : bilinear x2 folded into the weights; columns = (phase, co), 4*cout in total; stages as NORMAL
+int conv_pack_weights(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
                       void* wpack, float* bias_pack, cudaStream_t stream);
 int conv_launch(const ConvDesc& d, cudaStream_t stream);
 
-// Fused elementwise / gather kernels (glue.cu).  All tensors fp32 unless noted.
+// Fused elementwise / gather kernels (glue.cu).  Frames are fp32 NCHW; everything these kernels
+// exchange with the U-Nets is space-to-depth on the half-resolution grid [H/2][W/2][phase]:
+//   head inputs bf16 [N,H/2,W/2,4,16], U-Net outputs fp32 [N,H/2,W/2,4,4].
 //   coef: [Nt][6] = {c00, c01, c10, c11, 1-t, t} per sample (model.py:38-39,54)
 //   pair_mul: 1 when sample n uses frame pair n, 0 when all samples share pair 0 (multi-t)
 int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s);

@@ -153,6 +153,7 @@ class Engine:
 
     def tap(self, which: int) -> torch.Tensor:
         n = self.n_pairs if which == 0 else self.n
-        dst = torch.empty((n, self.h, self.w, 4), dtype=torch.float32, device=self.device)
+        dst = torch.empty((n, self.h // 2, self.w // 2, 4, 4), dtype=torch.float32, device=self.device)
         check(lib().rrin_engine_tap(self._h, _ptr(self.workspace), which, _ptr(dst), _stream()), "rrin_engine_tap")
-        return dst
+        # space-to-depth [n,H/2,W/2,phase,4] -> NCHW [n,4,H,W]
+        return dst.reshape(n, self.h // 2, self.w // 2, 2, 2, 4).permute(0, 5, 1, 3, 2, 4).reshape(n, 4, self.h, self.w)

@@ -8,6 +8,12 @@ import torch.nn.functional as F
 
 from rrin_b200._lib import check, lib
 
+SRC_PLAIN, SRC_CAT, SRC_POOL, SRC_UP, SRC_POOL_S2D, SRC_UP_S2D = range(6)
+EPI_BF16, EPI_F32X16, EPI_SCATTER = range(3)
+SCHED_TAPS9, SCHED_S2D16 = 0, 1
+PACK_NORMAL, PACK_S2D, PACK_FOLD = 0, 1, 2
+CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
+
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
@@ -17,45 +23,103 @@ def bf16_round(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
 
-def nhwc_bf16(x_nchw: torch.Tensor) -> torch.Tensor:
-    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+def cfg_info(cfg):
+    v = [C.c_int() for _ in range(4)]
+    check(lib().rrin_conv_config_info(cfg, *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)      # kcs, kb, nt, msub
 
 
-def conv3x3(src0, src1, mode, n, h, w, weight, bias, act, out_f32=False, cin_pad=None):
-    """src*: bf16 NHWC CUDA tensors. weight fp32 OIHW, bias fp32 (CUDA). Returns NCHW fp32."""
+def nhwc(x_nchw, dtype=torch.bfloat16):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def to_s2d(x_nchw, dtype=torch.bfloat16):
+    """[N,C,H,W] -> space-to-depth [N,H/2,W/2,4,C] (phase = 2*a+b for pixel (2y+a, 2x+b))."""
+    n, c, h, w = x_nchw.shape
+    return x_nchw.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, h // 2, w // 2, 4, c).contiguous().to(dtype)
+
+
+def from_s2d(x):
+    """[N,Hb,Wb,4,C] -> fp32 [N,C,2Hb,2Wb]."""
+    n, hb, wb, _, c = x.shape
+    return x.float().reshape(n, hb, wb, 2, 2, c).permute(0, 5, 1, 3, 2, 4).reshape(n, c, 2 * hb, 2 * wb).contiguous()
+
+
+def pack(kind, cfg, weight, bias, n_stages, sched):
     l = lib()
     cout, cin = weight.shape[:2]
-    c0 = src0.shape[-1]
-    c1 = src1.shape[-1] if src1 is not None else 0
-    cin_pad = cin_pad or (c0 + c1)
-    cfg = l.rrin_conv_select_config(cin_pad, 16 if out_f32 else cout, int(out_f32))
-    assert cfg >= 0, (cin_pad, cout, out_f32)
-    wp = torch.zeros(l.rrin_conv_packed_weight_bytes(cout, cin_pad, cfg), dtype=torch.uint8, device="cuda")
-    bp = torch.zeros(l.rrin_conv_packed_bias_count(cout, cfg), dtype=torch.float32, device="cuda")
+    _, _, nt, _ = cfg_info(cfg)
+    n_cols = {PACK_NORMAL: cout, PACK_S2D: nt, PACK_FOLD: 4 * cout}[kind]
+    n_cols = (n_cols + nt - 1) // nt * nt
+    wp = torch.zeros(l.rrin_conv_packed_weight_bytes(cfg, n_cols, n_stages, sched), dtype=torch.uint8, device="cuda")
+    bp = torch.zeros(l.rrin_conv_packed_bias_count(cfg, n_cols), dtype=torch.float32, device="cuda")
     wc, bc = weight.contiguous().float(), bias.contiguous().float()
-    check(l.rrin_pack_conv_raw(wc.data_ptr(), bc.data_ptr(), cout, cin, cin_pad, cfg, wp.data_ptr(), bp.data_ptr(), stream()))
-    if out_f32:
-        out = torch.full((n, h, w, 4), float("nan"), dtype=torch.float32, device="cuda")
-    else:
-        out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    check(l.rrin_conv3x3(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, n, h, w, cout,
-                         wp.data_ptr(), bp.data_ptr(), out.data_ptr(), int(out_f32), int(act), cfg, stream()), "rrin_conv3x3")
+    check(l.rrin_pack_conv_raw(kind, wc.data_ptr(), bc.data_ptr(), cout, cin, n_stages, cfg, wp.data_ptr(), bp.data_ptr(), stream()),
+          "rrin_pack_conv_raw")
     torch.cuda.synchronize()
-    o = out.float().permute(0, 3, 1, 2)
-    return o[:, :cout] if out_f32 else o
+    return wp, bp, n_cols
 
 
-def conv3x3_reference(src0, src1, mode, weight, bias, act):
-    """fp32 torch reference on the same bf16-rounded operands (TF32 off)."""
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    x = src0.float().permute(0, 3, 1, 2)
-    if mode == 1:
-        x = torch.cat((x, src1.float().permute(0, 3, 1, 2)), 1)
-    elif mode == 2:
+def launch(src0, src1, c0, c1, mode, pad_clamp, n, gh, gw, sched, n_cols, wp, bp, out, epi, cout_stride, act, ring_only, cfg):
+    check(lib().rrin_conv3x3(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, pad_clamp, n, gh, gw,
+                             sched, n_cols, wp.data_ptr(), bp.data_ptr(), out.data_ptr(), epi, cout_stride, int(act), int(ring_only),
+                             cfg, stream()), "rrin_conv3x3")
+    torch.cuda.synchronize()
+
+
+def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=False, out=None):
+    """Levels >= 1: NHWC bf16 sources, 9-tap schedule.  Returns (NCHW fp32, raw NHWC bf16 tensor)."""
+    kcs, kb, nt, _ = cfg_info(cfg)
+    cout, cin = weight.shape[:2]
+    c0 = src0.shape[-1] * (src0.shape[-2] if mode == SRC_POOL_S2D else 1)
+    c1 = src1.shape[-1] if src1 is not None else 0
+    wp, bp, n_cols = pack(PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
+    if out is None:
+        out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg)
+    return out.float().permute(0, 3, 1, 2), out
+
+
+def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring_only=False, out=None):
+    """Level 0: space-to-depth sources [N,hb,wb,4,C] (or NHWC [N,hb,wb,C] for SRC_UP_S2D), 16-entry schedule.
+    Returns hi-res NCHW fp32 [N,cout,2hb,2wb] and the raw output tensor."""
+    kcs, kb, nt, _ = cfg_info(cfg)
+    cout = weight.shape[0]
+    c0 = src0.shape[-1] * (src0.shape[-2] if src0.dim() == 5 else 1)
+    c1 = (src1.shape[-1] * src1.shape[-2]) if src1 is not None else 0
+    wp, bp, n_cols = pack(PACK_S2D, cfg, weight, bias, n_stages, SCHED_S2D16)
+    f32 = (nt == 16)
+    cpp = nt // 4
+    if out is None:
+        out = torch.full((n, hb, wb, 4, cpp), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+    launch(src0, src1, c0, c1, mode, 0, n, hb, wb, SCHED_S2D16, n_cols, wp, bp, out, EPI_F32X16 if f32 else EPI_BF16,
+           16 if f32 else nt, act, ring_only, cfg)
+    return from_s2d(out)[:, :cout], out
+
+
+def conv_fold(src, n, hc, wc, weight, bias, level0, out=None):
+    """Folded bilinear-x2 + conv: src NHWC bf16 [N,hc,wc,cin] (coarse); output hi-res [2hc,2wc].
+    level0=True -> output is space-to-depth [N,hc,wc,4,cout]; else NHWC [N,2hc,2wc,cout] via the scatter epilogue."""
+    kcs, kb, nt, _ = cfg_info(CFG_BIG)
+    cout, cin = weight.shape[:2]
+    wp, bp, n_cols = pack(PACK_FOLD, CFG_BIG, weight, bias, cin // kcs, SCHED_TAPS9)
+    if level0:
+        if out is None:
+            out = torch.full((n, hc, wc, 4, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        launch(src, None, cin, 0, SRC_PLAIN, 1, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, CFG_BIG)
+        return from_s2d(out), out
+    if out is None:
+        out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    launch(src, None, cin, 0, SRC_PLAIN, 1, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, CFG_BIG)
+    return out.float().permute(0, 3, 1, 2), out
+
+
+def reference(x_nchw, weight, bias, act, pre=None):
+    """float64 conv of bf16-rounded operands (x already holds bf16-representable values); `pre` = pool / up."""
+    x = x_nchw.float()
+    if pre == "pool":
         x = bf16_round(F.avg_pool2d(x, 2))
-    elif mode == 3:
+    elif pre == "up":
         x = bf16_round(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
-    cin = weight.shape[1]
-    y = F.conv2d(x[:, :cin].double(), bf16_round(weight).double(), bias.double(), padding=1).float()
+    y = F.conv2d(x.double(), bf16_round(weight).double(), bias.double(), padding=1).float()
     return F.leaky_relu(y, 0.1) if act else y

@@ -54,7 +54,7 @@ def test_forward_matches_reference_fixture(golden_dir, name, maxabs, min_psnr):
         assert err <= maxabs, f"{name}: max-abs {err}"
     assert p >= min_psnr, f"{name}: PSNR {p}"
     # flow tap against the reference's Flow U-Net output
-    flow = net._engines[next(iter(net._engines))].tap(0).cpu().permute(0, 3, 1, 2)
+    flow = net._engines[next(iter(net._engines))].tap(0).cpu()
     fref = torch.from_numpy(g["flow"])
     assert (flow - fref).abs().max().item() <= 0.02 * max(1.0, fref.abs().max().item())
 

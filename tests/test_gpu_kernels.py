@@ -14,9 +14,9 @@ if torch.cuda.is_available():
     from oracle import rrin_oracle as O
 
 
-def _rand_act(n, h, w, c, seed):
+def _rand(n, c, h, w, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    return (torch.randn(n, h, w, c, generator=g, device="cuda") * 0.7).to(torch.bfloat16)
+    return G.bf16_round(torch.randn(n, c, h, w, generator=g, device="cuda") * 0.7)
 
 
 def _rand_wb(cout, cin, seed):
@@ -26,56 +26,137 @@ def _rand_wb(cout, cin, seed):
     return w, b
 
 
-CONV_CASES = [
-    # name, mode, c0, c1, cout, cin_true, out_f32, act, n, h, w
-    ("head6", 0, 16, 0, 32, 6, False, True, 1, 32, 64),
-    ("head16_partial", 0, 16, 0, 32, 16, False, True, 2, 24, 40),
-    ("l0_32_32", 0, 32, 0, 32, 32, False, True, 1, 32, 64),
-    ("l0_32_32_partial", 0, 32, 0, 32, 32, False, True, 2, 48, 80),
-    ("l0_cat", 1, 32, 32, 32, 64, False, True, 1, 32, 48),
-    ("l0_up", 3, 64, 0, 32, 64, False, False, 1, 32, 48),
-    ("last4", 0, 32, 0, 4, 32, True, False, 1, 32, 64),
-    ("last2", 0, 32, 0, 2, 32, True, False, 2, 16, 48),
-    ("last3", 0, 32, 0, 3, 32, True, False, 1, 48, 16),
-    ("l1_pool", 2, 32, 0, 64, 32, False, True, 1, 24, 40),
-    ("l1_64_64", 0, 64, 0, 64, 64, False, True, 1, 24, 40),
-    ("l1_up", 3, 128, 0, 64, 128, False, False, 1, 32, 32),
-    ("l1_cat", 1, 64, 64, 64, 128, False, True, 1, 24, 40),
-    ("l2_pool", 2, 64, 0, 128, 64, False, True, 1, 16, 24),
-    ("l2_128_128", 0, 128, 0, 128, 128, False, True, 2, 12, 20),
-    ("l2_up", 3, 256, 0, 128, 256, False, False, 1, 16, 16),
-    ("l2_cat", 1, 128, 128, 128, 256, False, True, 1, 12, 20),
-    ("l3_256_256", 0, 256, 0, 256, 256, False, True, 1, 6, 10),
-    ("l3_pool", 2, 128, 0, 256, 128, False, True, 1, 6, 10),
-    ("l4_512_512", 0, 512, 0, 512, 512, False, True, 1, 3, 5),
-    ("l3_up", 3, 512, 0, 256, 512, False, False, 1, 6, 10),
-    ("l3_cat", 1, 256, 256, 256, 512, False, True, 1, 6, 10),
-    ("many_tiles", 0, 32, 0, 32, 32, False, True, 1, 368, 368),   # > 148 tiles: persistent loop, phases
-    ("many_tiles_l2", 0, 128, 0, 128, 128, False, True, 1, 208, 208),
+def _check(name, y, ref, f32=False, rel=1.0 / 128):
+    assert torch.isfinite(y).all(), f"{name}: non-finite output (unwritten pixels?)"
+    err = (y - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    tol = (3e-5 if f32 else rel) * scale + 1e-5
+    assert err <= tol, f"{name}: max err {err:.4g} (scale {scale:.3g}, tol {tol:.3g})"
+
+
+# ------------------------------------------------------------------ levels >= 1 (NHWC, 9 taps)
+NORMAL_CASES = [
+    # name, cfg, mode, cin(s), cout, act, n, h, w
+    ("l1_pool_s2d", 3, "pool_s2d", 32, 64, True, 1, 24, 40),
+    ("l1_64_64", 4, "plain", 64, 64, True, 1, 24, 40),
+    ("l1_up", 4, "up", 128, 64, False, 1, 32, 32),
+    ("l1_cat", 4, "cat", 64, 64, True, 1, 24, 40),
+    ("l2_pool", 5, "pool", 64, 128, True, 1, 16, 24),
+    ("l2_128_128", 5, "plain", 128, 128, True, 2, 12, 20),
+    ("l2_up", 5, "up", 256, 128, False, 1, 16, 16),
+    ("l2_cat", 5, "cat", 128, 128, True, 1, 12, 20),
+    ("l3_256_256", 5, "plain", 256, 256, True, 1, 6, 10),
+    ("l3_pool", 5, "pool", 128, 256, True, 1, 6, 10),
+    ("l4_512_512", 5, "plain", 512, 512, True, 1, 3, 5),
+    ("l3_up", 5, "up", 512, 256, False, 1, 6, 10),
+    ("l3_cat", 5, "cat", 256, 256, True, 1, 6, 10),
+    ("many_tiles_l1", 4, "plain", 64, 64, True, 1, 184, 184),      # > 148 tiles: persistent loop, phases
+    ("many_tiles_l2", 5, "plain", 128, 128, True, 1, 208, 208),
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv3x3_matches_torch(case):
-    name, mode, c0, c1, cout, cin_true, out_f32, act, n, h, w = case
-    sh, sw = (2 * h, 2 * w) if mode == 2 else (h // 2, w // 2) if mode == 3 else (h, w)
-    src0 = _rand_act(n, sh, sw, c0, 1)
-    if cin_true < c0:                       # packed head input: channels beyond cin_true are zero
-        src0[..., cin_true:] = 0
-    src1 = _rand_act(n, h, w, c1, 2) if mode == 1 else None
-    wgt, b = _rand_wb(cout, cin_true, 3)
-    y = G.conv3x3(src0, src1, mode, n, h, w, wgt, b, act, out_f32, cin_pad=c0 + c1)
-    ref = G.conv3x3_reference(src0, src1, mode, wgt, b, act)
-    assert torch.isfinite(y).all(), f"{name}: non-finite output (unwritten pixels?)"
-    err = (y - ref).abs()
-    scale = ref.abs().max().item()
-    tol = (2e-5 if out_f32 else 1.0 / 128) * max(scale, 1.0) + 1e-5
-    assert err.max().item() <= tol, f"{name}: max err {err.max().item():.4g} (scale {scale:.3g}, tol {tol:.3g})"
+@pytest.mark.parametrize("case", NORMAL_CASES, ids=[c[0] for c in NORMAL_CASES])
+def test_conv_levels_ge1(case):
+    name, cfg, mode, cin, cout, act, n, h, w = case
+    if mode == "plain":
+        x = _rand(n, cin, h, w, 1)
+        wgt, b = _rand_wb(cout, cin, 3)
+        y, _ = G.conv_normal(G.nhwc(x), None, G.SRC_PLAIN, n, h, w, wgt, b, act, cfg)
+        ref = G.reference(x, wgt, b, act)
+    elif mode == "cat":
+        x0, x1 = _rand(n, cin, h, w, 1), _rand(n, cin, h, w, 2)
+        wgt, b = _rand_wb(cout, 2 * cin, 3)
+        y, _ = G.conv_normal(G.nhwc(x0), G.nhwc(x1), G.SRC_CAT, n, h, w, wgt, b, act, cfg)
+        ref = G.reference(torch.cat((x0, x1), 1), wgt, b, act)
+    elif mode == "pool":
+        x = _rand(n, cin, 2 * h, 2 * w, 1)
+        wgt, b = _rand_wb(cout, cin, 3)
+        y, _ = G.conv_normal(G.nhwc(x), None, G.SRC_POOL, n, h, w, wgt, b, act, cfg)
+        ref = G.reference(x, wgt, b, act, pre="pool")
+    elif mode == "pool_s2d":
+        x = _rand(n, cin, 2 * h, 2 * w, 1)
+        wgt, b = _rand_wb(cout, cin, 3)
+        y, _ = G.conv_normal(G.to_s2d(x), None, G.SRC_POOL_S2D, n, h, w, wgt, b, act, cfg)
+        ref = G.reference(x, wgt, b, act, pre="pool")
+    else:
+        x = _rand(n, cin, h // 2, w // 2, 1)
+        wgt, b = _rand_wb(cout, cin, 3)
+        y, _ = G.conv_normal(G.nhwc(x), None, G.SRC_UP, n, h, w, wgt, b, act, cfg)
+        ref = G.reference(x, wgt, b, act, pre="up")
+    _check(name, y, ref)
 
 
+# ------------------------------------------------------------------ level 0 (space-to-depth, 16 entries)
+S2D_CASES = [
+    # name, cfg, mode, cin_true, stored C per phase, cout, act, n, H, W (full-res)
+    ("head6", 0, "plain", 6, 16, 32, True, 1, 64, 128),
+    ("head16_partial", 0, "plain", 16, 16, 32, True, 2, 48, 80),
+    ("l0_32_32", 1, "plain", 32, 32, 32, True, 1, 64, 128),
+    ("l0_32_32_partial", 1, "plain", 32, 32, 32, True, 2, 48, 80),
+    ("l0_cat", 1, "cat", 64, 32, 32, True, 1, 64, 96),
+    ("l0_up_exact", 1, "up", 64, 64, 32, False, 1, 64, 96),
+    ("last4", 2, "plain", 32, 32, 4, False, 1, 64, 128),
+    ("last2", 2, "plain", 32, 32, 2, False, 2, 32, 96),
+    ("last3", 2, "plain", 32, 32, 3, False, 1, 96, 32),
+    ("many_tiles_l0", 1, "plain", 32, 32, 32, True, 1, 368, 368),
+]
+
+
+@pytest.mark.parametrize("case", S2D_CASES, ids=[c[0] for c in S2D_CASES])
+def test_conv_level0_s2d(case):
+    name, cfg, mode, cin, cst, cout, act, n, h, w = case
+    hb, wb = h // 2, w // 2
+    if mode == "plain":
+        x = _rand(n, cst, h, w, 1)
+        if cin < cst:
+            x[:, cin:] = 0                      # packed head input: channels beyond cin are zero
+        wgt, b = _rand_wb(cout, cin, 3)
+        y, _ = G.conv_s2d(G.to_s2d(x), None, G.SRC_PLAIN, n, hb, wb, wgt, b, act, cfg, 1)
+        ref = G.reference(x[:, :cin], wgt, b, act)
+    elif mode == "cat":
+        x0, x1 = _rand(n, 32, h, w, 1), _rand(n, 32, h, w, 2)
+        wgt, b = _rand_wb(cout, 64, 3)
+        y, _ = G.conv_s2d(G.to_s2d(x0), G.to_s2d(x1), G.SRC_CAT, n, hb, wb, wgt, b, act, cfg, 2)
+        ref = G.reference(torch.cat((x0, x1), 1), wgt, b, act)
+    else:                                       # exact bilinear x2 of the level-1 tensor, evaluated per phase
+        x = _rand(n, 64, hb, wb, 1)
+        wgt, b = _rand_wb(cout, 64, 3)
+        y, _ = G.conv_s2d(G.nhwc(x), None, G.SRC_UP_S2D, n, hb, wb, wgt, b, act, cfg, 2)
+        ref = G.reference(x, wgt, b, act, pre="up")
+    _check(name, y, ref, f32=(cfg == 2))
+
+
+# ------------------------------------------------------------------ folded upsample + exact ring
+@pytest.mark.parametrize("level0,cin,cout,n,hc,wc", [(True, 64, 32, 1, 56, 72), (False, 128, 64, 1, 56, 72), (True, 64, 32, 2, 40, 64)],
+                         ids=["fold_l0", "fold_l1", "fold_l0_n2"])
+def test_conv_folded_upsample_with_ring(level0, cin, cout, n, hc, wc):
+    x = _rand(n, cin, hc, wc, 5)
+    wgt, b = _rand_wb(cout, cin, 6)
+    ref = G.reference(x, wgt, b, False, pre="up")
+    y, raw = G.conv_fold(G.nhwc(x), n, hc, wc, wgt, b, level0)
+    # interior: everything but the outermost hi-res ring (where zero padding != the fold's replicate padding)
+    _check("fold interior", y[:, :, 1:-1, 1:-1], ref[:, :, 1:-1, 1:-1])
+    assert (y[:, :, 0] - ref[:, :, 0]).abs().max() > 1e-2, "the ring is expected to differ before the fix-up"
+    # exact transform path on the ring of tiles, written into the same tensor
+    if level0:
+        y2, _ = G.conv_s2d(G.nhwc(x), None, G.SRC_UP_S2D, n, hc, wc, wgt, b, False, G.CFG_L0, 2, ring_only=True, out=raw)
+    else:
+        y2, _ = G.conv_normal(G.nhwc(x), None, G.SRC_UP, n, 2 * hc, 2 * wc, wgt, b, False, G.CFG_L1, ring_only=True, out=raw)
+    _check("fold + ring", y2, ref)
+
+
+# ------------------------------------------------------------------ glue kernels
 def _coef(ts):
     from rrin_b200.engine import time_coefficients
     return time_coefficients(list(ts), len(ts), torch.device("cuda"))
+
+
+def _s2d_f32(x_nchw, c_pad):
+    """[N,C,H,W] fp32 -> [N,H/2,W/2,4,c_pad] fp32 (zero padded channels), on the GPU."""
+    n, c, h, w = x_nchw.shape
+    xp = torch.zeros(n, c_pad, h, w)
+    xp[:, :c] = x_nchw
+    return G.to_s2d(xp.cuda(), torch.float32)
 
 
 def test_glue_kernels_match_oracle_ops():
@@ -90,55 +171,55 @@ def test_glue_kernels_match_oracle_ops():
     logit = torch.randn(n, 2, h, w, generator=g) * 2
     fres = torch.randn(n, 3, h, w, generator=g) * 0.5
     tt = torch.tensor(ts).view(n, 1, 1, 1)
-
-    def nhwc4(x):
-        o = torch.zeros(x.shape[0], h, w, 4)
-        o[..., : x.shape[1]] = x.permute(0, 2, 3, 1)
-        return o.cuda().contiguous()
-
     ad, bd, coef = a.cuda(), b.cuda(), _coef(ts)
-    flow4, res4, logit4, fres4 = nhwc4(flow), nhwc4(res), nhwc4(logit), nhwc4(fres)   # keep alive: raw pointers below
+    flow4, res4, logit4, fres4 = _s2d_f32(flow, 4), _s2d_f32(res, 4), _s2d_f32(logit, 4), _s2d_f32(fres, 4)   # keep alive
     s = G.stream()
+    hb, wb = h // 2, w // 2
+
+    def head(t16):     # bf16 [n,hb,wb,4,16] -> fp32 NCHW [n,16,h,w] on the CPU
+        return G.from_s2d(t16).cpu()
+
     # K6
-    x16 = torch.empty(n, h, w, 16, dtype=torch.bfloat16, device="cuda")
+    x16 = torch.empty(n, hb, wb, 4, 16, dtype=torch.bfloat16, device="cuda")
     check(l.rrin_pack_pair(ad.data_ptr(), bd.data_ptr(), n, h, w, x16.data_ptr(), s))
-    ref = torch.cat((a, b), 1).permute(0, 2, 3, 1)
-    assert torch.equal(x16[..., :6].float().cpu(), G.bf16_round(ref)) and (x16[..., 6:] == 0).all()
+    ref = torch.cat((a, b), 1)
+    assert torch.equal(head(x16)[:, :6], G.bf16_round(ref)) and (head(x16)[:, 6:] == 0).all()
     # K2
     f01, f10 = flow[:, :2], flow[:, 2:4]
     ft0 = -(1 - tt) * tt * f01 + tt * tt * f10
     ft1 = (1 - tt) * (1 - tt) * f01 - tt * (1 - tt) * f10
     r16 = torch.empty_like(x16)
     check(l.rrin_flow_tscale_pack(flow4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w, r16.data_ptr(), s))
-    ref = torch.cat((ft0, ft1, a, b), 1).permute(0, 2, 3, 1)
-    assert (r16[..., :10].float().cpu() - ref).abs().max() <= 2 ** -8 * ref.abs().max() and (r16[..., 10:] == 0).all()
+    ref = torch.cat((ft0, ft1, a, b), 1)
+    assert (head(r16)[:, :10] - ref).abs().max() <= 2 ** -8 * ref.abs().max() and (head(r16)[:, 10:] == 0).all()
     # K3
     ft0r, ft1r = ft0 + res[:, :2], ft1 + res[:, 2:4]
     xt1, xt2 = O.warp(a, ft0r), O.warp(b, ft1r)
     m16 = torch.empty_like(x16)
-    xt8 = torch.empty(n, h, w, 8, device="cuda")
+    xt8 = torch.empty(n, hb, wb, 4, 8, device="cuda")
     check(l.rrin_warp_pack(flow4.data_ptr(), res4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
                            m16.data_ptr(), xt8.data_ptr(), s))
-    xt_ref = torch.cat((xt1, xt2), 1).permute(0, 2, 3, 1)
-    assert (xt8[..., :6].cpu() - xt_ref).abs().max() <= 2e-5, (xt8[..., :6].cpu() - xt_ref).abs().max()
-    assert (xt8[..., 6:] == 0).all()
-    ref = torch.cat((ft0r, ft1r, a, b, xt1, xt2), 1).permute(0, 2, 3, 1)
-    assert (m16.float().cpu() - ref).abs().max() <= 2 ** -8 * ref.abs().max()
+    xt = G.from_s2d(xt8).cpu()
+    xt_ref = torch.cat((xt1, xt2), 1)
+    assert (xt[:, :6] - xt_ref).abs().max() <= 2e-5, (xt[:, :6] - xt_ref).abs().max()
+    assert (xt[:, 6:] == 0).all()
+    ref = torch.cat((ft0r, ft1r, a, b, xt1, xt2), 1)
+    assert (head(m16) - ref).abs().max() <= 2 ** -8 * ref.abs().max()
     # K4
     mask = torch.sigmoid(logit)
     w1, w2 = (1 - tt) * mask[:, 0:1], tt * mask[:, 1:2]
     blend = (w1 * xt1 + w2 * xt2) / (w1 + w2 + 1e-8)
-    out4 = torch.empty(n, h, w, 4, device="cuda")
+    out4 = torch.empty(n, hb, wb, 4, 4, device="cuda")
     f16 = torch.empty_like(x16)
     check(l.rrin_blend_pack(logit4.data_ptr(), xt8.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
                             out4.data_ptr(), f16.data_ptr(), s))
-    assert (out4[..., :3].cpu() - blend.permute(0, 2, 3, 1)).abs().max() <= 3e-5
-    ref = torch.cat((a, b, blend), 1).permute(0, 2, 3, 1)
-    assert (f16[..., :9].float().cpu() - ref).abs().max() <= 2 ** -8 and (f16[..., 9:] == 0).all()
+    assert (G.from_s2d(out4).cpu()[:, :3] - blend).abs().max() <= 3e-5
+    ref = torch.cat((a, b, blend), 1)
+    assert (head(f16)[:, :9] - ref).abs().max() <= 2 ** -8 and (head(f16)[:, 9:] == 0).all()
     # K5
     y = torch.empty(n, 3, h, w, device="cuda")
     check(l.rrin_residue_clamp(fres4.data_ptr(), out4.data_ptr(), n, h, w, y.data_ptr(), s))
-    ref = (fres + out4[..., :3].cpu().permute(0, 3, 1, 2)).clamp(0, 1)
+    ref = (fres + G.from_s2d(out4).cpu()[:, :3]).clamp(0, 1)
     assert (y.cpu() - ref).abs().max() <= 1e-6
     assert ((y == 0) | (y == 1)).float().mean() > 0.05      # the clamp is exercised
 
@@ -149,14 +230,15 @@ def test_glue_multi_t_shares_pair():
     h, w = 16, 32
     ts = [0.25, 0.5, 0.75]
     a, b = O.seeded_frames(1, h, w, seed=9)
-    flow = torch.randn(1, h, w, 4, generator=torch.Generator().manual_seed(1)).cuda()
+    flow = torch.randn(1, 4, h, w, generator=torch.Generator().manual_seed(1))
+    flow4 = _s2d_f32(flow, 4)
     coef = _coef(ts)
     ad, bd = a.cuda(), b.cuda()
-    r16 = torch.empty(3, h, w, 16, dtype=torch.bfloat16, device="cuda")
-    check(l.rrin_flow_tscale_pack(flow.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), 3, 0, h, w, r16.data_ptr(), G.stream()))
+    r16 = torch.empty(3, h // 2, w // 2, 4, 16, dtype=torch.bfloat16, device="cuda")
+    check(l.rrin_flow_tscale_pack(flow4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), 3, 0, h, w, r16.data_ptr(), G.stream()))
     torch.cuda.synchronize()
+    got = G.from_s2d(r16).cpu()
     for i, t in enumerate(ts):
-        f = flow[0].cpu()
-        ft0 = -(1 - t) * t * f[..., :2] + t * t * f[..., 2:]
-        assert (r16[i, ..., :2].float().cpu() - ft0).abs().max() <= 2 ** -8 * ft0.abs().max() + 1e-6
-        assert torch.equal(r16[i, ..., 4:7].float().cpu(), G.bf16_round(a[0].permute(1, 2, 0)))
+        ft0 = -(1 - t) * t * flow[0, :2] + t * t * flow[0, 2:]
+        assert (got[i, :2] - ft0).abs().max() <= 2 ** -8 * ft0.abs().max() + 1e-6
+        assert torch.equal(got[i, 4:7], G.bf16_round(a[0]))
