@@ -100,6 +100,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         : "memory");
 }
 
+// 4-D tiled tensor load through the TMA unit (cp.async.bulk.tensor): box of the tensor map at
+// coordinates {c0 (innermost) .. c3}; out-of-bounds elements are zero-filled; completion is
+// signalled on `bar` as the full box byte count.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
@@ -156,6 +169,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// K-major SWIZZLE_128B descriptor: rows of 128 bytes (64 bf16 of K), the 16-byte chunk index of a row
+// is XOR-ed with address bits [7,10) (absolute shared-memory address, as TMA writes it), 8-row groups
+// SBO bytes apart.  The start address may be offset by whole rows (tap shifts) and by 32-byte K steps;
+// base_offset stays 0 (measured with tools/umma_probe.cu: the hardware swizzles on absolute address bits).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (2ull << 61);
 }
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {

@@ -14,13 +14,17 @@ namespace rrin {
 //  4 : < 64, 64,  64, 2, 3,  9>  level-1 64->64 (weights resident), cat(64+64)->64, exact-upsample ring
 //  5 : < 64, 64, 128, 2, 3,  4>  levels >= 2 (Cout in {128,256,512} as n-tiles of 128) and every
 //                                folded-upsample conv (N = 4*Cout)
+//  6 : <128, 32, 128, 1, 2, 16>  level-0 32->32 with all 16 weight blocks (128 KB) resident: L2 bandwidth is about
+//                                HBM bandwidth on this part, so re-streaming weights per tile costs as much as the
+//                                activations themselves
 #define RRIN_CONV_CONFIGS(X)   \
     X(0, 64, 16, 128, 2, 3, 16) \
     X(1, 128, 32, 128, 2, 2, 5) \
     X(2, 128, 32, 16, 2, 2, 16) \
     X(3, 32, 32, 64, 4, 4, 9)   \
     X(4, 64, 64, 64, 2, 3, 9)   \
-    X(5, 64, 64, 128, 2, 3, 4)
+    X(5, 64, 64, 128, 2, 3, 4)  \
+    X(6, 128, 32, 128, 1, 2, 16)
 
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw; };
 static const CfgInfo kCfg[] = {

@@ -75,7 +75,7 @@ static Schedule build_schedule() {
             m.kind = PACK_S2D; m.sched = SCHED_S2D16;
             if (src == K_HEAD) { m.cfg = 0; m.n_stages = 1; m.n_cols = 128; }
             else if (is_last) { m.cfg = 2; m.n_stages = 1; m.n_cols = 16; }
-            else { m.cfg = 1; m.n_stages = cin / 32; m.n_cols = 128; }          // 32->32, cat(32+32), exact up 64->32
+            else { m.cfg = (cin == 32) ? 6 : 1; m.n_stages = cin / 32; m.n_cols = 128; }   // 32->32 (resident weights); cat(32+32), exact up 64->32
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
             if (level == 1) { m.cfg = (cin == 32) ? 3 : 4; m.n_stages = (cin == 32) ? 1 : cin / 64; }
