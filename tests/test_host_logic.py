@@ -1,0 +1,150 @@
+"""CPU tests of the host-side logic: C-ABI symbols, the parameter tree, sharding (incl. a
+world_size-2 gloo run), the drop-in module and the no-fallback rule."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from rrin_b200 import _lib
+    l = _lib.lib()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(l, s)]
+    assert not missing, missing
+    assert set(_lib._SIGNATURES) == set(syms), set(_lib._SIGNATURES) ^ set(syms)
+    assert l.rrin_num_convs() == 81
+
+
+def test_conv_table_matches_reference_parameter_tree():
+    """rrin_conv_info enumerates exactly the 81 convs of the module tree, with the true shapes."""
+    from rrin_b200 import Net, engine
+    net = Net()
+    sd = net.state_dict()
+    assert len(sd) == 162
+    assert sum(v.numel() for v in sd.values()) == 19_194_445
+    keys = list(sd)
+    order = list(dict.fromkeys(k.split(".")[0] for k in keys))
+    assert order == ["Mask", "Flow", "refine_flow", "final"]             # registration order, model.py:27-30
+    table = engine.conv_table()
+    assert len(table) == 81 and len({t[0] for t in table}) == 81
+    for key, cin, cout, level, src, act in table:
+        assert tuple(sd[key + ".weight"].shape) == (cout, cin, 3, 3), key
+        assert tuple(sd[key + ".bias"].shape) == (cout,), key
+        assert act == (0 if key.endswith("up.1") or key.endswith("last") else 1), key   # unet.py:47,60,63 only
+
+
+def test_net_accepts_optional_level_and_rejects_cpu_inputs():
+    from rrin_b200 import Net
+    Net(3)
+    net = Net()
+    x = torch.rand(1, 3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x, x, 0.5)
+
+
+def test_engine_create_rejects_bad_shapes_without_gpu():
+    import ctypes as C
+    from rrin_b200._lib import lib
+    l = lib()
+    h = C.c_void_p()
+    assert l.rrin_engine_create(1, 1, 72, 80, C.byref(h)) != 0         # 72 % 16 != 0 (reference: torch.cat error)
+    assert b"multiples of 16" in l.rrin_last_error()
+    assert l.rrin_engine_create(2, 3, 64, 64, C.byref(h)) != 0         # n_pairs must be 1 or n_samples
+    assert l.rrin_engine_create(1, 7, 1088, 1920, C.byref(h)) == 0
+    assert l.rrin_engine_num_launches(h) > 81
+    assert l.rrin_engine_workspace_bytes(h) < 8 << 30                  # 7 timesteps of 1080p stay far below 180 GB
+    l.rrin_engine_destroy(h)
+
+
+def test_dropin_module_is_importable_as_model():
+    code = ("import sys; sys.path[:0] = [%r, %r]; from model import Net; import rrin_b200; "
+            "assert Net is rrin_b200.Net; n = Net(); print(len(n.state_dict()))" % (os.path.join(ROOT, "dropin"), ROOT))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "162"
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rrin_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, f)) as fh:
+                    txt = fh.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+    for f in os.listdir(os.path.join(ROOT, "dropin")):
+        if f.endswith(".py"):
+            with open(os.path.join(ROOT, "dropin", f)) as fh:
+                assert "oracle" not in fh.read()
+
+
+# ----------------------------------------------------------------------------- sharding
+def test_pair_ranges_partition_the_clip():
+    from rrin_b200 import sharding as S
+    for n_frames in (0, 1, 2, 3, 7, 240, 241):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [S.pair_range(n_frames, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == max(n_frames - 1, 0)
+            for (a, b), (c, d) in zip(ranges, ranges[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    assert [S.pair_range(240, r, 8) for r in range(8)][0] == (0, 30)      # 239 pairs: 7 shards of 30, one of 29
+    assert S.frame_range(240, 7, 8) == (210, 240)
+    with pytest.raises(ValueError):
+        S.pair_range(10, 2, 2)
+
+
+def test_plan_covers_every_output_frame_once():
+    from rrin_b200 import sharding as S
+    for world in (1, 2, 8):
+        for sf in (1, 3, 7):
+            p = S.plan(25, world, sf)
+            idx = sorted(o for *_, o in p)
+            want = sorted(i for i in range(24 * (sf + 1) + 1) if i % (sf + 1))
+            assert idx == want
+            assert all(abs(t - k / (sf + 1)) < 1e-15 for _, _, k, t, _ in p)
+
+
+def _gloo_worker(rank, world, port, n_frames, q):
+    import torch.distributed as dist
+    from rrin_b200 import sharding as S
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = S.pair_range(n_frames, rank, world)
+    # each rank "interpolates" its pairs: a stand-in result that depends only on the pair index
+    mine = torch.zeros(n_frames - 1, dtype=torch.int64)
+    mine[lo:hi] = torch.arange(lo, hi) * 2 + 1
+    ms = torch.tensor([float(hi - lo)], dtype=torch.float64)            # bench.py's max-over-ranks reduction
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)                         # test-only gather (no collective on the product path)
+    if rank == 0:
+        q.put((mine.tolist(), ms.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shards_reassemble():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_frames = 12
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, ms = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [2 * i + 1 for i in range(n_frames - 1)]
+    assert ms == 6.0                                                    # 11 pairs over 2 ranks: 6 and 5
