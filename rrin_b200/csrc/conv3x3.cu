@@ -1,6 +1,10 @@
 // Host side of K1: configuration table, weight repack (K7: plain / space-to-depth / folded
 // upsample) and launcher for the tcgen05 implicit-GEMM 3x3 convolution (conv3x3.cuh).
 #include "conv3x3.cuh"
+#include "conv3x3_v2.cuh"
+#include <stdlib.h>
+#include <string.h>
+
 #include "rrin_internal.h"
 
 namespace rrin {
@@ -26,22 +30,52 @@ namespace rrin {
     X(5, 64, 64, 128, 2, 3, 4)  \
     X(6, 128, 32, 128, 1, 2, 16)
 
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw; };
-static const CfgInfo kCfg[] = {
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES>
+// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
+// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident
+// 12 : < 64, 32, 128, 4, 2,  6, S2D8 , 0>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
+// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1>  level-0 `last` 32->{2,3,4}, fp32 output
+// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1>  level-1 64->64, weights resident
+// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0>  level-1 cat(64+64)->64
+// 16 : < 64, 64, 128, 4, 2,  4, TAPS9, 0>  levels >= 2 plain / cat, and every weight-folded upsample conv
+#define RRIN_CONV2_CONFIGS(X)          \
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1) \
+    X(11, 64, 32, 128, 1, 4, 16, 2, 1) \
+    X(12, 64, 32, 128, 4, 2, 6, 2, 0)  \
+    X(13, 64, 32, 16, 2, 3, 16, 2, 1)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0)   \
+    X(16, 64, 64, 128, 4, 2, 4, 0, 0)
+
+constexpr int kV2Base = 10;
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res; };
+static const CfgInfo kCfg1[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW, -1, 0},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
-constexpr int kNumCfg = sizeof(kCfg) / sizeof(kCfg[0]);
+static const CfgInfo kCfg2[] = {
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>::PW, SCHED, RES},
+    RRIN_CONV2_CONFIGS(X)
+#undef X
+};
+constexpr int kNumCfg1 = sizeof(kCfg1) / sizeof(kCfg1[0]);
+constexpr int kNumCfg2 = sizeof(kCfg2) / sizeof(kCfg2[0]);
+static bool cfg_valid(int cfg) { return (cfg >= 0 && cfg < kNumCfg1) || (cfg >= kV2Base && cfg < kV2Base + kNumCfg2); }
+static bool cfg_is_v2(int cfg) { return cfg >= kV2Base; }
+static const CfgInfo& cfg_info(int cfg) { return cfg_is_v2(cfg) ? kCfg2[cfg - kV2Base] : kCfg1[cfg]; }
 
-int conv_num_configs() { return kNumCfg; }
+int conv_num_configs() { return kV2Base + kNumCfg2; }
+bool conv_config_valid(int cfg) { return cfg_valid(cfg); }
 int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub) {
-    if (cfg < 0 || cfg >= kNumCfg) return RRIN_ERR_BAD_ARG;
-    if (kcs) *kcs = kCfg[cfg].kcs;
-    if (kb) *kb = kCfg[cfg].kb;
-    if (nt) *nt = kCfg[cfg].nt;
-    if (msub) *msub = kCfg[cfg].msub;
+    if (!cfg_valid(cfg)) return RRIN_ERR_BAD_ARG;
+    const CfgInfo& c = cfg_info(cfg);
+    if (kcs) *kcs = c.kcs;
+    if (kb) *kb = c.kb;
+    if (nt) *nt = c.nt;
+    if (msub) *msub = c.msub;
     return RRIN_OK;
 }
 
@@ -50,6 +84,14 @@ int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub) {
 __host__ __device__ inline void s2d_entry(int e, int& u, int& r, int& v, int& c) {
     const int us[4] = {-1, 0, 0, 1}, ps[4] = {1, 0, 1, 0};
     u = us[e >> 2]; r = ps[e >> 2];
+    v = us[e & 3]; c = ps[e & 3];
+}
+// Half-phase schedule (TMA kernel): a stage holds the two phases of input phase row r; its 8 entries are
+// (row shift option, (column shift, column phase)): r = 0 -> u in {0, +1}, r = 1 -> u in {-1, 0}.
+__host__ __device__ inline void s2d8_entry(int r, int e, int& u, int& v, int& c) {
+    const int us[4] = {-1, 0, 0, 1}, ps[4] = {1, 0, 1, 0};
+    const int yopt = e >> 2;
+    u = (r == 0) ? (yopt ? 1 : 0) : (yopt ? 0 : -1);
     v = us[e & 3]; c = ps[e & 3];
 }
 
@@ -75,10 +117,11 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
         if (kind == PACK_NORMAL) {
             const int ci = st * kcs + k;
             if (ci < cin && col < cout) v = w[((long)col * cin + ci) * 9 + ent];
-        } else if (kind == PACK_S2D) {
-            const int cpp = nt / 4, ph = n / cpp, co = n - ph * cpp, ci = st * kb + k;
-            int u, rr, vv, cc;
-            s2d_entry(ent, u, rr, vv, cc);
+        } else if (kind == PACK_S2D || kind == PACK_S2D8) {
+            const int cpp = nt / 4, ph = n / cpp, co = n - ph * cpp;
+            int u, rr, vv, cc, ci;
+            if (kind == PACK_S2D) { s2d_entry(ent, u, rr, vv, cc); ci = st * kb + k; }
+            else { rr = st & 1; s2d8_entry(rr, ent, u, vv, cc); ci = (st >> 1) * kb + k; }
             const int dy = 2 * u + rr - (ph >> 1), dx = 2 * vv + cc - (ph & 1);
             if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1 && co < cout && ci < cin)
                 v = w[((long)co * cin + ci) * 9 + (dy + 1) * 3 + (dx + 1)];
@@ -96,35 +139,39 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ntiles * nt; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (kind == PACK_NORMAL) { if (i < cout) v = b[i]; }
-        else if (kind == PACK_S2D) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
+        else if (kind == PACK_S2D || kind == PACK_S2D8) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
         else { if (i < 4 * cout) v = b[i % cout]; }
         bp[i] = v;
     }
 }
 
-static int n_ent_of(int sched) { return sched == SCHED_S2D16 ? 16 : 9; }
+static int n_ent_of(int sched) { return sched == SCHED_S2D16 ? 16 : (sched == SCHED_S2D8 ? 8 : 9); }
 
 size_t conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched) {
-    const CfgInfo& c = kCfg[cfg];
+    const CfgInfo& c = cfg_info(cfg);
     const int n_ntiles = (n_cols + c.nt - 1) / c.nt;
     return (size_t)n_ntiles * n_stages * n_ent_of(sched) * c.kb * c.nt * 2;
 }
 int conv_packed_bias_count(int cfg, int n_cols) {
-    const CfgInfo& c = kCfg[cfg];
+    const CfgInfo& c = cfg_info(cfg);
     return ((n_cols + c.nt - 1) / c.nt) * c.nt;
 }
 
 int conv_pack_weights(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
                       void* wpack, float* bias_pack, cudaStream_t stream) {
-    if (cfg < 0 || cfg >= kNumCfg) { set_error("conv_pack_weights: bad config %d", cfg); return RRIN_ERR_BAD_ARG; }
-    const CfgInfo& c = kCfg[cfg];
-    int n_cols, n_ent;
-    if (kind == PACK_NORMAL) { n_cols = cout; n_ent = 9; if (c.kb != c.kcs) { set_error("pack: config %d is space-to-depth only", cfg); return RRIN_ERR_BAD_ARG; } }
-    else if (kind == PACK_S2D) { n_cols = c.nt; n_ent = 16; if (cout > c.nt / 4) { set_error("pack(s2d): cout %d > %d", cout, c.nt / 4); return RRIN_ERR_BAD_SHAPE; } }
-    else if (kind == PACK_FOLD) { n_cols = 4 * cout; n_ent = 9; if (c.kb != c.kcs || (4 * cout) % c.nt) { set_error("pack(fold): bad shape"); return RRIN_ERR_BAD_SHAPE; } }
+    if (!cfg_valid(cfg)) { set_error("conv_pack_weights: bad config %d", cfg); return RRIN_ERR_BAD_ARG; }
+    const CfgInfo& c = cfg_info(cfg);
+    int n_cols, n_ent, kspan;
+    if (kind == PACK_NORMAL) { n_cols = cout; n_ent = 9; kspan = c.kcs; if (c.kb != c.kcs) { set_error("pack: config %d is space-to-depth only", cfg); return RRIN_ERR_BAD_ARG; } }
+    else if (kind == PACK_S2D) { n_cols = c.nt; n_ent = 16; kspan = c.kb; if (cout > c.nt / 4) { set_error("pack(s2d): cout %d > %d", cout, c.nt / 4); return RRIN_ERR_BAD_SHAPE; } }
+    else if (kind == PACK_S2D8) {
+        n_cols = c.nt; n_ent = 8; kspan = c.kb;
+        if (cout > c.nt / 4 || c.kcs != 2 * c.kb || (n_stages & 1)) { set_error("pack(s2d8): bad shape (cout %d, config %d, %d stages)", cout, cfg, n_stages); return RRIN_ERR_BAD_SHAPE; }
+        if (cin > (n_stages / 2) * kspan) { set_error("pack(s2d8): cin %d does not fit %d stage pair(s) of %d", cin, n_stages / 2, kspan); return RRIN_ERR_BAD_SHAPE; }
+    }
+    else if (kind == PACK_FOLD) { n_cols = 4 * cout; n_ent = 9; kspan = c.kcs; if (c.kb != c.kcs || (4 * cout) % c.nt) { set_error("pack(fold): bad shape"); return RRIN_ERR_BAD_SHAPE; } }
     else { set_error("conv_pack_weights: bad kind %d", kind); return RRIN_ERR_BAD_ARG; }
-    const int kspan = (kind == PACK_S2D) ? c.kb : c.kcs;
-    if (n_stages < 1 || cin > n_stages * kspan) { set_error("pack: cin %d does not fit %d stage(s) of %d", cin, n_stages, kspan); return RRIN_ERR_BAD_SHAPE; }
+    if (n_stages < 1 || (kind != PACK_S2D8 && cin > n_stages * kspan)) { set_error("pack: cin %d does not fit %d stage(s) of %d", cin, n_stages, kspan); return RRIN_ERR_BAD_SHAPE; }
     const int n_ntiles = (n_cols + c.nt - 1) / c.nt;
     pack_weights_kernel<<<256, 256, 0, stream>>>(kind, w, b, cout, cin, c.kcs, c.kb, c.nt, n_ntiles, n_stages, n_ent,
                                                  reinterpret_cast<__nv_bfloat16*>(wpack), bias_pack);
@@ -132,9 +179,17 @@ int conv_pack_weights(int kind, const float* w, const float* b, int cout, int ci
     return RRIN_OK;
 }
 
-// ------------------------------------------------------------------ launcher
+// ------------------------------------------------------------------ launchers
 static int g_num_sms = 0;
-static bool g_attr_set[kNumCfg] = {};
+static bool g_attr_set[kV2Base + kNumCfg2] = {};
+
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 0;
+    }
+    return g_num_sms;
+}
 
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
 static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream) {
@@ -149,12 +204,132 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
     return RRIN_OK;
 }
 
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
+static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int grid, cudaStream_t stream) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
+    if (!g_attr_set[id]) {
+        RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        g_attr_set[id] = true;
+    }
+    kern<<<grid, kV2Threads, C::SMEM_BYTES, stream>>>(p, tm0, tm1);
+    RRIN_CUDA_CHECK(cudaGetLastError());
+    return RRIN_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Tensor map of a bf16 NHWC tensor [N,H,W,C] with box {64 ch, pw pixels, 18 rows, 1 image}, SWIZZLE_128B,
+// out-of-bounds elements read as zero (the conv's zero padding).
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, void* tmap_out) {
+    if (!cfg_valid(cfg) || !cfg_is_v2(cfg)) { set_error("conv_make_tmap: config %d is not a TMA config", cfg); return RRIN_ERR_BAD_ARG; }
+    if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || C % 64 || N <= 0 || H <= 0 || W <= 0) {
+        set_error("conv_make_tmap: bad tensor (C=%d must be a multiple of 64, base 16-byte aligned)", C);
+        return RRIN_ERR_BAD_SHAPE;
+    }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return RRIN_ERR_UNSUPPORTED; }
+    const CfgInfo& c = cfg_info(cfg);
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, N, H, W, C); return RRIN_ERR_CUDA; }
+    return RRIN_OK;
+}
+
+static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
+    const int cfg = d.cfg;
+    const CfgInfo& c = cfg_info(cfg);
+    if (d.mode != SRC_PLAIN && d.mode != SRC_CAT) { set_error("conv3x3(tma): source mode %d needs the transform kernel", d.mode); return RRIN_ERR_BAD_ARG; }
+    if (d.pad_clamp) { set_error("conv3x3(tma): replicate padding is not available (TMA zero-fills)"); return RRIN_ERR_BAD_ARG; }
+    if (d.ring_only) { set_error("conv3x3(tma): ring_only is not available"); return RRIN_ERR_BAD_ARG; }
+    const int ctot = d.c0 + (d.mode == SRC_CAT ? d.c1 : 0);
+    if (d.c0 % 64 || (d.mode == SRC_CAT && d.c1 % 64) || ctot % c.kcs) { set_error("conv3x3(tma): %d(+%d) stored channels not a multiple of 64 / stage width %d", d.c0, d.c1, c.kcs); return RRIN_ERR_BAD_SHAPE; }
+    ConvParamsV2 p{};
+    p.c0_chunks = d.c0 / 64;
+    p.N = d.N; p.H = d.H; p.W = d.W;
+    p.n_stages = ctot / c.kcs;
+    if (d.sched != c.sched) { set_error("conv3x3(tma): config %d runs schedule %d, not %d", cfg, c.sched, d.sched); return RRIN_ERR_BAD_ARG; }
+    if (d.sched == SCHED_S2D8 && (p.n_stages & 1)) { set_error("conv3x3(tma): the half-phase schedule needs an even number of 64-channel chunks"); return RRIN_ERR_BAD_SHAPE; }
+    if (d.sched == SCHED_S2D16 && p.n_stages != 1) { set_error("conv3x3(tma): the packed-head schedule takes exactly 64 stored channels"); return RRIN_ERR_BAD_SHAPE; }
+    if (d.n_cols <= 0 || d.n_cols % c.nt || d.n_cols > 512) { set_error("conv3x3(tma): %d GEMM columns (NT=%d)", d.n_cols, c.nt); return RRIN_ERR_BAD_SHAPE; }
+    p.n_ntiles = d.n_cols / c.nt;
+    p.wpack = reinterpret_cast<const __nv_bfloat16*>(d.wpack);
+    p.bias = d.bias;
+    p.out = d.out; p.epi = d.epi; p.cout_stride = d.cout_stride; p.act = d.act;
+    if (d.epi == EPI_F32X16 && c.nt != 16) { set_error("conv3x3: fp32 epilogue needs NT=16"); return RRIN_ERR_BAD_ARG; }
+    if (d.epi == EPI_SCATTER && (d.cout_stride % 32 || d.n_cols != 4 * d.cout_stride)) { set_error("conv3x3: bad scatter epilogue shape"); return RRIN_ERR_BAD_SHAPE; }
+    if (d.epi == EPI_BF16 && d.cout_stride < d.n_cols) { set_error("conv3x3: cout_stride %d < columns %d", d.cout_stride, d.n_cols); return RRIN_ERR_BAD_SHAPE; }
+    p.tiles_y = (d.H + kTileH - 1) / kTileH;
+    p.sx = (d.W + 7) / 8;
+    const long upn = (long)d.N * p.tiles_y * p.sx, total = upn * p.n_ntiles;
+    if (total > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
+    p.units_per_nt = (int)upn; p.total_units = (int)total;
+    if (c.res && (p.n_ntiles != 1 || p.n_stages * n_ent_of(d.sched) > c.sb)) {
+        set_error("conv3x3(tma): config %d keeps its weights resident: %d stage(s) x %d columns do not fit", cfg, p.n_stages, d.n_cols);
+        return RRIN_ERR_BAD_SHAPE;
+    }
+    CUtensorMap tm0, tm1;
+    if (d.tmap0) memcpy(&tm0, d.tmap0, sizeof tm0);
+    else if (int r = conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, &tm0)) return r;
+    if (d.mode == SRC_CAT) {
+        if (d.tmap1) memcpy(&tm1, d.tmap1, sizeof tm1);
+        else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, &tm1)) return r;
+    } else tm1 = tm0;
+    const int sms = num_sms();
+    if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
+    // at least one full-size tile per CTA when the launch is small
+    const long want = (total + c.msub - 1) / c.msub;
+    const int grid = (int)(want < sms ? (want > 0 ? want : 1) : sms);
+    // diagnostics only: RRIN_CONV_PROF=1 prints block 0's per-role wait cycles after every launch (synchronises)
+    static const bool prof_on = getenv("RRIN_CONV_PROF") != nullptr;
+    static unsigned long long* prof_buf = nullptr;
+    if (prof_on) {
+        if (!prof_buf) RRIN_CUDA_CHECK(cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long)));
+        RRIN_CUDA_CHECK(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), stream));
+        p.prof = prof_buf;
+    }
+    int rc = RRIN_ERR_BAD_ARG;
+    switch (cfg) {
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>(id, p, tm0, tm1, grid, stream); break;
+        RRIN_CONV2_CONFIGS(X)
+#undef X
+    }
+    if (prof_on && rc == RRIN_OK) {
+        unsigned long long h[16];
+        RRIN_CUDA_CHECK(cudaStreamSynchronize(stream));
+        RRIN_CUDA_CHECK(cudaMemcpy(h, prof_buf, sizeof h, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[conv prof cfg %d %dx%dx%d nst %d ent %d nt %d] block0: tiles %llu stages %llu | tma total %llu wait_empty %llu | "
+                        "mma total %llu wait_a %llu wait_b %llu wait_acc %llu | epi total %llu wait_full %llu\n",
+                cfg, d.N, d.H, d.W, p.n_stages, n_ent_of(d.sched), p.n_ntiles, h[7], h[2], h[1], h[0], h[6], h[3], h[4], h[5], h[9], h[8]);
+    }
+    return rc;
+}
+
 int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     const int cfg = d.cfg;
-    if (cfg < 0 || cfg >= kNumCfg) { set_error("conv3x3: bad config id %d", cfg); return RRIN_ERR_BAD_ARG; }
-    const CfgInfo& c = kCfg[cfg];
+    if (!cfg_valid(cfg)) { set_error("conv3x3: bad config id %d", cfg); return RRIN_ERR_BAD_ARG; }
+    const CfgInfo& c = cfg_info(cfg);
     if (d.N <= 0 || d.H <= 0 || d.W <= 0) { set_error("conv3x3: empty shape %dx%dx%d", d.N, d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
     if (d.mode < 0 || d.mode > SRC_UP_S2D || !d.src0 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
+    if (cfg_is_v2(cfg)) return conv_launch_v2(d, stream);
+    if (d.sched == SCHED_S2D8) { set_error("conv3x3: the half-phase schedule needs a TMA config"); return RRIN_ERR_BAD_ARG; }
     if (d.sched == SCHED_TAPS9 && c.kb != c.kcs) { set_error("conv3x3: config %d needs the space-to-depth schedule", cfg); return RRIN_ERR_BAD_ARG; }
     ConvParams p{};
     p.src0 = reinterpret_cast<const __nv_bfloat16*>(d.src0);
@@ -202,12 +377,9 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (work > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
     p.total_work = (int)work;
     p.b_resident = (p.n_ntiles == 1 && p.n_stages * p.n_ent <= c.sb) ? 1 : 0;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        RRIN_CUDA_CHECK(cudaGetDevice(&dev));
-        RRIN_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const int grid = p.total_work < g_num_sms ? p.total_work : g_num_sms;
+    const int sms = num_sms();
+    if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
+    const int grid = p.total_work < sms ? p.total_work : sms;
     switch (cfg) {
 #define X(id, KCS, KB, NT, MSUB, SA, SB) case id: return launch_cfg<KCS, KB, NT, MSUB, SA, SB>(id, p, grid, stream);
         RRIN_CONV_CONFIGS(X)

@@ -1,0 +1,373 @@
+// K1 (TMA-fed variant): 3x3 convolution + bias + optional LeakyReLU(0.1) as an implicit GEMM on
+// tcgen05 tensor cores with BOTH operands delivered by the TMA unit.
+//
+// Same GEMM view as conv3x3.cuh, used for every conv whose A operand is a stored tensor as-is
+// (plain, cat(up, skip), the packed head inputs, and the weight-folded upsample convs):
+//   nn.Conv2d (unet.py:29,38,59,62,78) + LeakyReLU (unet.py:47,60,63) + torch.cat (unet.py:93).
+//
+// Differences to conv3x3.cuh:
+//   * A operand: one cp.async.bulk.tensor (4-D tiled TMA, SWIZZLE_128B, out-of-bounds = zero = the
+//     conv's zero padding) per 64-channel chunk loads the whole halo tile
+//     [18 rows][8*MSUB+2 pixels][64 ch] -- no per-pixel address arithmetic in any warp.  A tap is a
+//     descriptor start offset of whole 128-byte rows; a K step is +32 bytes inside the swizzled row
+//     (the hardware swizzles on absolute shared-memory address bits, tools/umma_probe.cu).
+//   * work split: the (n-tile, row band, 8-pixel column group) units are divided EVENLY over the
+//     CTAs; each CTA cuts its contiguous unit range into tiles of 1..MSUB sub-tiles, so a launch
+//     finishes within one sub-tile of perfect balance instead of a whole-tile wave tail.
+//   * TMEM: the 512 columns form 512/NT accumulator slots used round-robin, one per sub-tile, each
+//     with its own full/empty mbarrier: the epilogue drains slot by slot while the MMA warp already
+//     refills the freed ones (MSUB=4, NT=128 uses all 512 columns and still overlaps).
+//   * space-to-depth level-0 tensors (4 phases x 32 ch = 128 ch per block pixel) are consumed as two
+//     64-channel stages; stage parity = input phase row r, 8 (block shift, phase) entries each.
+//
+// Warp roles (224 threads, 1 CTA / SM, persistent): warps 0-3 epilogue, warp 4 MMA issue,
+// warp 5 weight blocks (cp.async.bulk), warp 6 activation halo tiles (cp.async.bulk.tensor).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv3x3.cuh"
+#include "rrin_internal.h"
+
+namespace rrin {
+
+struct ConvParamsV2 {
+    int c0_chunks;               // 64-channel chunks taken from tensor map 0 (the rest from map 1: cat)
+    int N, H, W;                 // conv grid
+    int n_stages;                // 64-channel-chunk groups per tile (KCS channels each)
+    const __nv_bfloat16* wpack;  // [n_ntiles][n_stages][n_ent][KB/8][NT][8]
+    const float* bias;
+    void* out;
+    int epi, cout_stride, act;
+    int n_ntiles;
+    int tiles_y;                 // row bands per image
+    int sx;                      // 8-pixel column groups per band
+    int units_per_nt;            // N * tiles_y * sx
+    int total_units;             // n_ntiles * units_per_nt
+    unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
+};
+
+constexpr int kV2Threads = 7 * 32;
+
+// SCHED: 0 nine taps | 1 sixteen (block shift, phase) entries over one 64-channel chunk holding 4 phases x 16 ch (packed heads)
+//        | 2 half-phase: chunk parity = input phase row r, eight entries per chunk (level-0 tensors, 4 phases x 32 ch)
+// RES  : all n_stages * n_ent weight blocks stay resident in shared memory (loaded once per CTA)
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
+struct ConvCfgV2 {
+    static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
+    static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
+    static constexpr int BOX_BYTES = (kTileH + 2) * PW * 128;
+    static constexpr int BOX_STRIDE = (BOX_BYTES + 1023) / 1024 * 1024;
+    static constexpr int A_STAGE = BOXES * BOX_STRIDE;
+    static constexpr int B_BLOCK = NT * KB * 2;
+    static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
+    static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
+    static constexpr int BIAS_MAX = 512;
+    static constexpr int OFF_B = SA * A_STAGE;
+    static constexpr int OFF_BIAS = OFF_B + SB * B_BLOCK;
+    static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
+    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS;
+    static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
+    static_assert(KCS == 64, "one 64-channel TMA box per stage");
+    static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+    static_assert((SCHED == 0 && KB == 64) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
+    static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32, "accumulator slots");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    // A-descriptor start offset (16-byte units) of entry e; `parity` = stage & 1 (half-phase schedule only)
+    __host__ __device__ static constexpr int us(int i) { return (i + 1) / 2 - 1; }     // {-1, 0, 0, 1}
+    __host__ __device__ static constexpr int ps(int i) { return (i + 1) & 1; }         // { 1, 0, 1, 0}
+    __host__ __device__ static constexpr uint32_t ent_off(int parity, int e) {
+        if (SCHED == 0) return ((e / 3) * PW + (e % 3)) * 8;
+        if (SCHED == 1) return ((us(e >> 2) + 1) * PW + (us(e & 3) + 1)) * 8 + (ps(e >> 2) * 2 + ps(e & 3)) * (KB * 2 / 16);
+        return (((parity == 0 ? (e >> 2) : (e >> 2) - 1) + 1) * PW + (us(e & 3) + 1)) * 8 + ps(e & 3) * (KB * 2 / 16);
+    }
+};
+
+struct TileV2 { int nt, n, ty, sx0, m; };
+
+// The CTA's share of the work units and its cursor; every warp role walks the identical sequence.
+struct TileWalkV2 {
+    int u, u_end;
+    __device__ __forceinline__ void init(const ConvParamsV2& p) {
+        u = (int)((long long)p.total_units * blockIdx.x / gridDim.x);
+        u_end = (int)((long long)p.total_units * (blockIdx.x + 1) / gridDim.x);
+    }
+    template <int MSUB>
+    __device__ __forceinline__ bool next(const ConvParamsV2& p, TileV2& t) {
+        if (u >= u_end) return false;
+        t.nt = u / p.units_per_nt;
+        int r = u - t.nt * p.units_per_nt;
+        const int band = r / p.sx;
+        t.sx0 = r - band * p.sx;
+        t.n = band / p.tiles_y;
+        t.ty = band - t.n * p.tiles_y;
+        t.m = min(MSUB, min(p.sx - t.sx0, u_end - u));
+        u += t.m;
+        return true;
+    }
+};
+
+// tcgen05.mma with the 64-bit descriptors given as (lo, hi) halves: only the low words (start address) change
+// between MMAs of a tile, so the issue loop is 32-bit adds on uniform registers.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
+__global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
+                                                                     const __grid_constant__ CUtensorMap tm0,
+                                                                     const __grid_constant__ CUtensorMap tm1) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
+    constexpr int N_ENT = C::N_ENT;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
+    uint8_t* smem = smem_raw + (s_base - smem_u32(smem_raw));
+    const uint32_t s_a = s_base;
+    const uint32_t s_b = s_base + C::OFF_B;
+    float* bias_s = reinterpret_cast<float*>(smem + C::OFF_BIAS);
+    const uint32_t s_bar = s_base + C::OFF_BAR;
+    auto a_full = [&](int i) { return s_bar + 8u * i; };
+    auto a_empty = [&](int i) { return s_bar + 8u * (SA + i); };
+    auto b_full = [&](int i) { return s_bar + 8u * (2 * SA + i); };
+    auto b_empty = [&](int i) { return s_bar + 8u * (2 * SA + SB + i); };
+    auto acc_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + i); };
+    auto acc_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + C::SLOTS + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nst = p.n_stages;
+    const int nblk = nst * N_ENT;
+
+    // ---------------- one-time setup
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps * 32); }
+        mbar_fence_init();
+    }
+    if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); }
+    for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
+    if (warp == 4) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    TileWalkV2 walk;
+    walk.init(p);
+    TileV2 t;
+    const bool prof = p.prof != nullptr && blockIdx.x == 0;
+
+    if (warp == 6) {
+        // =========================================================== activation halo tiles (TMA), one elected thread
+        if (elect_one()) {
+            int it = 0;
+            long long tw = 0, t00 = clock64();
+            while (walk.next<MSUB>(p, t)) {
+                const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;          // halo origin; OOB -> zero fill
+                for (int st = 0; st < nst; ++st, ++it) {
+                    const int stage = it % SA;
+                    const long long c0 = prof ? clock64() : 0;
+                    mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
+                    if (prof) tw += clock64() - c0;
+                    mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
+                    const bool first = st < p.c0_chunks;
+                    tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n, a_full(stage));
+                }
+            }
+            if (prof) { p.prof[0] = tw; p.prof[1] = clock64() - t00; p.prof[2] = it; }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // =========================================================== weight blocks (bulk copies), one elected thread
+        if (elect_one()) {
+            if (RES) {
+                for (int b = 0; b < nblk; ++b) {
+                    mbar_arrive_expect_tx(b_full(b), C::B_BLOCK);
+                    bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KB), C::B_BLOCK, b_full(b));
+                }
+            } else {
+                int cnt = 0;
+                while (walk.next<MSUB>(p, t)) {
+                    const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);
+                    for (int b = 0; b < nblk; ++b, ++cnt) {
+                        const int slot = cnt % SB;
+                        mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_full(slot), C::B_BLOCK);
+                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), C::B_BLOCK, b_full(slot));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
+        // =========================================================== MMA issuer: ONE elected thread runs the whole role
+        // (no per-entry warp re-convergence; entries, K steps and their descriptor offsets are compile-time)
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            const uint64_t a_desc0 = make_smem_desc_sw128(0, C::PW * 128);
+            const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0 + (s_b >> 4);
+            int it = 0, cnt = 0, slot0 = 0, ntile = 0;
+            uint32_t use_bits = 0;                      // bit s: parity of the number of finished uses of slot s
+            long long twa = 0, twb = 0, twc = 0, t00 = clock64();
+            while (walk.next<MSUB>(p, t)) {
+                const int m = t.m;
+                for (int st = 0; st < nst; ++st, ++it) {
+                    const int stage = it % SA;
+                    { const long long c0 = prof ? clock64() : 0;
+                      mbar_wait(a_full(stage), (it / SA) & 1);
+                      if (prof) twa += clock64() - c0; }
+                    tc_fence_after();
+                    const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
+                    const int par = (SCHED == 2) ? (st & 1) : 0;
+#pragma unroll
+                    for (int e = 0; e < N_ENT; ++e) {
+                        int slot;
+                        if (RES) {
+                            slot = st * N_ENT + e;
+                            if (ntile == 0) { mbar_wait(b_full(slot), 0); tc_fence_after(); }
+                        } else {
+                            slot = cnt % SB;
+                            const long long c0 = prof ? clock64() : 0;
+                            mbar_wait(b_full(slot), (cnt / SB) & 1);
+                            if (prof) twb += clock64() - c0;
+                            tc_fence_after();
+                            ++cnt;
+                        }
+                        const uint32_t a_e = a_st + (par ? C::ent_off(1, e) : C::ent_off(0, e));
+                        const uint32_t b_e = b_lo0 + ((slot * C::B_BLOCK) >> 4);
+#pragma unroll 1
+                        for (int j = 0; j < m; ++j) {
+                            const int ts = (slot0 + j) % C::SLOTS;
+                            if (e == 0 && st == 0) {    // first write into this accumulator slot: the epilogue must have drained it
+                                const long long c0 = prof ? clock64() : 0;
+                                mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
+                                tc_fence_after();
+                                if (prof) twc += clock64() - c0;
+                            }
+#pragma unroll
+                            for (int s = 0; s < KB / 16; ++s)
+                                umma_bf16_lh(tmem_base + ts * NT, a_e + j * 64 + s * 2, a_hi, b_e + s * (2 * NT), b_hi, idesc,
+                                             (e | s) != 0 || st != 0);
+                        }
+                        if (!RES) umma_commit(b_empty(slot));
+                    }
+                    umma_commit(a_empty(stage));
+                }
+                for (int j = 0; j < m; ++j) {
+                    const int ts = (slot0 + j) % C::SLOTS;
+                    umma_commit(acc_full(ts));
+                    use_bits ^= 1u << ts;
+                }
+                slot0 = (slot0 + m) % C::SLOTS;
+                ++ntile;
+            }
+            if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; }
+        }
+        __syncwarp();
+    } else if (warp < kEpiWarps) {
+        // =========================================================== epilogue (warps 0-3)
+        const int mrow = warp * 32 + lane;              // accumulator row == TMEM lane
+        const int ly = mrow >> 3, lx = mrow & 7;
+        int slot0 = 0;
+        uint32_t use_bits = 0;
+        long long twf = 0, t00 = clock64();
+        while (walk.next<MSUB>(p, t)) {
+            const int gy = t.ty * kTileH + ly;
+            const float* bsrc = bias_s + t.nt * NT;
+#pragma unroll 1
+            for (int j = 0; j < t.m; ++j) {
+                const int ts = (slot0 + j) % C::SLOTS;
+                { const long long c0 = prof ? clock64() : 0;
+                  mbar_wait(acc_full(ts), (use_bits >> ts) & 1);
+                  if (prof) twf += clock64() - c0; }
+                tc_fence_after();
+                const int gx = (t.sx0 + j) * 8 + lx;
+                const bool ok = (gy < p.H) && (gx < p.W);
+                const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
+                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + ts * NT;
+                if (NT == 16) {                          // fp32 [.,16] epilogue of the `last` convs
+                    uint32_t r16[16];
+                    tmem_ld16(t0, r16);
+                    tmem_ld_wait();
+                    if (ok) {
+                        float4* o4 = reinterpret_cast<float4*>(p.out) + pix * 4;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            o4[q] = make_float4(__uint_as_float(r16[4 * q]) + bsrc[4 * q], __uint_as_float(r16[4 * q + 1]) + bsrc[4 * q + 1],
+                                                __uint_as_float(r16[4 * q + 2]) + bsrc[4 * q + 2], __uint_as_float(r16[4 * q + 3]) + bsrc[4 * q + 3]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < NT; c += 32) {
+                        uint32_t ra[16], rb[16];
+                        tmem_ld16(t0 + c, ra);
+                        tmem_ld16(t0 + c + 16, rb);
+                        tmem_ld_wait();
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float v0 = __uint_as_float(ra[2 * i]) + bsrc[c + 2 * i];
+                            float v1 = __uint_as_float(ra[2 * i + 1]) + bsrc[c + 2 * i + 1];
+                            if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
+                            o[i] = pack_bf16x2(v0, v1);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float v0 = __uint_as_float(rb[2 * i]) + bsrc[c + 16 + 2 * i];
+                            float v1 = __uint_as_float(rb[2 * i + 1]) + bsrc[c + 16 + 2 * i + 1];
+                            if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
+                            o[8 + i] = pack_bf16x2(v0, v1);
+                        }
+                        if (ok) {
+                            __nv_bfloat16* op;
+                            if (p.epi == EPI_SCATTER) {
+                                // folded upsample: global column g = (a, b, co); pixel (2y+a, 2x+b) of the hi-res NHWC tensor
+                                const int g = t.nt * NT + c, cs = p.cout_stride;
+                                const int ph = g / cs, co = g - ph * cs;
+                                const size_t hp = ((size_t)(t.n * 2 * p.H + 2 * gy + (ph >> 1)) * (2 * p.W) + 2 * gx + (ph & 1));
+                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + hp * cs + co;
+                            } else {
+                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout_stride + t.nt * NT + c;
+                            }
+                            uint4* o4 = reinterpret_cast<uint4*>(op);
+                            o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                            o4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                            o4[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(ts));
+            }
+            for (int j = 0; j < t.m; ++j) use_bits ^= 1u << ((slot0 + j) % C::SLOTS);
+            slot0 = (slot0 + t.m) % C::SLOTS;
+        }
+        if (prof && threadIdx.x == 0) { p.prof[8] = twf; p.prof[9] = clock64() - t00; }
+    }
+
+    // ---------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace rrin

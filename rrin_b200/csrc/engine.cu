@@ -71,20 +71,25 @@ static Schedule build_schedule() {
         L.key = std::string(kUNets[u].name) + "." + key;
         L.unet = u; L.cin = cin; L.cout = cout; L.level = level; L.src = src; L.act = act; L.is_last = is_last;
         Pack& m = L.main;
-        if (level == 0) {                       // space-to-depth schedule, 4 phases x cout columns
-            m.kind = PACK_S2D; m.sched = SCHED_S2D16;
-            if (src == K_HEAD) { m.cfg = 0; m.n_stages = 1; m.n_cols = 128; }
-            else if (is_last) { m.cfg = 2; m.n_stages = 1; m.n_cols = 16; }
-            else { m.cfg = (cin == 32) ? 6 : 1; m.n_stages = cin / 32; m.n_cols = 128; }   // 32->32 (resident weights); cat(32+32), exact up 64->32
+        // configs 0..6: transform kernel (conv3x3.cuh: pool / bilinear sources, exact border ring);
+        // configs 10..16: TMA-fed kernel (conv3x3_v2.cuh: every source that is a stored tensor as-is)
+        if (level == 0) {                       // space-to-depth: 4 phases x cout columns on the half-res grid
+            m.n_cols = is_last ? 16 : 128;
+            if (src == K_HEAD) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 10; m.n_stages = 1; }
+            else if (src == K_UP) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 1; m.n_stages = cin / 32; }   // exact bilinear (ring / small frames)
+            else { m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? 13 : (cin == 32 ? 11 : 12); m.n_stages = 2 * (cin / 32); }
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
-            if (level == 1) { m.cfg = (cin == 32) ? 3 : 4; m.n_stages = (cin == 32) ? 1 : cin / 64; }
-            else { m.cfg = 5; m.n_stages = cin / 64; }
+            const bool xform = (src == K_POOL || src == K_UP);
+            if (level == 1) {
+                if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }
+                else { m.cfg = xform ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
+            } else { m.cfg = xform ? 5 : 16; m.n_stages = cin / 64; }
         }
         place(m);
         if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns
             Pack& f = L.fold;
-            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = 5; f.n_stages = cin / 64; f.n_cols = 4 * cout;
+            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = 16; f.n_stages = cin / 64; f.n_cols = 4 * cout;
             place(f);
         }
         s.layers.push_back(L);
@@ -131,6 +136,7 @@ struct Launch {
     int layer = -1;          // conv: index into schedule().layers
     int use_fold = 0;        // conv: which Pack
     ConvDesc cd;             // pointers hold workspace OFFSETS (+1 so that 0 stays "null") until launch
+    alignas(64) unsigned char tmap[2][128];   // TMA configs: tensor maps of src0 / src1, encoded for `tmap_ws`
     std::string name;
     double flops = 0, bytes = 0;
 };
@@ -145,6 +151,7 @@ struct rrin_engine {
     size_t ws_bytes;
     size_t off_tmp[3], off_skip[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
     std::vector<Launch> launches;
+    const void* tmap_ws = nullptr;              // workspace base the cached tensor maps were encoded for
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every launch
     int prof_n = 0;
 };
@@ -180,7 +187,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
         int kcs, kb, nt, msub;
         conv_config_info(ln.cd.cfg, &kcs, &kb, &nt, &msub);
         char b[128];
-        snprintf(b, sizeof b, "conv3x3_umma<KCS%d,KB%d,NT%d,MSUB%d>%s", kcs, kb, nt, msub, tag);
+        snprintf(b, sizeof b, "conv3x3_%s<KCS%d,KB%d,NT%d,MSUB%d>%s", ln.cd.cfg >= 10 ? "tma" : "umma", kcs, kb, nt, msub, tag);
         ln.name = b;
         const double lp = (double)B * (H >> L.level) * (W >> L.level);      // output pixels of the reference conv
         if (counts_flops) {
@@ -227,8 +234,8 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
         const int ui = (cur + 1) % 3, vi = (cur + 2) % 3;
         // up.1 (no activation): input tmp[cur] is the level lvl+1 tensor with 2c channels
         if (lvl <= 1 && fold_ok) {
-            Launch f = base(li, 1, lvl + 1);          // folded: runs on the coarse grid, replicate padding
-            f.cd.mode = SRC_PLAIN; f.cd.pad_clamp = 1; f.cd.c0 = 2 * c;
+            Launch f = base(li, 1, lvl + 1);          // folded: runs on the coarse grid; its outermost 2 hi-res pixels are
+            f.cd.mode = SRC_PLAIN; f.cd.c0 = 2 * c;   // wrong (zero fill instead of the reference border) and rewritten by the ring
             f.cd.src0 = enc(tmp[cur]); f.cd.out = enc(tmp[ui]);
             if (lvl == 1) { f.cd.epi = EPI_SCATTER; f.cd.cout_stride = c; }
             else { f.cd.epi = EPI_BF16; f.cd.cout_stride = 128; }     // (phase, co) columns == space-to-depth pixel
@@ -363,6 +370,16 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
     float* xt8 = reinterpret_cast<float*>(ws + e->off_xt8);
     const int H = e->H, W = e->W, Np = e->Np, Nt = e->Nt, pm = e->pair_mul;
     auto dec = [&](const void* p) -> void* { return p ? ws + (reinterpret_cast<size_t>(p) - 1) : nullptr; };
+    if (e->tmap_ws != workspace) {                                // (re-)encode the TMA tensor maps for this workspace
+        for (Launch& ln : e->launches) {
+            if (ln.glue >= 0 || ln.cd.cfg < 10) continue;
+            const ConvDesc& c = ln.cd;
+            int r = conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, ln.tmap[0]);
+            if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, ln.tmap[1]);
+            if (r != RRIN_OK) return r;
+        }
+        e->tmap_ws = workspace;
+    }
     mark(e, st);                                                  // t0
     for (const Launch& ln : e->launches) {
         int r = RRIN_OK;
@@ -381,6 +398,7 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out);
             cd.wpack = blob + pk.w_off;
             cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
+            if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; }
             r = conv_launch(cd, st);
         }
         if (r != RRIN_OK) return r;
@@ -439,11 +457,11 @@ int rrin_engine_tap(const rrin_engine* e, const void* workspace, int which, floa
 // ------------------------------------------------------------------ unit-level wrappers
 int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub) { return conv_config_info(cfg, kcs, kb, nt, msub); }
 size_t rrin_conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched) {
-    if (cfg < 0 || cfg >= conv_num_configs()) return 0;
+    if (!conv_config_valid(cfg)) return 0;
     return conv_packed_weight_bytes(cfg, n_cols, n_stages, sched);
 }
 int rrin_conv_packed_bias_count(int cfg, int n_cols) {
-    if (cfg < 0 || cfg >= conv_num_configs()) return 0;
+    if (!conv_config_valid(cfg)) return 0;
     return conv_packed_bias_count(cfg, n_cols);
 }
 int rrin_pack_conv_raw(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg, void* wpack,

@@ -20,8 +20,8 @@ enum ConvEpilogue : int {
     EPI_F32X16 = 1,    // fp32 [N,H,W,16]   (space-to-depth `last` conv: 4 phases x 4 classes)
     EPI_SCATTER = 2,   // folded upsample: column (a,b,co) -> bf16 NHWC [N,2H,2W,cout_stride] at (2y+a,2x+b)
 };
-enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1 };
-enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2 };
+enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1, SCHED_S2D8 = 2 };   // S2D8: half-phase stages of the TMA kernel
+enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3 };
 
 // One 3x3 convolution launch (see conv3x3.cuh for the data layouts).
 struct ConvDesc {
@@ -41,9 +41,14 @@ struct ConvDesc {
     int act = 0;
     int ring_only = 0;
     int cfg = -1;
+    const void* tmap0 = nullptr;  // TMA configs: pre-encoded CUtensorMap (128 bytes, host memory) of src0 / src1, or null
+    const void* tmap1 = nullptr;
 };
 
 int conv_num_configs();
+bool conv_config_valid(int cfg);
+// TMA configs (id >= 10): encode the tensor map of a bf16 NHWC source [N,H,W,C] (C % 64 == 0) into tmap_out (128 bytes, host)
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, void* tmap_out);
 int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
 // packed sizes for a layer: n_cols GEMM columns, n_stages*n_ent weight blocks of KB x NT
 size_t conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);

@@ -10,9 +10,12 @@ from rrin_b200._lib import check, lib
 
 SRC_PLAIN, SRC_CAT, SRC_POOL, SRC_UP, SRC_POOL_S2D, SRC_UP_S2D = range(6)
 EPI_BF16, EPI_F32X16, EPI_SCATTER = range(3)
-SCHED_TAPS9, SCHED_S2D16 = 0, 1
-PACK_NORMAL, PACK_S2D, PACK_FOLD = 0, 1, 2
+SCHED_TAPS9, SCHED_S2D16, SCHED_S2D8 = 0, 1, 2
+PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8 = 0, 1, 2, 3
+# transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
+# TMA-fed kernel (conv3x3_v2.cuh)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG = range(10, 17)
 
 
 def stream():
@@ -49,7 +52,7 @@ def pack(kind, cfg, weight, bias, n_stages, sched):
     l = lib()
     cout, cin = weight.shape[:2]
     _, _, nt, _ = cfg_info(cfg)
-    n_cols = {PACK_NORMAL: cout, PACK_S2D: nt, PACK_FOLD: 4 * cout}[kind]
+    n_cols = {PACK_NORMAL: cout, PACK_S2D: nt, PACK_S2D8: nt, PACK_FOLD: 4 * cout}[kind]
     n_cols = (n_cols + nt - 1) // nt * nt
     wp = torch.zeros(l.rrin_conv_packed_weight_bytes(cfg, n_cols, n_stages, sched), dtype=torch.uint8, device="cuda")
     bp = torch.zeros(l.rrin_conv_packed_bias_count(cfg, n_cols), dtype=torch.float32, device="cuda")
@@ -81,36 +84,42 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
 
 
 def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring_only=False, out=None):
-    """Level 0: space-to-depth sources [N,hb,wb,4,C] (or NHWC [N,hb,wb,C] for SRC_UP_S2D), 16-entry schedule.
+    """Level 0: space-to-depth sources [N,hb,wb,4,C] (or NHWC [N,hb,wb,C] for SRC_UP_S2D), 16-entry schedule
+    (half-phase 8-entry schedule with twice the stages for the TMA configs 11..13).
     Returns hi-res NCHW fp32 [N,cout,2hb,2wb] and the raw output tensor."""
     kcs, kb, nt, _ = cfg_info(cfg)
     cout = weight.shape[0]
     c0 = src0.shape[-1] * (src0.shape[-2] if src0.dim() == 5 else 1)
     c1 = (src1.shape[-1] * src1.shape[-2]) if src1 is not None else 0
-    wp, bp, n_cols = pack(PACK_S2D, cfg, weight, bias, n_stages, SCHED_S2D16)
+    half = cfg in (T_L0, T_L0CAT, T_LAST)
+    kind, sched = (PACK_S2D8, SCHED_S2D8) if half else (PACK_S2D, SCHED_S2D16)
+    if half:
+        n_stages *= 2
+    wp, bp, n_cols = pack(kind, cfg, weight, bias, n_stages, sched)
     f32 = (nt == 16)
     cpp = nt // 4
     if out is None:
         out = torch.full((n, hb, wb, 4, cpp), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
-    launch(src0, src1, c0, c1, mode, 0, n, hb, wb, SCHED_S2D16, n_cols, wp, bp, out, EPI_F32X16 if f32 else EPI_BF16,
+    launch(src0, src1, c0, c1, mode, 0, n, hb, wb, sched, n_cols, wp, bp, out, EPI_F32X16 if f32 else EPI_BF16,
            16 if f32 else nt, act, ring_only, cfg)
     return from_s2d(out)[:, :cout], out
 
 
 def conv_fold(src, n, hc, wc, weight, bias, level0, out=None):
-    """Folded bilinear-x2 + conv: src NHWC bf16 [N,hc,wc,cin] (coarse); output hi-res [2hc,2wc].
-    level0=True -> output is space-to-depth [N,hc,wc,4,cout]; else NHWC [N,2hc,2wc,cout] via the scatter epilogue."""
-    kcs, kb, nt, _ = cfg_info(CFG_BIG)
+    """Folded bilinear-x2 + conv on the TMA kernel: src NHWC bf16 [N,hc,wc,cin] (coarse, zero-filled halo); output
+    hi-res [2hc,2wc].  level0=True -> output is space-to-depth [N,hc,wc,4,cout]; else NHWC [N,2hc,2wc,cout] via the
+    scatter epilogue.  The outermost 2 hi-res pixels differ from the reference (fixed by the exact ring pass)."""
+    kcs, kb, nt, _ = cfg_info(T_BIG)
     cout, cin = weight.shape[:2]
-    wp, bp, n_cols = pack(PACK_FOLD, CFG_BIG, weight, bias, cin // kcs, SCHED_TAPS9)
+    wp, bp, n_cols = pack(PACK_FOLD, T_BIG, weight, bias, cin // kcs, SCHED_TAPS9)
     if level0:
         if out is None:
             out = torch.full((n, hc, wc, 4, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-        launch(src, None, cin, 0, SRC_PLAIN, 1, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, CFG_BIG)
+        launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, T_BIG)
         return from_s2d(out), out
     if out is None:
         out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    launch(src, None, cin, 0, SRC_PLAIN, 1, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, CFG_BIG)
+    launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, T_BIG)
     return out.float().permute(0, 3, 1, 2), out
 
 
