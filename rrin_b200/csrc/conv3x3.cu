@@ -30,34 +30,34 @@ namespace rrin {
     X(5, 64, 64, 128, 2, 3, 4)  \
     X(6, 128, 32, 128, 1, 2, 16)
 
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES>
-// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
-// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident
-// 12 : < 64, 32, 128, 4, 2,  6, S2D8 , 0>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
-// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1>  level-0 `last` 32->{2,3,4}, fp32 output
-// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1>  level-1 64->64, weights resident
-// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 4, 2,  4, TAPS9, 0>  levels >= 2 plain / cat, and every weight-folded upsample conv
-#define RRIN_CONV2_CONFIGS(X)          \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1) \
-    X(11, 64, 32, 128, 1, 4, 16, 2, 1) \
-    X(12, 64, 32, 128, 4, 2, 6, 2, 0)  \
-    X(13, 64, 32, 16, 2, 3, 16, 2, 1)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0)   \
-    X(16, 64, 64, 128, 4, 2, 4, 0, 0)
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>
+// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
+// 11 : < 64, 32, 128, 1, 3, 16, S2D8 , 1, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident
+// 12 : < 64, 32, 128, 4, 2,  6, S2D8 , 0, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
+// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0>  level-0 `last` 32->{2,3,4}, fp32 output
+// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1>  level-1 64->64, weights resident
+// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1>  level-1 cat(64+64)->64
+// 16 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0>  levels >= 2 plain / cat, and every weight-folded upsample conv
+#define RRIN_CONV2_CONFIGS(X)             \
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1) \
+    X(11, 64, 32, 128, 1, 3, 16, 2, 1, 1) \
+    X(12, 64, 32, 128, 4, 2, 6, 2, 0, 1)  \
+    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1)   \
+    X(16, 64, 64, 128, 4, 2, 4, 0, 0, 0)
 
 constexpr int kV2Base = 10;
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma; };
 static const CfgInfo kCfg1[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW, -1, 0},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW, -1, 0, 0},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>::PW, SCHED, RES},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>::PW, SCHED, RES, ETMA},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -204,15 +204,16 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
     return RRIN_OK;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
-static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, int grid, cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
+static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo, int grid,
+                       cudaStream_t stream) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
     if (!g_attr_set[id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    kern<<<grid, kV2Threads, C::SMEM_BYTES, stream>>>(p, tm0, tm1);
+    kern<<<grid, kV2Threads, C::SMEM_BYTES, stream>>>(p, tm0, tm1, tmo);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
@@ -232,9 +233,10 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// Tensor map of a bf16 NHWC tensor [N,H,W,C] with box {64 ch, pw pixels, 18 rows, 1 image}, SWIZZLE_128B,
-// out-of-bounds elements read as zero (the conv's zero padding).
-int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, void* tmap_out) {
+// Tensor map of a bf16 NHWC tensor [N,H,W,C], SWIZZLE_128B.  which = 0: source of the A operand, box {64 ch, PW pixels,
+// 18 rows, 1 image}, out-of-bounds elements read as zero (the conv's zero padding); which = 1: epilogue destination,
+// box {64 ch, 8 pixels, 4 rows, 1 image} (one epilogue warp's share of a sub-tile), out-of-bounds elements not written.
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out) {
     if (!cfg_valid(cfg) || !cfg_is_v2(cfg)) { set_error("conv_make_tmap: config %d is not a TMA config", cfg); return RRIN_ERR_BAD_ARG; }
     if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || C % 64 || N <= 0 || H <= 0 || W <= 0) {
         set_error("conv_make_tmap: bad tensor (C=%d must be a multiple of 64, base 16-byte aligned)", C);
@@ -245,13 +247,16 @@ int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, void* 
     const CfgInfo& c = cfg_info(cfg);
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
+    const cuuint32_t box_in[4] = {64, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
+    const cuuint32_t box_out[4] = {64, 8, 4, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                    which ? box_out : box_in, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, N, H, W, C); return RRIN_ERR_CUDA; }
     return RRIN_OK;
 }
+bool conv_config_tma_epilogue(int cfg) { return cfg_valid(cfg) && cfg_info(cfg).etma != 0; }
 
 static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const int cfg = d.cfg;
@@ -285,13 +290,18 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
         set_error("conv3x3(tma): config %d keeps its weights resident: %d stage(s) x %d columns do not fit", cfg, p.n_stages, d.n_cols);
         return RRIN_ERR_BAD_SHAPE;
     }
-    CUtensorMap tm0, tm1;
+    CUtensorMap tm0, tm1, tmo;
     if (d.tmap0) memcpy(&tm0, d.tmap0, sizeof tm0);
-    else if (int r = conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, &tm0)) return r;
+    else if (int r = conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, 0, &tm0)) return r;
     if (d.mode == SRC_CAT) {
         if (d.tmap1) memcpy(&tm1, d.tmap1, sizeof tm1);
-        else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, &tm1)) return r;
+        else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, 0, &tm1)) return r;
     } else tm1 = tm0;
+    if (c.etma) {
+        if (d.epi != EPI_BF16 || d.cout_stride % 64) { set_error("conv3x3(tma): config %d stores bf16 NHWC with a multiple of 64 channels per pixel", cfg); return RRIN_ERR_BAD_ARG; }
+        if (d.tmap_out) memcpy(&tmo, d.tmap_out, sizeof tmo);
+        else if (int r = conv_make_tmap(d.out, d.N, d.H, d.W, d.cout_stride, cfg, 1, &tmo)) return r;
+    } else tmo = tm0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
     // at least one full-size tile per CTA when the launch is small
@@ -307,7 +317,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     int rc = RRIN_ERR_BAD_ARG;
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>(id, p, tm0, tm1, grid, stream); break;
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>(id, p, tm0, tm1, tmo, grid, stream); break;
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }

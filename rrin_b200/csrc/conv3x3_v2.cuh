@@ -52,7 +52,9 @@ constexpr int kV2Threads = 7 * 32;
 // SCHED: 0 nine taps | 1 sixteen (block shift, phase) entries over one 64-channel chunk holding 4 phases x 16 ch (packed heads)
 //        | 2 half-phase: chunk parity = input phase row r, eight entries per chunk (level-0 tensors, 4 phases x 32 ch)
 // RES  : all n_stages * n_ent weight blocks stay resident in shared memory (loaded once per CTA)
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
+// ETMA : bf16 NHWC epilogue through swizzled shared-memory staging + TMA tensor stores (full-line writes,
+//        edge clipping by the TMA unit) instead of per-thread 16-byte global stores
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
 struct ConvCfgV2 {
     static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
@@ -64,11 +66,14 @@ struct ConvCfgV2 {
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;
-    static constexpr int OFF_BIAS = OFF_B + SB * B_BLOCK;
+    static constexpr int EPI_STAGE = ETMA ? kEpiWarps * 4096 : 0;      // per warp: 32 pixels x 64 channels bf16, SWIZZLE_128B
+    static constexpr int OFF_EPI = OFF_B + SB * B_BLOCK;                // 1024-byte aligned (A stages and weight blocks are)
+    static constexpr int OFF_BIAS = OFF_EPI + EPI_STAGE;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
     static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS;
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
     static_assert(KCS == 64, "one 64-channel TMA box per stage");
+    static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
     static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert((SCHED == 0 && KB == 64) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
     static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32, "accumulator slots");
@@ -121,11 +126,12 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uin
         : "memory");
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
 __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
-                                                                     const __grid_constant__ CUtensorMap tm1) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES>;
+                                                                     const __grid_constant__ CUtensorMap tm1,
+                                                                     const __grid_constant__ CUtensorMap tmo) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
     constexpr int N_ENT = C::N_ENT;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps * 32); }
         mbar_fence_init();
     }
-    if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); }
+    if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); }
     for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
     if (warp == 4) {
         tmem_alloc(smem_u32(tmem_slot), 512);
@@ -300,7 +306,52 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + ts * NT;
-                if (NT == 16) {                          // fp32 [.,16] epilogue of the `last` convs
+                if constexpr (ETMA != 0) {
+                    // bf16 NHWC via this warp's 4 KB staging buffer (32 pixels x 128 B, 16-byte chunk k of row r at
+                    // k ^ (r & 7)) and one TMA tensor store per 64 columns; the box {64 ch, 8 px, 4 rows} is clipped
+                    // at the tensor edges by the TMA unit, so partial tiles need no masks.
+                    const uint32_t stg = s_base + C::OFF_EPI + warp * 4096;
+#pragma unroll 1
+                    for (int c = 0; c < NT; c += 64) {
+                        uint32_t o[32];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t ra[16], rb[16];
+                            tmem_ld16(t0 + c + 32 * h, ra);
+                            tmem_ld16(t0 + c + 32 * h + 16, rb);
+                            tmem_ld_wait();
+                            const float4* b4 = reinterpret_cast<const float4*>(bsrc + c + 32 * h);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 ba = b4[i], bb = b4[4 + i];
+                                float v[8] = {__uint_as_float(ra[4 * i]) + ba.x, __uint_as_float(ra[4 * i + 1]) + ba.y,
+                                              __uint_as_float(ra[4 * i + 2]) + ba.z, __uint_as_float(ra[4 * i + 3]) + ba.w,
+                                              __uint_as_float(rb[4 * i]) + bb.x, __uint_as_float(rb[4 * i + 1]) + bb.y,
+                                              __uint_as_float(rb[4 * i + 2]) + bb.z, __uint_as_float(rb[4 * i + 3]) + bb.w};
+                                if (p.act) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) v[q] = v[q] >= 0.f ? v[q] : 0.1f * v[q];
+                                }
+                                o[16 * h + 2 * i] = pack_bf16x2(v[0], v[1]);
+                                o[16 * h + 2 * i + 1] = pack_bf16x2(v[2], v[3]);
+                                o[16 * h + 8 + 2 * i] = pack_bf16x2(v[4], v[5]);
+                                o[16 * h + 8 + 2 * i + 1] = pack_bf16x2(v[6], v[7]);
+                            }
+                        }
+                        if (lane == 0) bulk_wait_group_read<0>();       // the previous store has finished reading the buffer
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg + lane * 128 + ((k ^ (lane & 7)) << 4)),
+                                         "r"(o[4 * k]), "r"(o[4 * k + 1]), "r"(o[4 * k + 2]), "r"(o[4 * k + 3]) : "memory");
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * warp, t.n);
+                            bulk_commit_group();
+                        }
+                    }
+                } else if (NT == 16) {                   // fp32 [.,16] epilogue of the `last` convs
                     uint32_t r16[16];
                     tmem_ld16(t0, r16);
                     tmem_ld_wait();
@@ -358,6 +409,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
             for (int j = 0; j < t.m; ++j) use_bits ^= 1u << ((slot0 + j) % C::SLOTS);
             slot0 = (slot0 + t.m) % C::SLOTS;
         }
+        if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed
         if (prof && threadIdx.x == 0) { p.prof[8] = twf; p.prof[9] = clock64() - t00; }
     }
 

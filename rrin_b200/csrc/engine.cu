@@ -136,7 +136,7 @@ struct Launch {
     int layer = -1;          // conv: index into schedule().layers
     int use_fold = 0;        // conv: which Pack
     ConvDesc cd;             // pointers hold workspace OFFSETS (+1 so that 0 stays "null") until launch
-    alignas(64) unsigned char tmap[2][128];   // TMA configs: tensor maps of src0 / src1, encoded for `tmap_ws`
+    alignas(64) unsigned char tmap[3][128];   // TMA configs: tensor maps of src0 / src1 / out, encoded for `tmap_ws`
     std::string name;
     double flops = 0, bytes = 0;
 };
@@ -374,8 +374,9 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
         for (Launch& ln : e->launches) {
             if (ln.glue >= 0 || ln.cd.cfg < 10) continue;
             const ConvDesc& c = ln.cd;
-            int r = conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, ln.tmap[0]);
-            if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, ln.tmap[1]);
+            int r = conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, 0, ln.tmap[0]);
+            if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, 0, ln.tmap[1]);
+            if (r == RRIN_OK && conv_config_tma_epilogue(c.cfg)) r = conv_make_tmap(dec(c.out), c.N, c.H, c.W, c.cout_stride, c.cfg, 1, ln.tmap[2]);
             if (r != RRIN_OK) return r;
         }
         e->tmap_ws = workspace;
@@ -398,7 +399,7 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out);
             cd.wpack = blob + pk.w_off;
             cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
-            if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; }
+            if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; cd.tmap_out = ln.tmap[2]; }
             r = conv_launch(cd, st);
         }
         if (r != RRIN_OK) return r;

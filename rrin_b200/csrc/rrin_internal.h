@@ -43,12 +43,15 @@ struct ConvDesc {
     int cfg = -1;
     const void* tmap0 = nullptr;  // TMA configs: pre-encoded CUtensorMap (128 bytes, host memory) of src0 / src1, or null
     const void* tmap1 = nullptr;
+    const void* tmap_out = nullptr; // TMA-epilogue configs: pre-encoded map of `out`, or null
 };
 
 int conv_num_configs();
 bool conv_config_valid(int cfg);
-// TMA configs (id >= 10): encode the tensor map of a bf16 NHWC source [N,H,W,C] (C % 64 == 0) into tmap_out (128 bytes, host)
-int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, void* tmap_out);
+// TMA configs (id >= 10): encode the tensor map of a bf16 NHWC tensor [N,H,W,C] (C % 64 == 0) into tmap_out (128 bytes, host);
+// which = 0: A-operand source (halo box), 1: epilogue destination (one warp's 8x4-pixel box)
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out);
+bool conv_config_tma_epilogue(int cfg);
 int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
 // packed sizes for a layer: n_cols GEMM columns, n_stages*n_ent weight blocks of KB x NT
 size_t conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);
