@@ -37,7 +37,8 @@ namespace rrin {
 // 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0>  level-0 `last` 32->{2,3,4}, fp32 output
 // 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1>  level-1 64->64, weights resident
 // 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0>  levels >= 2 plain / cat, and every weight-folded upsample conv
+// 16 : < 64, 64, 128, 4, 2,  3, TAPS9, 0, 1>  levels >= 2 plain / cat, folded upsample conv writing level 0
+// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0>  same tile, per-thread stores: folded upsample conv scattering into level 1
 #define RRIN_CONV2_CONFIGS(X)             \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1) \
     X(11, 64, 32, 128, 1, 3, 16, 2, 1, 1) \
@@ -45,7 +46,8 @@ namespace rrin {
     X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0)  \
     X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1)   \
     X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1)   \
-    X(16, 64, 64, 128, 4, 2, 4, 0, 0, 0)
+    X(16, 64, 64, 128, 4, 2, 3, 0, 0, 1)  \
+    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0)
 
 constexpr int kV2Base = 10;
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma; };
@@ -340,7 +342,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (d.mode < 0 || d.mode > SRC_UP_S2D || !d.src0 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
     if (cfg_is_v2(cfg)) return conv_launch_v2(d, stream);
     if (d.sched == SCHED_S2D8) { set_error("conv3x3: the half-phase schedule needs a TMA config"); return RRIN_ERR_BAD_ARG; }
-    if (d.sched == SCHED_TAPS9 && c.kb != c.kcs) { set_error("conv3x3: config %d needs the space-to-depth schedule", cfg); return RRIN_ERR_BAD_ARG; }
+    if ((d.sched == SCHED_TAPS9) != (c.kb == c.kcs)) { set_error("conv3x3: config %d runs the %s schedule", cfg, c.kb == c.kcs ? "9-tap" : "space-to-depth"); return RRIN_ERR_BAD_ARG; }
     ConvParams p{};
     p.src0 = reinterpret_cast<const __nv_bfloat16*>(d.src0);
     p.src1 = reinterpret_cast<const __nv_bfloat16*>(d.src1);

@@ -348,47 +348,62 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
         }
     } else if (warp == 4) {
         // =========================================================== MMA issuer
-        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform
-        // registers); one elected lane issues the tcgen05 instructions.
-        constexpr uint32_t idesc = make_idesc_bf16(128, NT);
-        const uint64_t a_desc0 = make_smem_desc(0, C::PS, C::PW * 16);
-        const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
-        const int n_ent = p.n_ent;
-        int it = 0, cnt = 0, tcount = 0;
-        for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-            const int buf = tcount & 1;
-            mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
-            const uint32_t d0 = tmem_base + buf * (MSUB * NT);
-            for (int st = 0; st < nst; ++st, ++it) {
-                const int stage = it % SA;
-                mbar_wait(a_full(stage), (it / SA) & 1);
-                const uint32_t a_stage = s_a + stage * C::A_STAGE;
-#pragma unroll 1
-                for (int e = 0; e < n_ent; ++e, ++cnt) {
-                    int slot;
-                    if (p.b_resident) { slot = st * n_ent + e; if (tcount == 0) mbar_wait(b_full(slot), 0); }
-                    else { slot = cnt % SB; mbar_wait(b_full(slot), (cnt / SB) & 1); }
+        // ONE elected thread runs the whole role: entries, K steps and their descriptor offsets are compile-time, the
+        // descriptors' high words are constants, so an MMA costs a couple of 32-bit adds on top of its issue slot.
+        if (elect_one()) {
+            constexpr bool S2D = (KB != KCS);
+            constexpr int N_ENT = S2D ? 16 : 9;
+            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            const uint64_t a_desc0 = make_smem_desc(0, C::PS, C::PW * 16);
+            const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0 + (s_b >> 4);
+            const bool resident = p.b_resident != 0;
+            int it = 0, cnt = 0, tcount = 0;
+            for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
+                const int buf = tcount & 1;
+                mbar_wait(acc_empty(buf), ((tcount >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * (MSUB * NT);
+                for (int st = 0; st < nst; ++st, ++it) {
+                    const int stage = it % SA;
+                    mbar_wait(a_full(stage), (it / SA) & 1);
                     tc_fence_after();
-                    const uint64_t a_ent = a_desc0 + ((a_stage >> 4) + p.ent_off[e]);
-                    const uint64_t b_blk = b_desc0 + ((s_b + slot * C::B_BLOCK) >> 4);
-                    if (elect_one()) {
+                    const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
+#pragma unroll
+                    for (int e = 0; e < N_ENT; ++e) {
+                        int slot;
+                        if (resident) {
+                            slot = st * N_ENT + e;
+                            if (tcount == 0) { mbar_wait(b_full(slot), 0); tc_fence_after(); }
+                        } else {
+                            slot = cnt % SB;
+                            mbar_wait(b_full(slot), (cnt / SB) & 1);
+                            tc_fence_after();
+                            ++cnt;
+                        }
+                        // entry -> descriptor start offset (16-byte units): tap (dy,dx) pixel shift, or (block shift, input phase plane)
+                        constexpr int us[4] = {-1, 0, 0, 1}, ps[4] = {1, 0, 1, 0};
+                        const uint32_t eoff = S2D ? (uint32_t)((us[(e >> 2) & 3] + 1) * C::PW + (us[e & 3] + 1) +
+                                                               (ps[(e >> 2) & 3] * 2 + ps[e & 3]) * (KB / 8) * (C::PS / 16))
+                                                  : (uint32_t)((e / 3) * C::PW + (e % 3));
+                        const uint32_t a_e = a_st + eoff;
+                        const uint32_t b_e = b_lo0 + ((slot * C::B_BLOCK) >> 4);
 #pragma unroll
                         for (int j = 0; j < MSUB; ++j) {
 #pragma unroll
                             for (int s = 0; s < KB / 16; ++s)
-                                umma_bf16(d0 + j * NT, a_ent + ((j * 128 + 2 * s * C::PS) >> 4), b_blk + ((2 * s * (NT * 16)) >> 4),
-                                          idesc, (st | e | s) != 0);
+                                umma_bf16_lh(d0 + j * NT, a_e + ((j * 128 + 2 * s * C::PS) >> 4), a_hi, b_e + s * (2 * NT), b_hi, idesc,
+                                             (e | s) != 0 || st != 0);
                         }
-                        if (!p.b_resident) umma_commit(b_empty(slot));
-                        if (e == n_ent - 1) {
-                            umma_commit(a_empty(stage));
-                            if (st == nst - 1) umma_commit(acc_full(buf));
-                        }
+                        if (!resident) umma_commit(b_empty(slot));
                     }
-                    __syncwarp();
+                    umma_commit(a_empty(stage));
+                    if (st == nst - 1) umma_commit(acc_full(buf));
                 }
             }
         }
+        __syncwarp();
     } else {
         // =========================================================== epilogue (warps 0-3)
         const int m = warp * 32 + lane;                 // accumulator row == TMEM lane

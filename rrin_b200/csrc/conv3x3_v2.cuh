@@ -112,20 +112,6 @@ struct TileWalkV2 {
     }
 };
 
-// tcgen05.mma with the 64-bit descriptors given as (lo, hi) halves: only the low words (start address) change
-// between MMAs of a tile, so the issue loop is 32-bit adds on uniform registers.
-__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                             uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
 __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
@@ -205,6 +191,17 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                     bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KB), C::B_BLOCK, b_full(b));
                 }
             } else {
+                // The layer's weights are cold in L2 at launch and every CTA walks the same block sequence, so each
+                // block would be a DRAM-latency miss for everyone: spread one L2 prefetch of the whole packed layer
+                // over the CTAs first (each takes a 16 KB-granular slice).
+                {
+                    const size_t total = (size_t)p.n_ntiles * nblk * C::B_BLOCK, gran = 16384;
+                    const size_t nchunk = (total + gran - 1) / gran;
+                    for (size_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+                        const size_t off = ch * gran;
+                        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.wpack) + off, (uint32_t)min(gran, total - off));
+                    }
+                }
                 int cnt = 0;
                 while (walk.next<MSUB>(p, t)) {
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);

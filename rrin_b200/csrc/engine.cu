@@ -8,6 +8,7 @@
 //   level l >= 1 (32*2^l channels): bf16 NHWC [N, H/2^l, W/2^l, C].
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -57,6 +58,12 @@ struct Schedule {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// diagnostics: RRIN_BIG_CFG=17 selects the per-thread-store variant of the levels >= 2 tile (A/B timing runs)
+static int big_cfg() {
+    const char* e = getenv("RRIN_BIG_CFG");
+    return (e && atoi(e) == 17) ? 17 : 16;
+}
+
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
@@ -84,12 +91,12 @@ static Schedule build_schedule() {
             if (level == 1) {
                 if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }
                 else { m.cfg = xform ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
-            } else { m.cfg = xform ? 5 : 16; m.n_stages = cin / 64; }
+            } else { m.cfg = xform ? 5 : big_cfg(); m.n_stages = cin / 64; }
         }
         place(m);
         if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns
             Pack& f = L.fold;
-            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = 16; f.n_stages = cin / 64; f.n_cols = 4 * cout;
+            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = (level == 0) ? 16 : 17; f.n_stages = cin / 64; f.n_cols = 4 * cout;   // 17: scatter epilogue
             place(f);
         }
         s.layers.push_back(L);

@@ -15,7 +15,7 @@ PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8 = 0, 1, 2, 3
 # transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 # TMA-fed kernel (conv3x3_v2.cuh)
-T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG = range(10, 17)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER = range(10, 18)
 
 
 def stream():
@@ -119,7 +119,7 @@ def conv_fold(src, n, hc, wc, weight, bias, level0, out=None):
         return from_s2d(out), out
     if out is None:
         out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, T_BIG)
+    launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, T_BIG_SCATTER)
     return out.float().permute(0, 3, 1, 2), out
 
 
