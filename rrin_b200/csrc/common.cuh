@@ -38,6 +38,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of a forward is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may start
+// (and run their prologue: barrier init, TMEM allocation, resident weight loads) while the previous kernel drains.
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible: it must precede the first
+// access to any activation buffer.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

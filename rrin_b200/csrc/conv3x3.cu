@@ -201,8 +201,7 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    kern<<<grid, kConvThreads, C::SMEM_BYTES, stream>>>(p);
-    RRIN_CUDA_CHECK(cudaGetLastError());
+    RRIN_CUDA_CHECK(launch_pdl(kern, grid, kConvThreads, C::SMEM_BYTES, stream, p));
     return RRIN_OK;
 }
 
@@ -215,8 +214,7 @@ static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, co
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    kern<<<grid, kV2Threads, C::SMEM_BYTES, stream>>>(p, tm0, tm1, tmo);
-    RRIN_CUDA_CHECK(cudaGetLastError());
+    RRIN_CUDA_CHECK(launch_pdl(kern, grid, kV2Threads, C::SMEM_BYTES, stream, p, tm0, tm1, tmo));
     return RRIN_OK;
 }
 

@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (warp != 5) pdl_wait();        // activations (reads and writes) only after the previous kernel has finished; weights are constant
 
     if (warp >= 6) {
         // =========================================================== producers: halo tiles

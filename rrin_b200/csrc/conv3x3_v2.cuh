@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (warp != 5) pdl_wait();        // activations (reads and writes) only after the previous kernel has finished; weights are constant
 
     TileWalkV2 walk;
     walk.init(p);

@@ -28,6 +28,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("RRIN_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // ------------------------------------------------------------------ static schedule
 enum SrcKind { K_PLAIN = 0, K_CAT = 1, K_POOL = 2, K_UP = 3, K_HEAD = 4 };
 

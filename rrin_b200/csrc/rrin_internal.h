@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <utility>
+
 namespace rrin {
 
 // How the conv's A operand (halo tile on the conv grid [H,W]) is formed from stored tensors.
@@ -45,6 +47,20 @@ struct ConvDesc {
     const void* tmap1 = nullptr;
     const void* tmap_out = nullptr; // TMA-epilogue configs: pre-encoded map of `out`, or null
 };
+
+// Launch with programmatic stream serialization (see common.cuh: pdl_wait / pdl_launch_dependents).
+// RRIN_PDL=0 in the environment falls back to plain stream order (A/B timing).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 int conv_num_configs();
 bool conv_config_valid(int cfg);
