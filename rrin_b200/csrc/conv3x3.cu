@@ -30,24 +30,26 @@ namespace rrin {
     X(5, 64, 64, 128, 2, 3, 4)  \
     X(6, 128, 32, 128, 1, 2, 16)
 
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>
-// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
-// 11 : < 64, 32, 128, 1, 3, 16, S2D8 , 1, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident
-// 12 : < 64, 32, 128, 4, 2,  6, S2D8 , 0, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
-// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0>  level-0 `last` 32->{2,3,4}, fp32 output
-// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1>  level-1 64->64, weights resident
-// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 4, 2,  3, TAPS9, 0, 1>  levels >= 2 plain / cat, folded upsample conv writing level 0
-// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0>  same tile, per-thread stores: folded upsample conv scattering into level 1
-#define RRIN_CONV2_CONFIGS(X)             \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1) \
-    X(11, 64, 32, 128, 1, 3, 16, 2, 1, 1) \
-    X(12, 64, 32, 128, 4, 2, 6, 2, 0, 1)  \
-    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1)   \
-    X(16, 64, 64, 128, 4, 2, 3, 0, 0, 1)  \
-    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0)
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>
+// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
+// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
+// 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
+// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0, 1>  level-0 `last` 32->{2,3,4}, fp32 output
+// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1>  level-1 64->64, weights resident
+// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1>  level-1 cat(64+64)->64
+// 16 : < 64, 64, 128, 4, 2,  3, TAPS9, 0, 1, 1>  levels >= 2 plain / cat
+// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0, 1>  same tile, per-thread stores: folded upsample conv scattering into level 1
+// 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
+#define RRIN_CONV2_CONFIGS(X)                \
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2) \
+    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2) \
+    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2)  \
+    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 1)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1)   \
+    X(16, 64, 64, 128, 4, 2, 3, 0, 0, 1, 1)  \
+    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0, 1)  \
+    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)
 
 constexpr int kV2Base = 10;
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma; };
@@ -58,8 +60,8 @@ static const CfgInfo kCfg1[] = {
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>::PW, SCHED, RES, ETMA},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::PW, SCHED, RES, ETMA},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -127,6 +129,18 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
             const int dy = 2 * u + rr - (ph >> 1), dx = 2 * vv + cc - (ph & 1);
             if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1 && co < cout && ci < cin)
                 v = w[((long)co * cin + ci) * 9 + (dy + 1) * 3 + (dx + 1)];
+            if (kind == PACK_S2D8 && nt == 128) {
+                // half entries (conv3x3_v2.cuh): a +-1 row block shift feeds one output phase row only -> the block is
+                // stored compactly as [KB/8][64][8] (first half of its slot) for an N = 64 MMA
+                const int hf = (rr == 0) ? ((ent >> 2) == 1 ? 2 : 0) : ((ent >> 2) == 0 ? 1 : 0);
+                if (hf) {
+                    const int lo = (hf == 2) ? 64 : 0;
+                    if (n < lo || n >= lo + 64) continue;
+                    const long blk = i - (((long)k8 * nt + n) * 8 + e8);
+                    wp[blk + ((long)k8 * 64 + (n - lo)) * 8 + e8] = __float2bfloat16_rn(v);
+                    continue;
+                }
+            }
         } else {  // PACK_FOLD
             const int ph = col / cout, co = col - ph * cout, ci = st * kcs + k;
             if (ph < 4 && ci < cin) {
@@ -205,16 +219,16 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
     return RRIN_OK;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
 static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo, int grid,
                        cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
     if (!g_attr_set[id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    RRIN_CUDA_CHECK(launch_pdl(kern, grid, kV2Threads, C::SMEM_BYTES, stream, p, tm0, tm1, tmo));
+    RRIN_CUDA_CHECK(launch_pdl(kern, grid, C::THREADS, C::SMEM_BYTES, stream, p, tm0, tm1, tmo));
     return RRIN_OK;
 }
 
@@ -317,7 +331,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     int rc = RRIN_ERR_BAD_ARG;
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>(id, p, tm0, tm1, tmo, grid, stream); break;
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>(id, p, tm0, tm1, tmo, grid, stream); break;
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }

@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "conv3x3.cuh"
 #include "rrin_internal.h"
@@ -47,14 +49,18 @@ struct ConvParamsV2 {
     unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
 };
 
-constexpr int kV2Threads = 7 * 32;
+constexpr int v2_threads(int ew) { return (4 * ew + 3) * 32; }     // EW epilogue groups of 4 warps + MMA, weights, activations
 
 // SCHED: 0 nine taps | 1 sixteen (block shift, phase) entries over one 64-channel chunk holding 4 phases x 16 ch (packed heads)
 //        | 2 half-phase: chunk parity = input phase row r, eight entries per chunk (level-0 tensors, 4 phases x 32 ch)
 // RES  : all n_stages * n_ent weight blocks stay resident in shared memory (loaded once per CTA)
 // ETMA : bf16 NHWC epilogue through swizzled shared-memory staging + TMA tensor stores (full-line writes,
 //        edge clipping by the TMA unit) instead of per-thread 16-byte global stores
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
+// EW   : epilogue groups (of 4 warps, one per TMEM lane quadrant); group g drains the sub-tiles whose running
+//        sequence number is congruent to g, so two accumulator slots are drained concurrently when EW = 2
+// Half entries (SCHED 2, NT = 128): an entry whose block shift is +-1 row feeds only one output phase row a, i.e.
+//        one 64-column half of the accumulator: it runs as an N = 64 MMA on a half-size weight block.
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
 struct ConvCfgV2 {
     static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
@@ -62,12 +68,16 @@ struct ConvCfgV2 {
     static constexpr int BOX_STRIDE = (BOX_BYTES + 1023) / 1024 * 1024;
     static constexpr int A_STAGE = BOXES * BOX_STRIDE;
     static constexpr int B_BLOCK = NT * KB * 2;
+    static constexpr bool HALF = (SCHED == 2 && NT == 128);
+    static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
+    static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;
+    static constexpr int THREADS = v2_threads(EW);
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;
-    static constexpr int EPI_STAGE = ETMA ? kEpiWarps * 4096 : 0;      // per warp: 32 pixels x 64 channels bf16, SWIZZLE_128B
-    static constexpr int OFF_EPI = OFF_B + SB * B_BLOCK;                // 1024-byte aligned (A stages and weight blocks are)
+    static constexpr int EPI_STAGE = ETMA ? 4 * EW * 4096 : 0;         // per warp: 32 pixels x 64 channels bf16, SWIZZLE_128B
+    static constexpr int OFF_EPI = OFF_B + B_BYTES;                     // 1024-byte aligned (A stages and weight blocks are)
     static constexpr int OFF_BIAS = OFF_EPI + EPI_STAGE;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
     static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS;
@@ -76,7 +86,18 @@ struct ConvCfgV2 {
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
     static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert((SCHED == 0 && KB == 64) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
-    static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32, "accumulator slots");
+    static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32 && SLOTS % EW == 0, "accumulator slots");
+    static_assert(!RES || SB % N_ENT == 0, "resident weights: SB counts whole stages of blocks");
+    // half entry? (parity, e) -> 0 full | 1 lower columns [0,64) (a = 0) | 2 upper columns [64,128) (a = 1)
+    __host__ __device__ static constexpr int half_of(int parity, int e) {
+        return !HALF ? 0 : (parity == 0 ? ((e >> 2) == 1 ? 2 : 0) : ((e >> 2) == 0 ? 1 : 0));
+    }
+    // byte offset of block (parity, e) inside a resident stage
+    __host__ __device__ static constexpr int res_off(int parity, int e) {
+        return !HALF ? e * B_BLOCK
+                     : (parity == 0 ? (e < 4 ? e * B_BLOCK : 4 * B_BLOCK + (e - 4) * (B_BLOCK / 2))
+                                    : (e < 4 ? e * (B_BLOCK / 2) : 2 * B_BLOCK + (e - 4) * B_BLOCK));
+    }
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     // A-descriptor start offset (16-byte units) of entry e; `parity` = stage & 1 (half-phase schedule only)
     __host__ __device__ static constexpr int us(int i) { return (i + 1) / 2 - 1; }     // {-1, 0, 0, 1}
@@ -112,13 +133,14 @@ struct TileWalkV2 {
     }
 };
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA>
-__global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
+__global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tmo) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
     constexpr int N_ENT = C::N_ENT;
+    constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
     uint8_t* smem = smem_raw + (s_base - smem_u32(smem_raw));
@@ -146,9 +168,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps * 32); }
         mbar_fence_init();
     }
-    if (warp == 6 && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); }
+    if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); }
     for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
-    if (warp == 4) {
+    if (warp == W_MMA) {
         tmem_alloc(smem_u32(tmem_slot), 512);
         tmem_relinquish();
     }
@@ -157,14 +179,14 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (warp != 5) pdl_wait();        // activations (reads and writes) only after the previous kernel has finished; weights are constant
+    if (warp != W_B) pdl_wait();      // activations (reads and writes) only after the previous kernel has finished; weights are constant
 
     TileWalkV2 walk;
     walk.init(p);
     TileV2 t;
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
 
-    if (warp == 6) {
+    if (warp == W_A) {
         // =========================================================== activation halo tiles (TMA), one elected thread
         if (elect_one()) {
             int it = 0;
@@ -184,13 +206,20 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
             if (prof) { p.prof[0] = tw; p.prof[1] = clock64() - t00; p.prof[2] = it; }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == W_B) {
         // =========================================================== weight blocks (bulk copies), one elected thread
+        // packed layout in global memory: uniform B_BLOCK-byte blocks [stage][entry]; a half entry uses the first half
         if (elect_one()) {
             if (RES) {
-                for (int b = 0; b < nblk; ++b) {
-                    mbar_arrive_expect_tx(b_full(b), C::B_BLOCK);
-                    bulk_g2s(s_b + b * C::B_BLOCK, p.wpack + (size_t)b * (NT * KB), C::B_BLOCK, b_full(b));
+                for (int st = 0; st < nst; ++st) {
+#pragma unroll
+                    for (int e = 0; e < N_ENT; ++e) {
+                        const int b = st * N_ENT + e;
+                        const bool odd = (SCHED == 2) && (st & 1);
+                        const uint32_t bytes = (odd ? C::half_of(1, e) : C::half_of(0, e)) ? C::B_BLOCK / 2 : C::B_BLOCK;
+                        mbar_arrive_expect_tx(b_full(b), bytes);
+                        bulk_g2s(s_b + st * C::B_STAGE + (odd ? C::res_off(1, e) : C::res_off(0, e)), p.wpack + (size_t)b * (NT * KB), bytes, b_full(b));
+                    }
                 }
             } else {
                 // The layer's weights are cold in L2 at launch and every CTA walks the same block sequence, so each
@@ -209,26 +238,78 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);
                     for (int b = 0; b < nblk; ++b, ++cnt) {
                         const int slot = cnt % SB;
+                        uint32_t bytes = C::B_BLOCK;
+                        if (C::HALF) {
+                            const int st = b / N_ENT, e = b - st * N_ENT;
+                            if ((st & 1) ? (e < 4) : (e >= 4)) bytes = C::B_BLOCK / 2;
+                        }
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
-                        mbar_arrive_expect_tx(b_full(slot), C::B_BLOCK);
-                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), C::B_BLOCK, b_full(slot));
+                        mbar_arrive_expect_tx(b_full(slot), bytes);
+                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), bytes, b_full(slot));
                     }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == W_MMA) {
         // =========================================================== MMA issuer: ONE elected thread runs the whole role
         // (no per-entry warp re-convergence; entries, K steps and their descriptor offsets are compile-time)
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            constexpr uint32_t idesc = make_idesc_bf16(128, NT), idesc_h = make_idesc_bf16(128, 64);
             const uint64_t a_desc0 = make_smem_desc_sw128(0, C::PW * 128);
-            const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
+            const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128), b_desc0h = make_smem_desc(0, 64 * 16, 128);
             const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0 + (s_b >> 4);
+            const uint32_t b_lo0h = (uint32_t)b_desc0h + (s_b >> 4);          // half entries: [KB/8][64][8] blocks
             int it = 0, cnt = 0, slot0 = 0, ntile = 0;
             uint32_t use_bits = 0;                      // bit s: parity of the number of finished uses of slot s
             long long twa = 0, twb = 0, twc = 0, t00 = clock64();
+            // one K stage with a compile-time stage parity: every entry offset, half-entry shape and resident block
+            // offset below is an immediate
+            auto run_stage = [&](auto par_c, const int st, const int stage, const int m, const int ntile) {
+                constexpr int PAR = decltype(par_c)::value;
+                const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
+                const uint32_t b_st = RES ? (uint32_t)((st * C::B_STAGE) >> 4) : 0u;
+#pragma unroll
+                for (int e = 0; e < N_ENT; ++e) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int hf = C::half_of(PAR, e);                       // 0 full, 1 lower 64 columns, 2 upper
+                    int slot = 0;
+                    uint32_t b_e;
+                    if (RES) {
+                        if (ntile == 0) { mbar_wait(b_full(st * N_ENT + e), 0); tc_fence_after(); }
+                        b_e = (hf ? b_lo0h : b_lo0) + b_st + (uint32_t)(C::res_off(PAR, e) >> 4);
+                    } else {
+                        slot = cnt % SB;
+                        const long long c0 = prof ? clock64() : 0;
+                        mbar_wait(b_full(slot), (cnt / SB) & 1);
+                        if (prof) twb += clock64() - c0;
+                        tc_fence_after();
+                        ++cnt;
+                        b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
+                    }
+                    const uint32_t a_e = a_st + C::ent_off(PAR, e);
+                    const uint32_t b_ks = hf ? 2 * 64 : 2 * NT;               // descriptor step per K=16: two core-matrix planes
+                    const uint32_t id = hf ? idesc_h : idesc;
+                    const uint32_t dcol = (hf == 2) ? 64 : 0;
+#pragma unroll 1
+                    for (int j = 0; j < m; ++j) {
+                        const int ts = (slot0 + j) % C::SLOTS;
+                        if (e == 0 && st == 0) {    // first write into this accumulator slot: the epilogue must have drained it
+                            const long long c0 = prof ? clock64() : 0;
+                            mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
+                            tc_fence_after();
+                            if (prof) twc += clock64() - c0;
+                        }
+#pragma unroll
+                        for (int s = 0; s < KB / 16; ++s)
+                            umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
+                                         (e | s) != 0 || st != 0);
+                    }
+                    if (!RES) umma_commit(b_empty(slot));
+                }
+                umma_commit(a_empty(stage));
+            };
             while (walk.next<MSUB>(p, t)) {
                 const int m = t.m;
                 for (int st = 0; st < nst; ++st, ++it) {
@@ -237,41 +318,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                       mbar_wait(a_full(stage), (it / SA) & 1);
                       if (prof) twa += clock64() - c0; }
                     tc_fence_after();
-                    const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
-                    const int par = (SCHED == 2) ? (st & 1) : 0;
-#pragma unroll
-                    for (int e = 0; e < N_ENT; ++e) {
-                        int slot;
-                        if (RES) {
-                            slot = st * N_ENT + e;
-                            if (ntile == 0) { mbar_wait(b_full(slot), 0); tc_fence_after(); }
-                        } else {
-                            slot = cnt % SB;
-                            const long long c0 = prof ? clock64() : 0;
-                            mbar_wait(b_full(slot), (cnt / SB) & 1);
-                            if (prof) twb += clock64() - c0;
-                            tc_fence_after();
-                            ++cnt;
-                        }
-                        const uint32_t a_e = a_st + (par ? C::ent_off(1, e) : C::ent_off(0, e));
-                        const uint32_t b_e = b_lo0 + ((slot * C::B_BLOCK) >> 4);
-#pragma unroll 1
-                        for (int j = 0; j < m; ++j) {
-                            const int ts = (slot0 + j) % C::SLOTS;
-                            if (e == 0 && st == 0) {    // first write into this accumulator slot: the epilogue must have drained it
-                                const long long c0 = prof ? clock64() : 0;
-                                mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
-                                tc_fence_after();
-                                if (prof) twc += clock64() - c0;
-                            }
-#pragma unroll
-                            for (int s = 0; s < KB / 16; ++s)
-                                umma_bf16_lh(tmem_base + ts * NT, a_e + j * 64 + s * 2, a_hi, b_e + s * (2 * NT), b_hi, idesc,
-                                             (e | s) != 0 || st != 0);
-                        }
-                        if (!RES) umma_commit(b_empty(slot));
-                    }
-                    umma_commit(a_empty(stage));
+                    if (SCHED == 2 && (st & 1)) run_stage(std::integral_constant<int, 1>{}, st, stage, m, ntile);
+                    else run_stage(std::integral_constant<int, 0>{}, st, stage, m, ntile);
                 }
                 for (int j = 0; j < m; ++j) {
                     const int ts = (slot0 + j) % C::SLOTS;
@@ -284,11 +332,12 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
             if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; }
         }
         __syncwarp();
-    } else if (warp < kEpiWarps) {
-        // =========================================================== epilogue (warps 0-3)
-        const int mrow = warp * 32 + lane;              // accumulator row == TMEM lane
+    } else if (warp < 4 * EW) {
+        // =========================================================== epilogue: EW groups of 4 warps (quadrant = warp % 4)
+        const int quad = warp & 3, grp = warp >> 2;
+        const int mrow = quad * 32 + lane;              // accumulator row == TMEM lane
         const int ly = mrow >> 3, lx = mrow & 7;
-        int slot0 = 0;
+        int slot0 = 0, seq = 0;                         // seq: running sub-tile number; group grp drains seq % EW == grp
         uint32_t use_bits = 0;
         long long twf = 0, t00 = clock64();
         while (walk.next<MSUB>(p, t)) {
@@ -296,6 +345,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
             const float* bsrc = bias_s + t.nt * NT;
 #pragma unroll 1
             for (int j = 0; j < t.m; ++j) {
+                if (EW > 1 && ((seq + j) % EW) != grp) continue;
                 const int ts = (slot0 + j) % C::SLOTS;
                 { const long long c0 = prof ? clock64() : 0;
                   mbar_wait(acc_full(ts), (use_bits >> ts) & 1);
@@ -304,7 +354,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                 const int gx = (t.sx0 + j) * 8 + lx;
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
-                const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + ts * NT;
+                const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * NT;
                 if constexpr (ETMA != 0) {
                     // bf16 NHWC via this warp's 4 KB staging buffer (32 pixels x 128 B, 16-byte chunk k of row r at
                     // k ^ (r & 7)) and one TMA tensor store per 64 columns; the box {64 ch, 8 px, 4 rows} is clipped
@@ -346,7 +396,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * warp, t.n);
+                            tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * quad, t.n);
                             bulk_commit_group();
                         }
                     }
@@ -407,6 +457,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
             }
             for (int j = 0; j < t.m; ++j) use_bits ^= 1u << ((slot0 + j) % C::SLOTS);
             slot0 = (slot0 + t.m) % C::SLOTS;
+            seq += t.m;
         }
         if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed
         if (prof && threadIdx.x == 0) { p.prof[8] = twf; p.prof[9] = clock64() - t00; }
@@ -415,7 +466,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) conv3x3_tma_kernel(const __grid
     // ---------------- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

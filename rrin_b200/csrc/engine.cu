@@ -101,7 +101,7 @@ static Schedule build_schedule() {
         place(m);
         if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns
             Pack& f = L.fold;
-            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = (level == 0) ? 16 : 17; f.n_stages = cin / 64; f.n_cols = 4 * cout;   // 17: scatter epilogue
+            f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = (level == 0) ? 18 : 17; f.n_stages = cin / 64; f.n_cols = 4 * cout;   // 17: scatter epilogue
             place(f);
         }
         s.layers.push_back(L);

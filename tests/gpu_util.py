@@ -15,7 +15,7 @@ PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8 = 0, 1, 2, 3
 # transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 # TMA-fed kernel (conv3x3_v2.cuh)
-T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER = range(10, 18)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0 = range(10, 19)
 
 
 def stream():
@@ -109,13 +109,14 @@ def conv_fold(src, n, hc, wc, weight, bias, level0, out=None):
     """Folded bilinear-x2 + conv on the TMA kernel: src NHWC bf16 [N,hc,wc,cin] (coarse, zero-filled halo); output
     hi-res [2hc,2wc].  level0=True -> output is space-to-depth [N,hc,wc,4,cout]; else NHWC [N,2hc,2wc,cout] via the
     scatter epilogue.  The outermost 2 hi-res pixels differ from the reference (fixed by the exact ring pass)."""
-    kcs, kb, nt, _ = cfg_info(T_BIG)
+    cfg = T_FOLD0 if level0 else T_BIG_SCATTER
+    kcs, kb, nt, _ = cfg_info(cfg)
     cout, cin = weight.shape[:2]
-    wp, bp, n_cols = pack(PACK_FOLD, T_BIG, weight, bias, cin // kcs, SCHED_TAPS9)
+    wp, bp, n_cols = pack(PACK_FOLD, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if level0:
         if out is None:
             out = torch.full((n, hc, wc, 4, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-        launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, T_BIG)
+        launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, T_FOLD0)
         return from_s2d(out), out
     if out is None:
         out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=torch.bfloat16, device="cuda")

@@ -65,6 +65,7 @@ NORMAL_CASES = [
     ("tma_many_tiles_l2", 16, "plain", 128, 128, True, 1, 208, 208),
     ("tma_many_tiles_l3_ntiles", 16, "plain", 256, 256, True, 2, 100, 72),
     ("tma_direct_l2_cat", 17, "cat", 128, 128, True, 1, 12, 20),
+    ("tma_msub3_many_tiles", 18, "plain", 64, 128, False, 1, 120, 200),
     ("tma_direct_many_tiles_l3", 17, "plain", 256, 256, True, 1, 100, 72),
 ]
 
