@@ -21,14 +21,18 @@ namespace rrin {
 //  6 : <128, 32, 128, 1, 2, 16>  level-0 32->32 with all 16 weight blocks (128 KB) resident: L2 bandwidth is about
 //                                HBM bandwidth on this part, so re-streaming weights per tile costs as much as the
 //                                activations themselves
-#define RRIN_CONV_CONFIGS(X)   \
-    X(0, 64, 16, 128, 2, 3, 16) \
-    X(1, 128, 32, 128, 2, 2, 5) \
-    X(2, 128, 32, 16, 2, 2, 16) \
-    X(3, 32, 32, 64, 4, 4, 9)   \
-    X(4, 64, 64, 64, 2, 3, 9)   \
-    X(5, 64, 64, 128, 2, 3, 4)  \
-    X(6, 128, 32, 128, 1, 2, 16)
+//  7 : < 64, 64,  64, 1, 3,  6> STRIP  level-1 border ring after a folded upsample conv (exact bilinear, 128-pixel strips)
+//  8 : < 64, 16, 128, 1, 3, 12> STRIP  level-0 border ring (space-to-depth grid, 4 phases x 16 source channels per stage)
+#define RRIN_CONV_CONFIGS(X)      \
+    X(0, 64, 16, 128, 2, 3, 16, 0) \
+    X(1, 128, 32, 128, 2, 2, 5, 0) \
+    X(2, 128, 32, 16, 2, 2, 16, 0) \
+    X(3, 32, 32, 64, 4, 4, 9, 0)   \
+    X(4, 64, 64, 64, 2, 3, 9, 0)   \
+    X(5, 64, 64, 128, 2, 3, 4, 0)  \
+    X(6, 128, 32, 128, 1, 2, 16, 0) \
+    X(7, 64, 64, 64, 1, 3, 6, 1)   \
+    X(8, 64, 16, 128, 1, 3, 12, 1)
 
 // TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>
 // 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
@@ -52,16 +56,16 @@ namespace rrin {
     X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)
 
 constexpr int kV2Base = 10;
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip; };
 static const CfgInfo kCfg1[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB>::PW, -1, 0, 0},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, STRIP) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 static const CfgInfo kCfg2[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::PW, SCHED, RES, ETMA},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::PW, SCHED, RES, ETMA, 0},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -207,10 +211,10 @@ static int num_sms() {
     return g_num_sms;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP>
 static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream) {
-    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB>;
-    auto kern = conv3x3_umma_kernel<KCS, KB, NT, MSUB, SA, SB>;
+    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>;
+    auto kern = conv3x3_umma_kernel<KCS, KB, NT, MSUB, SA, SB, STRIP>;
     if (!g_attr_set[id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
@@ -394,18 +398,30 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (d.epi == EPI_BF16 && d.cout_stride < d.n_cols) { set_error("conv3x3: cout_stride %d < columns %d", d.cout_stride, d.n_cols); return RRIN_ERR_BAD_SHAPE; }
     p.tiles_x = (d.W + 8 * c.msub - 1) / (8 * c.msub);
     p.tiles_y = (d.H + kTileH - 1) / kTileH;
-    p.ring_only = d.ring_only && p.tiles_x > 2 && p.tiles_y > 2;
-    if (d.ring_only && !p.ring_only) { set_error("conv3x3: ring_only needs more than 2x2 tiles (the caller should run the full exact path)"); return RRIN_ERR_BAD_SHAPE; }
-    p.tiles_per_img = p.ring_only ? 2 * p.tiles_x + 2 * (p.tiles_y - 2) : p.tiles_x * p.tiles_y;
+    if (c.strip) {
+        // border ring in 128-pixel strips: thickness 2 grid pixels (NHWC grid: the 2 hi-res pixels a folded upsample conv
+        // leaves wrong) or 1 (space-to-depth grid: one block pixel = 2 hi-res pixels)
+        if (!d.ring_only || (d.mode != SRC_UP && d.mode != SRC_UP_S2D)) { set_error("conv3x3: config %d recomputes border rings of upsample convs only", cfg); return RRIN_ERR_BAD_ARG; }
+        p.ring_t = (d.mode == SRC_UP_S2D) ? 1 : 2;
+        if (d.H <= 2 * p.ring_t || d.W <= 2 * p.ring_t) { set_error("conv3x3: frame too small for a border ring"); return RRIN_ERR_BAD_SHAPE; }
+        p.ring_only = 1;
+        p.nseg_h = (d.W + kStripLen - 1) / kStripLen;
+        p.nseg_v = (d.H - 2 * p.ring_t + kStripLen - 1) / kStripLen;
+        p.tiles_per_img = 2 * p.ring_t * (p.nseg_h + p.nseg_v);
+    } else {
+        p.ring_only = d.ring_only && p.tiles_x > 2 && p.tiles_y > 2;
+        if (d.ring_only && !p.ring_only) { set_error("conv3x3: ring_only needs more than 2x2 tiles (the caller should run the full exact path)"); return RRIN_ERR_BAD_SHAPE; }
+        p.tiles_per_img = p.ring_only ? 2 * p.tiles_x + 2 * (p.tiles_y - 2) : p.tiles_x * p.tiles_y;
+    }
     const long work = (long)p.n_ntiles * d.N * p.tiles_per_img;
     if (work > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
     p.total_work = (int)work;
-    p.b_resident = (p.n_ntiles == 1 && p.n_stages * p.n_ent <= c.sb) ? 1 : 0;
+    p.b_resident = (!c.strip && p.n_ntiles == 1 && p.n_stages * p.n_ent <= c.sb) ? 1 : 0;   // strips permute weight blocks per item
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
     const int grid = p.total_work < sms ? p.total_work : sms;
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB) case id: return launch_cfg<KCS, KB, NT, MSUB, SA, SB>(id, p, grid, stream);
+#define X(id, KCS, KB, NT, MSUB, SA, SB, STRIP) case id: return launch_cfg<KCS, KB, NT, MSUB, SA, SB, STRIP>(id, p, grid, stream);
         RRIN_CONV_CONFIGS(X)
 #undef X
     }

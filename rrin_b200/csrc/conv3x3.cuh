@@ -62,6 +62,7 @@ struct ConvParams {
     int n_ntiles;
     int tiles_x, tiles_y;
     int ring_only;               // work items enumerate only the outermost ring of tiles
+    int ring_t, nseg_h, nseg_v;  // STRIP kernels: ring thickness in grid pixels, 128-pixel segments per horizontal / vertical side
     int tiles_per_img;           // tiles_x*tiles_y, or the ring count
     int total_work;              // n_ntiles * N * tiles_per_img
     int b_resident;              // all n_stages*n_ent weight blocks stay in SMEM (requires n_ntiles == 1)
@@ -73,11 +74,18 @@ constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kConvThreads = (kEpiWarps + 2 + kProdWarps) * 32;
 constexpr int kTileH = 16;
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
+// STRIP: the work item is a kStripLen-pixel strip along the frame border (1 x L or L x 1 grid pixels) instead of a
+// 16 x 8 tile: halo = 3 lines x (L+2) positions, accumulator row m = position m along the strip.  Used to recompute the
+// outermost ring after a weight-folded upsample conv: only those pixels differ (zero padding vs folded halo).
+// A strip covers kStripLen positions; the accumulator still has 128 rows (rows >= kStripLen read past the 3 halo lines and
+// are discarded): short strips spread the latency-bound halo construction over many more CTAs than 128-pixel ones.
+constexpr int kStripLen = 32;
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP = 0>
 struct ConvCfg {
     static constexpr int CH8 = KCS / 8;                // 16-byte channel groups (planes) per stage
-    static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
-    static constexpr int HALO_PX = (kTileH + 2) * PW;
+    static constexpr int PW = STRIP ? kStripLen + 2 : 8 * MSUB + 2;            // halo line pitch in pixels
+    static constexpr int HALO_PX = (STRIP ? 3 : kTileH + 2) * PW;
+    static_assert(!STRIP || MSUB == 1, "a strip is one 128-row accumulator");
     static constexpr int PLANE_PX = HALO_PX | 1;       // odd -> conflict-free plane-strided stores
     static constexpr int PS = PLANE_PX * 16;           // bytes per 8-channel plane
     static constexpr int A_STAGE = CH8 * PS;
@@ -162,9 +170,37 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int w) {
     return t;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB>
+// STRIP work item -> (n-tile, image, orientation, fixed coordinate, first position, end of valid positions).
+// Horizontal strips (rows 0..T-1 and H-T..H-1) span the full width; vertical strips (columns 0..T-1, W-T..W-1) cover
+// rows T..H-T-1 only, so every ring pixel is written by exactly one strip.
+struct StripCoord { int nt, n, vert, fixed, start, limit; };
+__device__ __forceinline__ StripCoord decode_strip(const ConvParams& p, int w) {
+    StripCoord t;
+    const int per_nt = p.tiles_per_img * p.N;
+    t.nt = w / per_nt;
+    int r = w - t.nt * per_nt;
+    t.n = r / p.tiles_per_img;
+    r -= t.n * p.tiles_per_img;
+    const int T = p.ring_t, hcount = 2 * T * p.nseg_h;
+    t.vert = r >= hcount;
+    if (t.vert) r -= hcount;
+    const int nseg = t.vert ? p.nseg_v : p.nseg_h;
+    const int side = r / (T * nseg);
+    r -= side * (T * nseg);
+    const int line = r / nseg, seg = r - line * nseg;
+    const int extent = t.vert ? p.W : p.H;               // range of the fixed coordinate
+    t.fixed = side ? extent - 1 - line : line;
+    t.start = (t.vert ? T : 0) + seg * kStripLen;
+    t.limit = t.vert ? p.H - T : p.W;
+    return t;
+}
+// transposed tap / entry for vertical strips: the halo is stored with lines = columns, so the standard entry offsets
+// address the transposed geometry and the weight block of the transposed entry has to be paired with them
+__device__ __forceinline__ int transpose_entry(int e, int n_ent) { return n_ent == 9 ? (e % 3) * 3 + e / 3 : ((e & 3) << 2) | (e >> 2); }
+
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __grid_constant__ ConvParams p) {
-    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB>;
+    using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_a = s_base;
@@ -216,9 +252,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
         const bool async_mode = (p.mode == SRC_PLAIN || p.mode == SRC_CAT);
         int it = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-            const TileCoord tc = decode_tile(p, w);
-            const int n = tc.n;
-            const int y0 = tc.ty * kTileH - 1, x0 = tc.tx * (8 * MSUB) - 1;   // halo origin
+            int n, y0, x0;                                                      // image, halo origin
+            bool vert = false;                                                  // strips: halo lines are columns
+            if (STRIP) {
+                const StripCoord sc = decode_strip(p, w);
+                n = sc.n; vert = sc.vert != 0;
+                y0 = (vert ? sc.start : sc.fixed) - 1; x0 = (vert ? sc.fixed : sc.start) - 1;
+            } else {
+                const TileCoord tc = decode_tile(p, w);
+                n = tc.n;
+                y0 = tc.ty * kTileH - 1; x0 = tc.tx * (8 * MSUB) - 1;
+            }
             for (int st = 0; st < nst; ++st, ++it) {
                 const int stage = it % SA;
                 mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
@@ -281,7 +325,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                     const int cs = p.c0;
                     const int sh = pool ? 2 * p.H : (s2d ? p.H : p.H >> 1), sw = pool ? 2 * p.W : (s2d ? p.W : p.W >> 1);
                     constexpr int PPH = KB / 8;            // planes per phase (s2d)
-                    const int pa = s2d ? (c8 / PPH) >> 1 : 0, pb = s2d ? (c8 / PPH) & 1 : 0;
+                    // vertical strips store phase (a,b) in plane group (b,a): see transpose_entry
+                    const int pq = s2d ? c8 / PPH : 0;
+                    const int pa = vert ? (pq & 1) : (pq >> 1), pb = vert ? (pq >> 1) : (pq & 1);
                     const int coff = s2d ? st * KB + (c8 % PPH) * 8 : st * KCS + c8 * 8;
                     const __nv_bfloat16* src = p.src0 + (size_t)n * sh * sw * cs + coff;
                     for (int px = px0; px < C::HALO_PX; px += U * PXSTEP) {
@@ -290,7 +336,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                         for (int u = 0; u < U; ++u) {
                             const int q = px + u * PXSTEP;
                             const int hy = q / C::PW, hx = q - hy * C::PW;
-                            const int gy = y0 + hy, gx = x0 + hx;
+                            const int gy = y0 + (vert ? hx : hy), gx = x0 + (vert ? hy : hx);
                             okk[u] = (q < C::HALO_PX) && ((unsigned)gy < (unsigned)p.H) && ((unsigned)gx < (unsigned)p.W);
                             int iy0 = 0, iy1 = 0, ix0 = 0, ix1 = 0;
                             wx[u] = wy[u] = 0.f;
@@ -339,11 +385,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                 for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
                     const int nt = w / per_nt;
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)nt * nblk * (NT * KB);
+                    const bool vert = STRIP && decode_strip(p, w).vert;
                     for (int b = 0; b < nblk; ++b, ++cnt) {
                         const int slot = cnt % SB;
+                        int bs = b;
+                        if (vert) { const int st = b / p.n_ent, e = b - st * p.n_ent; bs = st * p.n_ent + transpose_entry(e, p.n_ent); }
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
                         mbar_arrive_expect_tx(b_full(slot), C::B_BLOCK);
-                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), C::B_BLOCK, b_full(slot));
+                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)bs * (NT * KB), C::B_BLOCK, b_full(slot));
                     }
                 }
             }
@@ -356,7 +405,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
             constexpr bool S2D = (KB != KCS);
             constexpr int N_ENT = S2D ? 16 : 9;
             constexpr uint32_t idesc = make_idesc_bf16(128, NT);
-            const uint64_t a_desc0 = make_smem_desc(0, C::PS, C::PW * 16);
+            const uint64_t a_desc0 = make_smem_desc(0, C::PS, STRIP ? 128 : C::PW * 16);   // strip: 8-row groups are 8 positions apart
             const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
             const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0 + (s_b >> 4);
@@ -412,17 +461,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
         const int ly = m >> 3, lx = m & 7;
         int tcount = 0;
         for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcount) {
-            const TileCoord tc = decode_tile(p, w);
-            const int nt = tc.nt, n = tc.n;
+            int nt, n, gy, gx0;
+            bool sok = true;
+            if (STRIP) {
+                const StripCoord sc = decode_strip(p, w);
+                const int pos = sc.start + m;
+                nt = sc.nt; n = sc.n; sok = (m < kStripLen) && (pos < sc.limit);
+                gy = sc.vert ? pos : sc.fixed; gx0 = sc.vert ? sc.fixed : pos;
+            } else {
+                const TileCoord tc = decode_tile(p, w);
+                nt = tc.nt; n = tc.n;
+                gy = tc.ty * kTileH + ly; gx0 = tc.tx * (8 * MSUB) + lx;
+            }
             const int buf = tcount & 1;
             mbar_wait(acc_full(buf), (tcount >> 1) & 1);
             tc_fence_after();
-            const int gy = tc.ty * kTileH + ly;
             const float* bsrc = bias_s + nt * NT;
 #pragma unroll 1
             for (int j = 0; j < MSUB; ++j) {
-                const int gx = tc.tx * (8 * MSUB) + 8 * j + lx;
-                const bool ok = (gy < p.H) && (gx < p.W);
+                const int gx = gx0 + 8 * j;
+                const bool ok = sok && (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16) + (buf * MSUB + j) * NT;
                 if (p.epi == EPI_F32X16) {

@@ -48,7 +48,7 @@ struct Layer {
     int unet;        // 0 Flow, 1 refine_flow, 2 Mask, 3 final   (execution order)
     int cin, cout;   // true channel counts (unet.py)
     int level, src, act, is_last;
-    Pack main, fold; // `fold` only for up.1 convs writing level 0 or 1
+    Pack main, fold, strip; // `fold` / `strip` only for up.1 convs writing level 0 or 1 (folded interior + exact border ring)
 };
 
 struct UNetDef { const char* name; int cin, ncls, depth; };
@@ -103,6 +103,10 @@ static Schedule build_schedule() {
             Pack& f = L.fold;
             f.kind = PACK_FOLD; f.sched = SCHED_TAPS9; f.cfg = (level == 0) ? 18 : 17; f.n_stages = cin / 64; f.n_cols = 4 * cout;   // 17: scatter epilogue
             place(f);
+            Pack& r = L.strip;                    // exact bilinear on 128-pixel border strips (conv3x3.cuh, STRIP configs)
+            if (level == 0) { r.kind = PACK_S2D; r.sched = SCHED_S2D16; r.cfg = 8; r.n_stages = cin / 16; r.n_cols = 128; }
+            else { r.kind = PACK_NORMAL; r.sched = SCHED_TAPS9; r.cfg = 7; r.n_stages = cin / 64; r.n_cols = cout; }
+            place(r);
         }
         s.layers.push_back(L);
     };
@@ -146,7 +150,7 @@ static const Schedule& schedule() {
 struct Launch {
     int glue = -1;           // >= 0: glue kernel id (0 pack_pair .. 4 residue_clamp)
     int layer = -1;          // conv: index into schedule().layers
-    int use_fold = 0;        // conv: which Pack
+    int use_fold = 0;        // conv: which Pack (0 main, 1 fold, 2 strip)
     ConvDesc cd;             // pointers hold workspace OFFSETS (+1 so that 0 stays "null") until launch
     alignas(64) unsigned char tmap[3][128];   // TMA configs: tensor maps of src0 / src1 / out, encoded for `tmap_ws`
     std::string name;
@@ -187,7 +191,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
     const bool fold_ok = (H > 64 && W > 64);     // the exact border ring needs more than 2x2 tiles of 32x32 pixels
     auto base = [&](int layer, int use_fold, int grid_lvl) {
         const Layer& L = s.layers[layer];
-        const Pack& pk = use_fold ? L.fold : L.main;
+        const Pack& pk = use_fold == 1 ? L.fold : (use_fold == 2 ? L.strip : L.main);
         Launch ln;
         ln.layer = layer; ln.use_fold = use_fold;
         ln.cd.N = B; ln.cd.H = H >> grid_lvl; ln.cd.W = W >> grid_lvl;
@@ -206,7 +210,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
             ln.flops = 2.0 * 9 * L.cin * L.cout * lp;
             double in_b = 2.0 * (L.src == K_HEAD ? 16 : L.cin) * lp;
             if (L.src == K_POOL) in_b *= 4; else if (L.src == K_UP) in_b /= 4;
-            const Pack& pk = ln.use_fold ? L.fold : L.main;
+            const Pack& pk = ln.use_fold == 1 ? L.fold : (ln.use_fold == 2 ? L.strip : L.main);
             ln.bytes = in_b + (L.is_last ? 16.0 * lp : 2.0 * L.cout * lp) + (double)conv_packed_weight_bytes(pk.cfg, pk.n_cols, pk.n_stages, pk.sched);
         }
         e->launches.push_back(ln);
@@ -252,7 +256,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
             if (lvl == 1) { f.cd.epi = EPI_SCATTER; f.cd.cout_stride = c; }
             else { f.cd.epi = EPI_BF16; f.cd.cout_stride = 128; }     // (phase, co) columns == space-to-depth pixel
             finish(f, " fold", true);
-            Launch r = base(li, 0, 1);                // exact transform path on the outermost ring of tiles
+            Launch r = base(li, 2, 1);                // exact bilinear + conv on the border ring, in 128-pixel strips
             r.cd.mode = (lvl == 0) ? SRC_UP_S2D : SRC_UP; r.cd.c0 = 2 * c; r.cd.ring_only = 1;
             r.cd.src0 = enc(tmp[cur]); r.cd.out = enc(tmp[ui]); r.cd.epi = EPI_BF16; r.cd.cout_stride = (lvl == 0) ? 128 : c;
             finish(r, " ring", false);
@@ -326,6 +330,9 @@ int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* st
     if (r == RRIN_OK && L.fold.kind >= 0)
         r = conv_pack_weights(L.fold.kind, w, b, L.cout, L.cin, L.fold.n_stages, L.fold.cfg, base + L.fold.w_off,
                               reinterpret_cast<float*>(base + L.fold.b_off), st);
+    if (r == RRIN_OK && L.strip.kind >= 0)
+        r = conv_pack_weights(L.strip.kind, w, b, L.cout, L.cin, L.strip.n_stages, L.strip.cfg, base + L.strip.w_off,
+                              reinterpret_cast<float*>(base + L.strip.b_off), st);
     return r;
 }
 
@@ -406,7 +413,7 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             }
         } else {
             const Layer& L = s.layers[ln.layer];
-            const Pack& pk = ln.use_fold ? L.fold : L.main;
+            const Pack& pk = ln.use_fold == 1 ? L.fold : (ln.use_fold == 2 ? L.strip : L.main);
             ConvDesc cd = ln.cd;
             cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out);
             cd.wpack = blob + pk.w_off;

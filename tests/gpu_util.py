@@ -14,6 +14,7 @@ SCHED_TAPS9, SCHED_S2D16, SCHED_S2D8 = 0, 1, 2
 PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8 = 0, 1, 2, 3
 # transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
+CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
 T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0 = range(10, 19)
 

@@ -155,9 +155,11 @@ def test_conv_level0_s2d(case):
 
 
 # ------------------------------------------------------------------ folded upsample + exact ring
-@pytest.mark.parametrize("level0,cin,cout,n,hc,wc", [(True, 64, 32, 1, 56, 72), (False, 128, 64, 1, 56, 72), (True, 64, 32, 2, 40, 64)],
-                         ids=["fold_l0", "fold_l1", "fold_l0_n2"])
-def test_conv_folded_upsample_with_ring(level0, cin, cout, n, hc, wc):
+@pytest.mark.parametrize("ring", ["strips", "tiles"])
+@pytest.mark.parametrize("level0,cin,cout,n,hc,wc", [(True, 64, 32, 1, 56, 72), (False, 128, 64, 1, 56, 72), (True, 64, 32, 2, 40, 64),
+                                                     (True, 64, 32, 1, 136, 200), (False, 128, 64, 1, 72, 136)],
+                         ids=["fold_l0", "fold_l1", "fold_l0_n2", "fold_l0_multiseg", "fold_l1_multiseg"])
+def test_conv_folded_upsample_with_ring(level0, cin, cout, n, hc, wc, ring):
     x = _rand(n, cin, hc, wc, 5)
     wgt, b = _rand_wb(cout, cin, 6)
     ref = G.reference(x, wgt, b, False, pre="up")
@@ -166,12 +168,18 @@ def test_conv_folded_upsample_with_ring(level0, cin, cout, n, hc, wc):
     # clamps the bilinear taps and zero-pads the upsampled image)
     _check("fold interior", y[:, :, 2:-2, 2:-2], ref[:, :, 2:-2, 2:-2])
     assert (y[:, :, 0] - ref[:, :, 0]).abs().max() > 1e-2, "the ring is expected to differ before the fix-up"
-    # exact transform path on the ring of tiles, written into the same tensor
+    # exact transform path on the border ring, written into the same tensor: 128-pixel strips (what the engine
+    # launches) or the outermost ring of 16x16 tiles
+    strips = ring == "strips"
     if level0:
-        y2, _ = G.conv_s2d(G.nhwc(x), None, G.SRC_UP_S2D, n, hc, wc, wgt, b, False, G.CFG_L0, 2, ring_only=True, out=raw)
+        y2, _ = G.conv_s2d(G.nhwc(x), None, G.SRC_UP_S2D, n, hc, wc, wgt, b, False, G.CFG_L0_STRIP if strips else G.CFG_L0,
+                           cin // 16 if strips else 2, ring_only=True, out=raw)
     else:
-        y2, _ = G.conv_normal(G.nhwc(x), None, G.SRC_UP, n, 2 * hc, 2 * wc, wgt, b, False, G.CFG_L1, ring_only=True, out=raw)
+        y2, _ = G.conv_normal(G.nhwc(x), None, G.SRC_UP, n, 2 * hc, 2 * wc, wgt, b, False, G.CFG_L1_STRIP if strips else G.CFG_L1,
+                              ring_only=True, out=raw)
     _check("fold + ring", y2, ref)
+    if strips:      # the strips rewrite exactly the outermost 2 hi-res pixels: the interior is untouched
+        assert torch.equal(y2[:, :, 2:-2, 2:-2], y[:, :, 2:-2, 2:-2])
 
 
 # ------------------------------------------------------------------ glue kernels

@@ -11,12 +11,13 @@ from rrin_b200 import Net
 
 h = int(sys.argv[1]) if len(sys.argv) > 1 else 1088
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+reps = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 5
+nb = int(os.environ.get("BATCH", "1"))
 net = Net()
 net.load_state_dict(O.seeded_state_dict(), strict=True)
 net = net.cuda().eval()
 a, b = O.seeded_frames(1, h, w, seed=2, smooth=True)
-a, b = a.cuda(), b.cuda()
+a, b = a.cuda().expand(nb, -1, -1, -1).contiguous(), b.cuda().expand(nb, -1, -1, -1).contiguous()
 for _ in range(3):
     net(a, b, t=0.5)
 torch.cuda.synchronize()
@@ -26,7 +27,7 @@ for _ in range(20):
     net(a, b, t=0.5)
 e1.record()
 torch.cuda.synchronize()
-print(f"forward {h}x{w}: {e0.elapsed_time(e1) / 20:.3f} ms  ({20e3 / e0.elapsed_time(e1):.1f} frames/s)")
+print(f"forward {nb}x{h}x{w}: {e0.elapsed_time(e1) / 20:.3f} ms  ({nb * 20e3 / e0.elapsed_time(e1):.1f} frames/s)")
 eng = net._engines[next(iter(net._engines))]
 wts = net._weights(a.device)
 table = eng.launch_table()
