@@ -91,7 +91,11 @@ RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int wh
  *   epi      : 0 bf16 NHWC [N,H,W,cout_stride] | 1 fp32 [N,H,W,16] | 2 folded-upsample scatter into bf16
  *              [N,2H,2W,cout_stride]
  *   pack kind: 0 plain | 1 space-to-depth | 2 bilinear-x2-folded weights (4*cout columns, pad_clamp=1 input)
- *   cfg      : tile configuration 0..rrin-internal (rrin_conv_config_info gives KCS, KB, NT, MSUB). */
+ *   sched 2  : half-phase schedule of the TMA-fed kernel for level-0 tensors (pack kind 3)
+ *   pool_out : optional second output of the TMA-epilogue configs: F.avg_pool2d(out, 2) (unet.py:46) written by the
+ *              same epilogue, bf16 NHWC [N,H/2,W/2,cout_stride] (space-to-depth grid: [N,H,W,cout_stride/4]); or NULL
+ *   cfg      : tile configuration: 0..8 transform kernel (pool / bilinear sources, border strips), 10..18 TMA-fed kernel
+ *              (rrin_conv_config_info gives KCS, KB, NT, MSUB). */
 RRIN_API int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
 RRIN_API size_t rrin_conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);
 RRIN_API int rrin_conv_packed_bias_count(int cfg, int n_cols);
@@ -99,7 +103,7 @@ RRIN_API int rrin_pack_conv_raw(int kind, const float* w, const float* b, int co
                        void* wpack, float* bias_pack, void* stream);
 RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                  int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
-                 int act, int ring_only, int cfg, void* stream);
+                 int act, int ring_only, int cfg, void* pool_out, void* stream);
 
 /* Glue kernels.  Frames are fp32 NCHW; tensors exchanged with the U-Nets are space-to-depth on the half-res
  * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8]. */

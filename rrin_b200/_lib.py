@@ -34,7 +34,7 @@ _SIGNATURES = {
     "rrin_conv_packed_weight_bytes": (cs, [ci, ci, ci, ci]),
     "rrin_conv_packed_bias_count": (ci, [ci, ci]),
     "rrin_pack_conv_raw": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
-    "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
     "rrin_pack_pair": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "rrin_flow_tscale_pack": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_warp_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),

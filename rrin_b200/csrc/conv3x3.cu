@@ -296,6 +296,11 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     p.wpack = reinterpret_cast<const __nv_bfloat16*>(d.wpack);
     p.bias = d.bias;
     p.out = d.out; p.epi = d.epi; p.cout_stride = d.cout_stride; p.act = d.act;
+    p.pool_out = reinterpret_cast<__nv_bfloat16*>(d.pool_out);
+    if (d.pool_out) {
+        if (!c.etma) { set_error("conv3x3(tma): config %d has no pooled second output", cfg); return RRIN_ERR_BAD_ARG; }
+        if (c.sched == SCHED_S2D8 ? (c.nt != 128 || d.n_cols != 128) : ((d.H | d.W) & 1)) { set_error("conv3x3(tma): pooled output needs an even grid (or the 4-phase level-0 grid)"); return RRIN_ERR_BAD_SHAPE; }
+    }
     if (d.epi == EPI_F32X16 && c.nt != 16) { set_error("conv3x3: fp32 epilogue needs NT=16"); return RRIN_ERR_BAD_ARG; }
     if (d.epi == EPI_SCATTER && (d.cout_stride % 32 || d.n_cols != 4 * d.cout_stride)) { set_error("conv3x3: bad scatter epilogue shape"); return RRIN_ERR_BAD_SHAPE; }
     if (d.epi == EPI_BF16 && d.cout_stride < d.n_cols) { set_error("conv3x3: cout_stride %d < columns %d", d.cout_stride, d.n_cols); return RRIN_ERR_BAD_SHAPE; }
@@ -357,6 +362,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (d.N <= 0 || d.H <= 0 || d.W <= 0) { set_error("conv3x3: empty shape %dx%dx%d", d.N, d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
     if (d.mode < 0 || d.mode > SRC_UP_S2D || !d.src0 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
     if (cfg_is_v2(cfg)) return conv_launch_v2(d, stream);
+    if (d.pool_out) { set_error("conv3x3: config %d has no pooled second output", cfg); return RRIN_ERR_BAD_ARG; }
     if (d.sched == SCHED_S2D8) { set_error("conv3x3: the half-phase schedule needs a TMA config"); return RRIN_ERR_BAD_ARG; }
     if ((d.sched == SCHED_TAPS9) != (c.kb == c.kcs)) { set_error("conv3x3: config %d runs the %s schedule", cfg, c.kb == c.kcs ? "9-tap" : "space-to-depth"); return RRIN_ERR_BAD_ARG; }
     ConvParams p{};

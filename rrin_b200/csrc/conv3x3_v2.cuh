@@ -41,6 +41,9 @@ struct ConvParamsV2 {
     const float* bias;
     void* out;
     int epi, cout_stride, act;
+    // optional second output (TMA-epilogue configs): F.avg_pool2d(out, 2) (unet.py:46) as bf16 NHWC [N, H/2, W/2, cout_stride]
+    // on an NHWC grid, or [N, H, W, cout_stride/4] (mean over the 4 phases) on the space-to-depth grid; null = none
+    __nv_bfloat16* pool_out;
     int n_ntiles;
     int tiles_y;                 // row bands per image
     int sx;                      // 8-pixel column groups per band
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     // k ^ (r & 7)) and one TMA tensor store per 64 columns; the box {64 ch, 8 px, 4 rows} is clipped
                     // at the tensor edges by the TMA unit, so partial tiles need no masks.
                     const uint32_t stg = s_base + C::OFF_EPI + warp * 4096;
+                    float pacc[SCHED == 2 ? 32 : 1];     // space-to-depth grid: running sum over the 4 phases (pool_out)
 #pragma unroll 1
                     for (int c = 0; c < NT; c += 64) {
                         uint32_t o[32];
@@ -398,6 +402,60 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                         if (lane == 0) {
                             tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * quad, t.n);
                             bulk_commit_group();
+                        }
+                        if (p.pool_out != nullptr) {
+                            if constexpr (SCHED == 2) {
+                                // mean over the 4 phases of this block pixel, of the bf16-rounded outputs, h-major like
+                                // ATen's avg_pool2d: ((p0 + p1) + p2) + p3.  This chunk holds phases c/32 and c/32 + 1.
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const float2 a = unpack_bf16x2(o[i]), b = unpack_bf16x2(o[16 + i]);
+                                    if (c == 0) { pacc[2 * i] = a.x + b.x; pacc[2 * i + 1] = a.y + b.y; }
+                                    else { pacc[2 * i] = (pacc[2 * i] + a.x) + b.x; pacc[2 * i + 1] = (pacc[2 * i + 1] + a.y) + b.y; }
+                                }
+                                if (c == NT - 64 && ok) {
+                                    uint4* d4 = reinterpret_cast<uint4*>(p.pool_out + pix * (size_t)(NT / 4));
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        d4[k] = make_uint4(pack_bf16x2(pacc[8 * k] * 0.25f, pacc[8 * k + 1] * 0.25f),
+                                                           pack_bf16x2(pacc[8 * k + 2] * 0.25f, pacc[8 * k + 3] * 0.25f),
+                                                           pack_bf16x2(pacc[8 * k + 4] * 0.25f, pacc[8 * k + 5] * 0.25f),
+                                                           pack_bf16x2(pacc[8 * k + 6] * 0.25f, pacc[8 * k + 7] * 0.25f));
+                                }
+                            } else {
+                                // 2x2 mean over this warp's 4 x 8 pixels from the staged bf16 tile: lane -> pooled pixel
+                                // (lane >> 2) of the 2 x 4 and channels 16 * (lane & 3) .. +15 of the 64-channel chunk
+                                const int pp = lane >> 2, q = lane & 3, pyl = pp >> 2, pxl = pp & 3;
+                                float acc[16];
+#pragma unroll
+                                for (int dd = 0; dd < 4; ++dd) {                 // (dy, dx) = (0,0) (0,1) (1,0) (1,1)
+                                    const int r = (2 * pyl + (dd >> 1)) * 8 + 2 * pxl + (dd & 1);
+#pragma unroll
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        uint32_t v0, v1, v2, v3;
+                                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                                     : "r"(stg + r * 128 + (((2 * q + kk) ^ (r & 7)) << 4)));
+                                        const uint32_t vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) {
+                                            const float2 f = unpack_bf16x2(vv[i]);
+                                            if (dd == 0) { acc[8 * kk + 2 * i] = f.x; acc[8 * kk + 2 * i + 1] = f.y; }
+                                            else { acc[8 * kk + 2 * i] += f.x; acc[8 * kk + 2 * i + 1] += f.y; }
+                                        }
+                                    }
+                                }
+                                const int py = (t.ty * kTileH + 4 * quad) / 2 + pyl, px = (t.sx0 + j) * 4 + pxl;
+                                if (py < (p.H >> 1) && px < (p.W >> 1)) {
+                                    uint4* d4 = reinterpret_cast<uint4*>(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride +
+                                                                         t.nt * NT + c + 16 * q);
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k)
+                                        d4[k] = make_uint4(pack_bf16x2(acc[8 * k] * 0.25f, acc[8 * k + 1] * 0.25f),
+                                                           pack_bf16x2(acc[8 * k + 2] * 0.25f, acc[8 * k + 3] * 0.25f),
+                                                           pack_bf16x2(acc[8 * k + 4] * 0.25f, acc[8 * k + 5] * 0.25f),
+                                                           pack_bf16x2(acc[8 * k + 6] * 0.25f, acc[8 * k + 7] * 0.25f));
+                                }
+                            }
                         }
                     }
                 } else if (NT == 16) {                   // fp32 [.,16] epilogue of the `last` convs

@@ -92,11 +92,11 @@ static Schedule build_schedule() {
             else { m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? 13 : (cin == 32 ? 11 : 12); m.n_stages = 2 * (cin / 32); }
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
-            const bool xform = (src == K_POOL || src == K_UP);
+            // K_POOL sources are read from the pooled copy the previous level's block.2 epilogue wrote: plain convs
             if (level == 1) {
-                if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }
-                else { m.cfg = xform ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
-            } else { m.cfg = xform ? 5 : big_cfg(); m.n_stages = cin / 64; }
+                if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }                // 32 channels: cp.async producers (KCS = 32)
+                else { m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
+            } else { m.cfg = (src == K_UP) ? 5 : big_cfg(); m.n_stages = cin / 64; }
         }
         place(m);
         if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns
@@ -165,7 +165,7 @@ using namespace rrin;
 struct rrin_engine {
     int Np, Nt, H, W, pair_mul;
     size_t ws_bytes;
-    size_t off_tmp[3], off_skip[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
+    size_t off_tmp[3], off_skip[4], off_pool[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
     std::vector<Launch> launches;
     const void* tmap_ws = nullptr;              // workspace base the cached tensor maps were encoded for
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every launch
@@ -209,7 +209,8 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
         if (counts_flops) {
             ln.flops = 2.0 * 9 * L.cin * L.cout * lp;
             double in_b = 2.0 * (L.src == K_HEAD ? 16 : L.cin) * lp;
-            if (L.src == K_POOL) in_b *= 4; else if (L.src == K_UP) in_b /= 4;
+            if (L.src == K_UP) in_b /= 4;
+            if (ln.cd.pool_out) in_b += 2.0 * L.cout * lp / 4;                  // pooled second output
             const Pack& pk = ln.use_fold == 1 ? L.fold : (ln.use_fold == 2 ? L.strip : L.main);
             ln.bytes = in_b + (L.is_last ? 16.0 * lp : 2.0 * L.cout * lp) + (double)conv_packed_weight_bytes(pk.cfg, pk.n_cols, pk.n_stages, pk.sched);
         }
@@ -222,10 +223,10 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
         const int c = 32 << i;
         {   // block.0
             Launch ln = base(li, 0, i == 0 ? 1 : i);
-            if (i == 0) { ln.cd.mode = SRC_PLAIN; ln.cd.c0 = 64; ln.cd.cout_stride = 128; }
-            else if (i == 1) { ln.cd.mode = SRC_POOL_S2D; ln.cd.c0 = 128; ln.cd.cout_stride = c; }
-            else { ln.cd.mode = SRC_POOL; ln.cd.c0 = c / 2; ln.cd.cout_stride = c; }
-            ln.cd.src0 = enc(x); ln.cd.out = enc(tmp[0]); ln.cd.epi = EPI_BF16;
+            ln.cd.mode = SRC_PLAIN;                    // level >= 1: avg_pool2d (unet.py:46) was applied by the previous block.2 epilogue
+            if (i == 0) { ln.cd.c0 = 64; ln.cd.cout_stride = 128; }
+            else { ln.cd.c0 = c / 2; ln.cd.cout_stride = c; }
+            ln.cd.src0 = enc(i == 0 ? x : e->off_pool[i - 1]); ln.cd.out = enc(tmp[0]); ln.cd.epi = EPI_BF16;
             finish(ln, "", true); ++li;
         }
         {   // block.2
@@ -233,6 +234,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
             ln.cd.mode = SRC_PLAIN; ln.cd.c0 = (i == 0) ? 128 : c; ln.cd.cout_stride = (i == 0) ? 128 : c;
             const size_t o = (i < d - 1) ? e->off_skip[i] : tmp[1];
             ln.cd.src0 = enc(tmp[0]); ln.cd.out = enc(o); ln.cd.epi = EPI_BF16;
+            if (i < d - 1) ln.cd.pool_out = enc(e->off_pool[i]);               // skip + its 2x2 mean for the next level
             finish(ln, "", true); ++li;
             x = o;
         }
@@ -351,6 +353,7 @@ int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** o
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     for (int i = 0; i < 3; ++i) e->off_tmp[i] = take(lvl_bytes(B, H, W, 0));
     for (int l = 0; l < 4; ++l) e->off_skip[l] = take(lvl_bytes(B, H, W, l));
+    for (int l = 0; l < 4; ++l) e->off_pool[l] = take(lvl_bytes(B, H, W, l) / 4);          // avg_pool2d of level l: level-(l+1) grid, level-l channels
     e->off_h16 = take((size_t)B * px * 16 * 2);
     e->off_flow4 = take((size_t)n_pairs * px * 16);
     e->off_u4 = take((size_t)n_samples * px * 16);
@@ -415,7 +418,7 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             const Layer& L = s.layers[ln.layer];
             const Pack& pk = ln.use_fold == 1 ? L.fold : (ln.use_fold == 2 ? L.strip : L.main);
             ConvDesc cd = ln.cd;
-            cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out);
+            cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out); cd.pool_out = dec(cd.pool_out);
             cd.wpack = blob + pk.w_off;
             cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
             if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; cd.tmap_out = ln.tmap[2]; }
@@ -490,11 +493,11 @@ int rrin_pack_conv_raw(int kind, const float* w, const float* b, int cout, int c
 }
 int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                  int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
-                 int act, int ring_only, int cfg, void* stream) {
+                 int act, int ring_only, int cfg, void* pool_out, void* stream) {
     ConvDesc cd;
     cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = src_mode; cd.pad_clamp = pad_clamp;
     cd.N = N; cd.H = H; cd.W = W; cd.sched = sched; cd.n_cols = n_cols; cd.wpack = wpack; cd.bias = bias_pack;
-    cd.out = out; cd.epi = epi; cd.cout_stride = cout_stride; cd.act = act; cd.ring_only = ring_only; cd.cfg = cfg;
+    cd.out = out; cd.epi = epi; cd.cout_stride = cout_stride; cd.act = act; cd.ring_only = ring_only; cd.cfg = cfg; cd.pool_out = pool_out;
     return conv_launch(cd, static_cast<cudaStream_t>(stream));
 }
 int rrin_pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, void* stream) {

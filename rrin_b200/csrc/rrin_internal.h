@@ -38,6 +38,7 @@ struct ConvDesc {
     const void* wpack = nullptr;
     const float* bias = nullptr;
     void* out = nullptr;
+    void* pool_out = nullptr;     // TMA-epilogue configs: also write avg_pool2d(out, 2) (see ConvParamsV2::pool_out), or null
     int epi = EPI_BF16;
     int cout_stride = 0;
     int act = 0;

@@ -64,14 +64,14 @@ def pack(kind, cfg, weight, bias, n_stages, sched):
     return wp, bp, n_cols
 
 
-def launch(src0, src1, c0, c1, mode, pad_clamp, n, gh, gw, sched, n_cols, wp, bp, out, epi, cout_stride, act, ring_only, cfg):
+def launch(src0, src1, c0, c1, mode, pad_clamp, n, gh, gw, sched, n_cols, wp, bp, out, epi, cout_stride, act, ring_only, cfg, pool_out=None):
     check(lib().rrin_conv3x3(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, pad_clamp, n, gh, gw,
                              sched, n_cols, wp.data_ptr(), bp.data_ptr(), out.data_ptr(), epi, cout_stride, int(act), int(ring_only),
-                             cfg, stream()), "rrin_conv3x3")
+                             cfg, pool_out.data_ptr() if pool_out is not None else None, stream()), "rrin_conv3x3")
     torch.cuda.synchronize()
 
 
-def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=False, out=None):
+def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=False, out=None, pool_out=None):
     """Levels >= 1: NHWC bf16 sources, 9-tap schedule.  Returns (NCHW fp32, raw NHWC bf16 tensor)."""
     kcs, kb, nt, _ = cfg_info(cfg)
     cout, cin = weight.shape[:2]
@@ -80,11 +80,11 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
     wp, bp, n_cols = pack(PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if out is None:
         out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg)
+    launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg, pool_out)
     return out.float().permute(0, 3, 1, 2), out
 
 
-def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring_only=False, out=None):
+def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring_only=False, out=None, pool_out=None):
     """Level 0: space-to-depth sources [N,hb,wb,4,C] (or NHWC [N,hb,wb,C] for SRC_UP_S2D), 16-entry schedule
     (half-phase 8-entry schedule with twice the stages for the TMA configs 11..13).
     Returns hi-res NCHW fp32 [N,cout,2hb,2wb] and the raw output tensor."""
@@ -102,7 +102,7 @@ def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring
     if out is None:
         out = torch.full((n, hb, wb, 4, cpp), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, hb, wb, sched, n_cols, wp, bp, out, EPI_F32X16 if f32 else EPI_BF16,
-           16 if f32 else nt, act, ring_only, cfg)
+           16 if f32 else nt, act, ring_only, cfg, pool_out)
     return from_s2d(out)[:, :cout], out
 
 

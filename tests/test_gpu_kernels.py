@@ -154,6 +154,35 @@ def test_conv_level0_s2d(case):
     _check(name, y, ref, f32=(cfg in (2, 13)))
 
 
+# ------------------------------------------------------------------ pooled second output of the TMA epilogue (unet.py:46)
+@pytest.mark.parametrize("cfg,cin,cout,n,h,w", [(14, 64, 64, 1, 24, 40), (14, 64, 64, 2, 184, 72), (16, 128, 128, 1, 12, 20),
+                                                (16, 256, 256, 1, 100, 72), (16, 128, 128, 2, 208, 104)],
+                         ids=["l1", "l1_many", "l2", "l3_ntiles", "l2_many"])
+def test_conv_with_pooled_output(cfg, cin, cout, n, h, w):
+    x = _rand(n, cin, h, w, 1)
+    wgt, b = _rand_wb(cout, cin, 3)
+    pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    y, raw = G.conv_normal(G.nhwc(x), None, G.SRC_PLAIN, n, h, w, wgt, b, True, cfg, pool_out=pool)
+    _check("conv", y, G.reference(x, wgt, b, True))
+    want = G.bf16_round(torch.nn.functional.avg_pool2d(raw.float().permute(0, 3, 1, 2), 2))       # pool of the STORED bf16 tensor
+    got = pool.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2 ** -8 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 64, 128), (2, 48, 80), (1, 368, 368)], ids=["small", "partial_n2", "many"])
+def test_conv_level0_with_pooled_output(n, h, w):
+    x = _rand(n, 32, h, w, 1)
+    wgt, b = _rand_wb(32, 32, 3)
+    pool = torch.full((n, h // 2, w // 2, 32), float("nan"), dtype=torch.bfloat16, device="cuda")
+    y, raw = G.conv_s2d(G.to_s2d(x), None, G.SRC_PLAIN, n, h // 2, w // 2, wgt, b, True, G.T_L0, 1, pool_out=pool)
+    _check("conv", y, G.reference(x, wgt, b, True))
+    want = G.bf16_round(torch.nn.functional.avg_pool2d(G.from_s2d(raw), 2))
+    got = pool.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2 ** -8 * max(1.0, want.abs().max().item())
+
+
 # ------------------------------------------------------------------ folded upsample + exact ring
 @pytest.mark.parametrize("ring", ["strips", "tiles"])
 @pytest.mark.parametrize("level0,cin,cout,n,hc,wc", [(True, 64, 32, 1, 56, 72), (False, 128, 64, 1, 56, 72), (True, 64, 32, 2, 40, 64),
