@@ -331,6 +331,8 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const long want = (total + c.msub - 1) / c.msub;
     const int grid = (int)(want < sms ? (want > 0 ? want : 1) : sms);
     // diagnostics only: RRIN_CONV_PROF=1 prints block 0's per-role wait cycles after every launch (synchronises)
+    static const int dbg = getenv("RRIN_CONV_DBG") ? atoi(getenv("RRIN_CONV_DBG")) : 0;
+    p.dbg = dbg;
     static const bool prof_on = getenv("RRIN_CONV_PROF") != nullptr;
     static unsigned long long* prof_buf = nullptr;
     if (prof_on) {

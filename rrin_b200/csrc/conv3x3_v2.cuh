@@ -49,6 +49,7 @@ struct ConvParamsV2 {
     int sx;                      // 8-pixel column groups per band
     int units_per_nt;            // N * tiles_y * sx
     int total_units;             // n_ntiles * units_per_nt
+    int dbg;                     // diagnostics (RRIN_CONV_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores (timing only, wrong results)
     unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
 };
 
@@ -187,6 +188,14 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     TileWalkV2 walk;
     walk.init(p);
     TileV2 t;
+    // Streamed weights: every CTA walks the same (stage, entry) block sequence, so in lock-step all 148 SMs would ask L2
+    // for the same 8-16 KB block at the same moment.  Rotating the stage order per CTA (K-sum order is free) spreads the
+    // requests over the layer's stages.
+    // (Half-entry schedule: even rotations only -- the first stage processed must start with a full-width entry, which
+    // initialises all 128 accumulator columns.)
+    // The rotation is a function of the tile's row band and n-tile only, so a pixel's K-sum order -- and with it the
+    // bit pattern of the result -- does not depend on the batch size or the grid.
+    auto rot_of = [&](const TileV2& tt) { return RES ? 0 : (int)((unsigned)(tt.ty + tt.nt) % (unsigned)nst) & (C::HALF ? ~1 : ~0); };
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
 
     if (warp == W_A) {
@@ -196,11 +205,14 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             long long tw = 0, t00 = clock64();
             while (walk.next<MSUB>(p, t)) {
                 const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;          // halo origin; OOB -> zero fill
-                for (int st = 0; st < nst; ++st, ++it) {
+                const int st_rot = rot_of(t);
+                for (int si = 0; si < nst; ++si, ++it) {
+                    const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                     const int stage = it % SA;
                     const long long c0 = prof ? clock64() : 0;
                     mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
                     if (prof) tw += clock64() - c0;
+                    if (p.dbg & 1) { mbar_arrive(a_full(stage)); continue; }
                     mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
                     const bool first = st < p.c0_chunks;
                     tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n, a_full(stage));
@@ -239,14 +251,16 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 int cnt = 0;
                 while (walk.next<MSUB>(p, t)) {
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);
-                    for (int b = 0; b < nblk; ++b, ++cnt) {
+                    const int st_rot = rot_of(t);
+                    for (int bi = 0; bi < nblk; ++bi, ++cnt) {
                         const int slot = cnt % SB;
+                        const int si = bi / N_ENT, e = bi - si * N_ENT;
+                        const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
+                        const int b = st * N_ENT + e;
                         uint32_t bytes = C::B_BLOCK;
-                        if (C::HALF) {
-                            const int st = b / N_ENT, e = b - st * N_ENT;
-                            if ((st & 1) ? (e < 4) : (e >= 4)) bytes = C::B_BLOCK / 2;
-                        }
+                        if (C::HALF && ((st & 1) ? (e < 4) : (e >= 4))) bytes = C::B_BLOCK / 2;
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
+                        if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
                         mbar_arrive_expect_tx(b_full(slot), bytes);
                         bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), bytes, b_full(slot));
                     }
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             long long twa = 0, twb = 0, twc = 0, t00 = clock64();
             // one K stage with a compile-time stage parity: every entry offset, half-entry shape and resident block
             // offset below is an immediate
-            auto run_stage = [&](auto par_c, const int st, const int stage, const int m, const int ntile) {
+            auto run_stage = [&](auto par_c, const int st, const bool first_stage, const int stage, const int m, const int ntile) {
                 constexpr int PAR = decltype(par_c)::value;
                 const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
                 const uint32_t b_st = RES ? (uint32_t)((st * C::B_STAGE) >> 4) : 0u;
@@ -298,7 +312,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
 #pragma unroll 1
                     for (int j = 0; j < m; ++j) {
                         const int ts = (slot0 + j) % C::SLOTS;
-                        if (e == 0 && st == 0) {    // first write into this accumulator slot: the epilogue must have drained it
+                        if (e == 0 && first_stage) {    // first write into this accumulator slot: the epilogue must have drained it
                             const long long c0 = prof ? clock64() : 0;
                             mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
                             tc_fence_after();
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
 #pragma unroll
                         for (int s = 0; s < KB / 16; ++s)
                             umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
-                                         (e | s) != 0 || st != 0);
+                                         (e | s) != 0 || !first_stage);
                     }
                     if (!RES) umma_commit(b_empty(slot));
                 }
@@ -315,14 +329,16 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             };
             while (walk.next<MSUB>(p, t)) {
                 const int m = t.m;
-                for (int st = 0; st < nst; ++st, ++it) {
+                const int st_rot = rot_of(t);
+                for (int si = 0; si < nst; ++si, ++it) {
+                    const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                     const int stage = it % SA;
                     { const long long c0 = prof ? clock64() : 0;
                       mbar_wait(a_full(stage), (it / SA) & 1);
                       if (prof) twa += clock64() - c0; }
                     tc_fence_after();
-                    if (SCHED == 2 && (st & 1)) run_stage(std::integral_constant<int, 1>{}, st, stage, m, ntile);
-                    else run_stage(std::integral_constant<int, 0>{}, st, stage, m, ntile);
+                    if (SCHED == 2 && (st & 1)) run_stage(std::integral_constant<int, 1>{}, st, si == 0, stage, m, ntile);
+                    else run_stage(std::integral_constant<int, 0>{}, st, si == 0, stage, m, ntile);
                 }
                 for (int j = 0; j < m; ++j) {
                     const int ts = (slot0 + j) % C::SLOTS;
@@ -399,7 +415,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                                          "r"(o[4 * k]), "r"(o[4 * k + 1]), "r"(o[4 * k + 2]), "r"(o[4 * k + 3]) : "memory");
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(p.dbg & 4)) {
                             tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * quad, t.n);
                             bulk_commit_group();
                         }
