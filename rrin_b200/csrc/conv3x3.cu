@@ -41,7 +41,8 @@ namespace rrin {
 // 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0, 1>  level-0 `last` 32->{2,3,4}, fp32 output
 // 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1>  level-1 64->64, weights resident
 // 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 4, 2,  3, TAPS9, 0, 1, 1>  levels >= 2 plain / cat
+// 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
+//                                                 the next tile's MMAs start as soon as the first slots are drained)
 // 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0, 1>  same tile, per-thread stores: folded upsample conv scattering into level 1
 // 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
 #define RRIN_CONV2_CONFIGS(X)                \
@@ -51,7 +52,7 @@ namespace rrin {
     X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 1)  \
     X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1)   \
     X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1)   \
-    X(16, 64, 64, 128, 4, 2, 3, 0, 0, 1, 1)  \
+    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)  \
     X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0, 1)  \
     X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)
 

@@ -281,38 +281,42 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             int it = 0, cnt = 0, slot0 = 0, ntile = 0;
             uint32_t use_bits = 0;                      // bit s: parity of the number of finished uses of slot s
             long long twa = 0, twb = 0, twc = 0, t00 = clock64();
-            // one K stage with a compile-time stage parity: every entry offset, half-entry shape and resident block
-            // offset below is an immediate
-            auto run_stage = [&](auto par_c, const int st, const bool first_stage, const int stage, const int m, const int ntile) {
-                constexpr int PAR = decltype(par_c)::value;
+            bool a_rdy = false, b_rdy = false;      // barrier of the NEXT stage / weight block already seen complete (polled ahead)
+            // One K stage as straight-line code: stage parity PAR and sub-tile count M are compile-time, so every entry
+            // offset, half-entry shape, resident block offset and accumulator column is an immediate on three bases
+            // (A stage, weight block, first accumulator slot).  A tight issue stream is what keeps the tensor pipe busy:
+            // measured (tools/umma_queue_probe.cu) a 128x128x16 MMA retires in 64 cycles only if its issue costs < 64.
+            auto run_stage = [&](auto par_c, auto m_c, const int st, const bool first_stage, const int stage) {
+                constexpr int PAR = decltype(par_c)::value, M = decltype(m_c)::value;
                 const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
                 const uint32_t b_st = RES ? (uint32_t)((st * C::B_STAGE) >> 4) : 0u;
 #pragma unroll
                 for (int e = 0; e < N_ENT; ++e) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int hf = C::half_of(PAR, e);                       // 0 full, 1 lower 64 columns, 2 upper
                     int slot = 0;
                     uint32_t b_e;
                     if (RES) {
-                        if (ntile == 0) { mbar_wait(b_full(st * N_ENT + e), 0); tc_fence_after(); }
                         b_e = (hf ? b_lo0h : b_lo0) + b_st + (uint32_t)(C::res_off(PAR, e) >> 4);
                     } else {
                         slot = cnt % SB;
-                        const long long c0 = prof ? clock64() : 0;
-                        mbar_wait(b_full(slot), (cnt / SB) & 1);
-                        if (prof) twb += clock64() - c0;
+                        if (!b_rdy) {
+                            const long long c0 = prof ? clock64() : 0;
+                            mbar_wait(b_full(slot), (cnt / SB) & 1);
+                            if (prof) twb += clock64() - c0;
+                        }
                         tc_fence_after();
                         ++cnt;
+                        b_rdy = mbar_test(b_full(cnt % SB), (cnt / SB) & 1);  // next block: polled while this entry's MMAs issue
                         b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
                     }
                     const uint32_t a_e = a_st + C::ent_off(PAR, e);
                     const uint32_t b_ks = hf ? 2 * 64 : 2 * NT;               // descriptor step per K=16: two core-matrix planes
                     const uint32_t id = hf ? idesc_h : idesc;
                     const uint32_t dcol = (hf == 2) ? 64 : 0;
-#pragma unroll 1
-                    for (int j = 0; j < m; ++j) {
-                        const int ts = (slot0 + j) % C::SLOTS;
-                        if (e == 0 && first_stage) {    // first write into this accumulator slot: the epilogue must have drained it
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        const int ts = (slot0 + j) % C::SLOTS;                // accumulator slots are used round-robin
+                        if (e == 0 && first_stage) {    // first write into this slot: the epilogue must have drained its previous use
                             const long long c0 = prof ? clock64() : 0;
                             mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
                             tc_fence_after();
@@ -327,18 +331,29 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 }
                 umma_commit(a_empty(stage));
             };
+            auto run_m = [&](auto par_c, const int m, const int st, const bool first_stage, const int stage) {
+                if (m == 1) run_stage(par_c, std::integral_constant<int, 1>{}, st, first_stage, stage);
+                if constexpr (MSUB >= 2) { if (m == 2) run_stage(par_c, std::integral_constant<int, 2>{}, st, first_stage, stage); }
+                if constexpr (MSUB >= 3) { if (m == 3) run_stage(par_c, std::integral_constant<int, 3>{}, st, first_stage, stage); }
+                if constexpr (MSUB >= 4) { if (m == 4) run_stage(par_c, std::integral_constant<int, 4>{}, st, first_stage, stage); }
+            };
             while (walk.next<MSUB>(p, t)) {
                 const int m = t.m;
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                     const int stage = it % SA;
-                    { const long long c0 = prof ? clock64() : 0;
-                      mbar_wait(a_full(stage), (it / SA) & 1);
-                      if (prof) twa += clock64() - c0; }
+                    if (!a_rdy) {
+                        const long long c0 = prof ? clock64() : 0;
+                        mbar_wait(a_full(stage), (it / SA) & 1);
+                        if (prof) twa += clock64() - c0;
+                    }
+                    if (RES && ntile == 0)                                    // resident weights: first use of this stage's blocks
+                        for (int e = 0; e < N_ENT; ++e) mbar_wait(b_full(st * N_ENT + e), 0);
                     tc_fence_after();
-                    if (SCHED == 2 && (st & 1)) run_stage(std::integral_constant<int, 1>{}, st, si == 0, stage, m, ntile);
-                    else run_stage(std::integral_constant<int, 0>{}, st, si == 0, stage, m, ntile);
+                    a_rdy = mbar_test(a_full((it + 1) % SA), ((it + 1) / SA) & 1);   // next stage: polled while this one issues
+                    if (SCHED == 2 && (st & 1)) run_m(std::integral_constant<int, 1>{}, m, st, si == 0, stage);
+                    else run_m(std::integral_constant<int, 0>{}, m, st, si == 0, stage);
                 }
                 for (int j = 0; j < m; ++j) {
                     const int ts = (slot0 + j) % C::SLOTS;
