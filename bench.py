@@ -3,12 +3,13 @@
 
 Contract: ``python bench.py --gpus N --steps K --warmup W`` (N>1: launched under torchrun,
 one rank per GPU).  A *step* is one pass of the hot path (``Net.forward``,
-/root/reference/model.py:59-65) over one 1920x1088 frame pair at t=0.5 -- the unit of
-BASELINE.json configs[2] ("1080p 2x interpolation of a 240-frame synthetic clip, sharded over
-1/2/4/8 B200").  Each rank owns a contiguous shard of the synthetic clip, device resident, and
-interpolates K consecutive pairs of it; there is no data-path collective (frame pairs are
-independent), torch.distributed is used only for the barrier and the max over
-ranks of the device-timed region.  One JSON line is printed by rank 0.
+/root/reference/model.py:59-65) over one batch of ``--batch`` (default 2) consecutive
+1920x1088 frame pairs at t=0.5 -- the unit of BASELINE.json configs[2] ("1080p 2x
+interpolation of a 240-frame synthetic clip, sharded over 1/2/4/8 B200").  Each rank owns a
+contiguous shard of the synthetic clip (rrin_b200.sharding), device resident, and interpolates
+K consecutive batches of it; there is no data-path collective (frame pairs are independent,
+SURVEY.md 8(e)), torch.distributed is used only for the barrier and the max over ranks of the
+device-timed region.  One JSON line is printed by rank 0; ``value`` counts interpolated frames.
 
 ``--impl reference`` times the reference's own CPU path instead: the oracle port
 (oracle/rrin_oracle.py: the same torch CPU operators at the same call sites as the reference,
@@ -157,8 +158,10 @@ def run_gpu(args):
 
     # this rank's shard of the synthetic 240-frame clip (contiguous pairs; one frame shared by
     # consecutive pairs), generated on the device: smooth content + per-frame shift, U[0,1)
-    K, Wm = args.steps, args.warmup
-    pairs_per_rank = (CLIP_FRAMES - 1 + world - 1) // world
+    from rrin_b200 import sharding
+    K, Wm, B = args.steps, args.warmup, args.batch
+    lo_pair, hi_pair = sharding.pair_range(CLIP_FRAMES, rank, world)
+    pairs_per_rank = hi_pair - lo_pair
     n_frames = min(pairs_per_rank, 12) + 1                      # frames kept resident; steps cycle over them
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     lo = torch.rand(1, 3, H // 8 + 8, W // 8 + 8, generator=g, device=dev)
@@ -169,8 +172,16 @@ def run_gpu(args):
     del big, lo
 
     def pair(i):
-        j = i % (n_frames - 1)
-        return frames[j], frames[j + 1]
+        """Batch i of this rank's shard: B consecutive frame pairs (frame j+1 of one pair is frame j of the next)."""
+        js = [(i * B + k) % (n_frames - 1) for k in range(B)]
+        if B == 1:
+            return frames[js[0]], frames[js[0] + 1]
+        return torch.cat([frames[j] for j in js]), torch.cat([frames[j + 1] for j in js])
+
+    batches = [pair(i) for i in range(max(1, min(K + max(Wm, 3), (n_frames - 1) // B + 1)))]   # assembled outside the timed region
+
+    def batch(i):
+        return batches[i % len(batches)]
 
     def barrier():
         if world > 1:
@@ -179,14 +190,14 @@ def run_gpu(args):
 
     # ---------------- device-resident throughput (`value`)
     for i in range(max(Wm, 3)):
-        net(*pair(i), t=0.5)
+        net(*batch(i), t=0.5)
     barrier()
     clocks = ClockSampler(local)
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        y = net(*pair(i), t=0.5)
+        y = net(*batch(i), t=0.5)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -196,11 +207,11 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_max = float(tmax.item())
-    value = world * K / (ms_max * 1e-3)
+    value = world * K * B / (ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers (`e2e`)
-    hp = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in [pair(i) for i in range(min(4, n_frames - 1))]]
-    out_host = torch.empty(1, 3, H, W).pin_memory()
+    hp = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in batches[:4]]
+    out_host = torch.empty(B, 3, H, W).pin_memory()
     ke = max(3, min(K, 20))
 
     def e2e_step(i):
@@ -219,7 +230,7 @@ def run_gpu(args):
     t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * ke / (float(t2.item()) * 1e-3)
+    e2e_value = world * ke * B / (float(t2.item()) * 1e-3)
     frame_bytes = 3 * H * W * 4
 
     line = None
@@ -231,7 +242,7 @@ def run_gpu(args):
         acc = [0.0] * len(table)
         reps = 3
         for r in range(reps):
-            for i, v in enumerate(eng.profile(w, *pair(r), 0.5)):
+            for i, v in enumerate(eng.profile(w, *batch(r), 0.5)):
                 acc[i] += v / reps
         classes = {}
         for (name, layer, fl, by), t in zip(table, acc):
@@ -272,16 +283,18 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 operands, f32 accumulate", "data": "synthetic",
-                "config": {"workload": "1080p (1920x1088) 2x interpolation of a synthetic clip, one frame pair per step, t=0.5, "
-                                       "random-init weights (torch.manual_seed(0))",
+                "config": {"workload": f"1080p (1920x1088) 2x interpolation of a synthetic clip, one batch of {B} consecutive frame pair(s) "
+                                       "per step, t=0.5, random-init weights (torch.manual_seed(0))",
+                           "batch": B,
                            "sharding": f"{world} rank(s), contiguous shards of the {CLIP_FRAMES}-frame clip, no collective",
-                           "l2": "per-step working set (~0.65 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                           "l2": f"per-step working set (~{0.75 * B:.1f} GB of activations) exceeds the 126 MB L2; no explicit flush",
                            "tflop_per_frame": FLOP_PER_PX * H * W / 1e12,
-                           "tensor_frac_of_burst_peak": value / world * FLOP_PER_PX * H * W / 1e12 / peaks["tf_burst"]},
+                           "tensor_frac_of_burst_peak": value / world * FLOP_PER_PX * H * W / 1e12 / peaks["tf_burst"],
+                           "tensor_frac_of_sustained_peak": value / world * FLOP_PER_PX * H * W / 1e12 / peaks["tf_sustained"]},
                 "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 2 * frame_bytes,
-                        "d2h_bytes_per_step": frame_bytes, "steps": ke,
-                        "api": "Net.forward(img1.cuda(), img2.cuda(), t) then .cpu() from pinned host buffers, sync per frame"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * frame_bytes,
+                        "d2h_bytes_per_step": B * frame_bytes, "steps": ke,
+                        "api": "Net.forward(img1.cuda(), img2.cuda(), t) then .cpu() from pinned host buffers, sync per step"},
                 "gpu_launches": eng.num_launches * K,
                 "roofline": roofline, "cpu_baseline": cpu}
     if world > 1:
@@ -294,8 +307,9 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=2, help="frame pairs per step (per GPU)")
     ap.add_argument("--impl", default="rrin_b200", choices=["rrin_b200", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":
