@@ -147,6 +147,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep stdout to the one JSON line (no version banner)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 

@@ -49,7 +49,8 @@ struct ConvParamsV2 {
     int sx;                      // 8-pixel column groups per band
     int units_per_nt;            // N * tiles_y * sx
     int total_units;             // n_ntiles * units_per_nt
-    int dbg;                     // diagnostics (RRIN_CONV_DBG): 1 skip activation loads, 2 skip weight loads, 4 skip stores (timing only, wrong results)
+    int dbg;                     // diagnostics (RRIN_CONV_DBG, timing only, wrong results): 1 skip activation loads, 2 skip weight loads,
+                                 // 4 skip stores, 8 skip the whole epilogue, 16 issue one MMA per (stage, sub-tile)
     unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
 };
 
@@ -116,23 +117,31 @@ struct ConvCfgV2 {
 struct TileV2 { int nt, n, ty, sx0, m; };
 
 // The CTA's share of the work units and its cursor; every warp role walks the identical sequence.
+// The cursor position (n-tile, image, band, column group) is carried incrementally: no divisions per tile.
 struct TileWalkV2 {
     int u, u_end;
+    int nt, n, ty, sx0;          // decomposition of u
     __device__ __forceinline__ void init(const ConvParamsV2& p) {
         u = (int)((long long)p.total_units * blockIdx.x / gridDim.x);
         u_end = (int)((long long)p.total_units * (blockIdx.x + 1) / gridDim.x);
+        nt = u / p.units_per_nt;
+        int r = u - nt * p.units_per_nt;
+        const int band = r / p.sx;
+        sx0 = r - band * p.sx;
+        n = band / p.tiles_y;
+        ty = band - n * p.tiles_y;
     }
     template <int MSUB>
     __device__ __forceinline__ bool next(const ConvParamsV2& p, TileV2& t) {
         if (u >= u_end) return false;
-        t.nt = u / p.units_per_nt;
-        int r = u - t.nt * p.units_per_nt;
-        const int band = r / p.sx;
-        t.sx0 = r - band * p.sx;
-        t.n = band / p.tiles_y;
-        t.ty = band - t.n * p.tiles_y;
-        t.m = min(MSUB, min(p.sx - t.sx0, u_end - u));
+        t.nt = nt; t.n = n; t.ty = ty; t.sx0 = sx0;
+        t.m = min(MSUB, min(p.sx - sx0, u_end - u));
         u += t.m;
+        sx0 += t.m;
+        if (sx0 == p.sx) {                      // next band / image / n-tile
+            sx0 = 0;
+            if (++ty == p.tiles_y) { ty = 0; if (++n == p.N) { n = 0; ++nt; } }
+        }
         return true;
     }
 };
@@ -324,8 +333,9 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                         }
 #pragma unroll
                         for (int s = 0; s < KB / 16; ++s)
-                            umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
-                                         (e | s) != 0 || !first_stage);
+                            if (!(p.dbg & 16) || (e | s) == 0)                 // diagnostics: one MMA per (stage, sub-tile) only
+                                umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
+                                             (e | s) != 0 || !first_stage);
                     }
                     if (!RES) umma_commit(b_empty(slot));
                 }
@@ -389,6 +399,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * NT;
+                if (p.dbg & 8) { tc_fence_before(); mbar_arrive(acc_empty(ts)); continue; }   // diagnostics: no epilogue work at all
                 if constexpr (ETMA != 0) {
                     // bf16 NHWC via this warp's 4 KB staging buffer (32 pixels x 128 B, 16-byte chunk k of row r at
                     // k ^ (r & 7)) and one TMA tensor store per 64 columns; the box {64 ch, 8 px, 4 rows} is clipped

@@ -5,7 +5,7 @@
 tag=${1:-r01}; shift
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?" 
-python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err; echo "ref rc=$?"
 python tools/profile_step.py 1088 1920 1 > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/${tag}_launches.csv \
@@ -20,7 +20,7 @@ print(sum(1 for n, *_ in e.launch_table() if n.startswith("conv")))
 PY
 )
 for i in "$@"; do
-  ncu --set full --clock-control none --import-source on -k regex:conv3x3_umma -s $((nconv + i)) -c 1 \
+  ncu --set full --clock-control none --import-source on -k regex:conv3x3 -s $((nconv + i)) -c 1 \
       -o gpurun_out/${tag}_conv${i} -f python tools/profile_step.py 1088 1920 1 > gpurun_out/${tag}_ncu_conv${i}.log 2>&1
 done
 for g in warp_pack blend_pack; do

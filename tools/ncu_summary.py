@@ -22,7 +22,7 @@ KEYS = [
 
 
 def short(name):
-    m = re.search(r"(conv3x3_umma_kernel<[^>]*>|\w+_kernel)", name)
+    m = re.search(r"(conv3x3_\w+_kernel<[^>]*>|\w+_kernel)", name)
     return m.group(1) if m else name[:60]
 
 
