@@ -352,8 +352,8 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
         RRIN_CUDA_CHECK(cudaStreamSynchronize(stream));
         RRIN_CUDA_CHECK(cudaMemcpy(h, prof_buf, sizeof h, cudaMemcpyDeviceToHost));
         fprintf(stderr, "[conv prof cfg %d %dx%dx%d nst %d ent %d nt %d] block0: tiles %llu stages %llu | tma total %llu wait_empty %llu | "
-                        "mma total %llu wait_a %llu wait_b %llu wait_acc %llu | epi total %llu wait_full %llu\n",
-                cfg, d.N, d.H, d.W, p.n_stages, n_ent_of(d.sched), p.n_ntiles, h[7], h[2], h[1], h[0], h[6], h[3], h[4], h[5], h[9], h[8]);
+                        "mma total %llu wait_a %llu wait_b %llu wait_acc %llu issue %llu commit %llu | epi total %llu wait_full %llu\n",
+                cfg, d.N, d.H, d.W, p.n_stages, n_ent_of(d.sched), p.n_ntiles, h[7], h[2], h[1], h[0], h[6], h[3], h[4], h[5], h[10], h[11], h[9], h[8]);
     }
     return rc;
 }

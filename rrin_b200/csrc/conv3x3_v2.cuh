@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             int it = 0, cnt = 0, slot0 = 0, ntile = 0;
             uint32_t use_bits = 0;                      // bit s: parity of the number of finished uses of slot s
             long long twa = 0, twb = 0, twc = 0, t00 = clock64();
+            long long tmma = 0, tcom = 0;           // diagnostics: cycles inside the MMA issue blocks / in the per-entry commit
             bool a_rdy = false, b_rdy = false;      // barrier of the NEXT stage / weight block already seen complete (polled ahead)
             // One K stage as straight-line code: stage parity PAR and sub-tile count M are compile-time, so every entry
             // offset, half-entry shape, resident block offset and accumulator column is an immediate on three bases
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     const uint32_t b_ks = hf ? 2 * 64 : 2 * NT;               // descriptor step per K=16: two core-matrix planes
                     const uint32_t id = hf ? idesc_h : idesc;
                     const uint32_t dcol = (hf == 2) ? 64 : 0;
+                    const long long cm0 = prof ? clock64() : 0;
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
                         const int ts = (slot0 + j) % C::SLOTS;                // accumulator slots are used round-robin
@@ -337,7 +339,9 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                                 umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
                                              (e | s) != 0 || !first_stage);
                     }
+                    const long long cm1 = prof ? clock64() : 0;
                     if (!RES) umma_commit(b_empty(slot));
+                    if (prof) { tmma += cm1 - cm0; tcom += clock64() - cm1; }
                 }
                 umma_commit(a_empty(stage));
             };
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 slot0 = (slot0 + m) % C::SLOTS;
                 ++ntile;
             }
-            if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; }
+            if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; p.prof[10] = tmma; p.prof[11] = tcom; }
         }
         __syncwarp();
     } else if (warp < 4 * EW) {

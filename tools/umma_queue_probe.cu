@@ -81,6 +81,60 @@ __global__ void __launch_bounds__(128, 1) tight(int iters, long long* out) {
     if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// tight issue with a tcgen05.commit (to a barrier nobody waits on) after every CK MMAs, optionally a fence + test_wait too
+template <int N, int CK, int EXTRA>
+__global__ void __launch_bounds__(128, 1) tight_commit(int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, bar2[8];
+    __shared__ uint32_t tslot;
+    const uint32_t sA = smem_u32(smem), sB = sA + 64 * 1024;
+    for (int i = threadIdx.x; i < 128 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bar2[i]), 1); mbar_fence_init(); }
+    if (threadIdx.x < 32) { tmem_alloc(smem_u32(&tslot), 512); tmem_relinquish(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tslot;
+    constexpr uint32_t idesc = make_idesc_bf16(128, N);
+    if (threadIdx.x < 32) {
+        if (elect_one()) {
+            const uint64_t ad = make_smem_desc_sw128(sA, 18 * 128), bd = make_smem_desc(sB, N * 16, 128);
+            const uint32_t a_lo = (uint32_t)ad, a_hi = (uint32_t)(ad >> 32), b_lo = (uint32_t)bd, b_hi = (uint32_t)(bd >> 32);
+            long long t0 = clock64();
+            uint32_t acc = 0;
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    umma_bf16_lh(tmem + (i & 1) * N, a_lo + (i >> 2) * 144 + (i & 3) * 2, a_hi, b_lo + (i & 3) * (2 * N), b_hi, idesc, 1);
+                    if ((i + 1) % CK == 0) {
+                        umma_commit(smem_u32(&bar2[(i / CK) & 7]));
+                        if (EXTRA) { tc_fence_after(); acc += mbar_test(smem_u32(&bar2[((i / CK) + 3) & 7]), it & 1); }
+                    }
+                }
+            }
+            umma_commit(smem_u32(&bar));
+            mbar_wait(smem_u32(&bar), 0);
+            long long t1 = clock64();
+            if (blockIdx.x == 0) *out = t1 - t0 + (acc == 0xffffffffu);
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+template <int N, int CK, int EXTRA>
+static void run_tc(long long* d_out) {
+    const int smem = 128 * 1024;
+    cudaFuncSetAttribute(tight_commit<N, CK, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    tight_commit<N, CK, EXTRA><<<148, 128, smem>>>(200, d_out);
+    tight_commit<N, CK, EXTRA><<<148, 128, smem>>>(200, d_out);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return; }
+    long long c; cudaMemcpy(&c, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("N=%3d commit every %2d MMAs%s: %.1f cycles/MMA\n", N, CK, EXTRA ? " + fence + test_wait" : "", (double)c / 3200.0);
+}
+
 template <int N>
 static void run_tight(long long* d_out) {
     const int smem = 128 * 1024;
@@ -93,6 +147,9 @@ static void run_tight(long long* d_out) {
 }
 
 int main() {
+    { long long* d; cudaMalloc(&d, 8);
+      run_tc<128, 16, 0>(d); run_tc<128, 8, 0>(d); run_tc<128, 4, 0>(d); run_tc<128, 2, 0>(d); run_tc<128, 1, 0>(d);
+      run_tc<128, 8, 1>(d); run_tc<128, 4, 1>(d); run_tc<128, 2, 1>(d); run_tc<64, 8, 0>(d); run_tc<64, 2, 0>(d); }
     { long long* d; cudaMalloc(&d, 8); run_tight<16>(d); run_tight<32>(d); run_tight<64>(d); run_tight<128>(d); run_tight<256>(d); }
     const int smem = 128 * 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
