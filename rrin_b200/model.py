@@ -87,6 +87,29 @@ class Net(nn.Module):
             eng = self._engine(dev, n, h, w)
             return eng.forward(self._weights(dev), input0, input1, t)
 
+    def forward_into(self, input0: torch.Tensor, input1: torch.Tensor, t, out: torch.Tensor) -> torch.Tensor:
+        """``forward`` writing into a caller-provided contiguous fp32 ``[N,3,H,W]`` CUDA tensor (streaming pipelines reuse
+        their output buffers instead of allocating one per call)."""
+        self._check(input0, input1)
+        n, _, h, w = input0.shape
+        if tuple(out.shape) != (n, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != input0.device:
+            raise RuntimeError("forward_into: `out` must be a contiguous fp32 [N,3,H,W] tensor on the inputs' device")
+        with torch.no_grad():
+            eng = self._engine(input0.device, n, h, w)
+            return eng.run(self._weights(input0.device), input0, input1, eng._coef(t), out=out)
+
+    def forward_multi_into(self, input0: torch.Tensor, input1: torch.Tensor, ts: Sequence[float], out: torch.Tensor) -> torch.Tensor:
+        """``forward_multi`` writing into a caller-provided contiguous fp32 ``[T,3,H,W]`` CUDA tensor."""
+        self._check(input0, input1)
+        if input0.shape[0] != 1:
+            raise RuntimeError("forward_multi takes one frame pair ([1,3,H,W]) and a list of t")
+        _, _, h, w = input0.shape
+        if tuple(out.shape) != (len(ts), 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != input0.device:
+            raise RuntimeError("forward_multi_into: `out` must be a contiguous fp32 [T,3,H,W] tensor on the inputs' device")
+        with torch.no_grad():
+            eng = self._engine(input0.device, len(ts), h, w, n_pairs=1)
+            return eng.run(self._weights(input0.device), input0, input1, eng._coef(list(ts)), out=out)
+
     def forward_multi(self, input0: torch.Tensor, input1: torch.Tensor,
                       ts: Sequence[float]) -> torch.Tensor:
         """All timesteps ``ts`` of one frame pair ``[1,3,H,W]`` in one pass -> ``[T,3,H,W]``.

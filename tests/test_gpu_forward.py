@@ -212,3 +212,25 @@ def test_convert_loop_through_dropin_module(tmp_path):
     # the Flow-shared call returns the same frames as the reference's per-timestep loop
     multi = model.forward_multi(frames[0].cuda(), frames[1].cuda(), [i / (sf + 1) for i in range(1, sf + 1)]).cpu()
     assert torch.equal(multi, torch.cat(outs[:3]))
+
+
+@pytest.mark.parametrize("n_frames,batch,sf", [(6, 2, 1), (5, 3, 1), (4, 2, 3), (2, 2, 1)], ids=["even", "tail", "slowmo", "one_pair"])
+def test_clip_pipeline_matches_per_pair_calls(n_frames, batch, sf):
+    """The streaming pipeline (each frame uploaded once, copies overlapped with compute) returns exactly the frames
+    the reference's loop computes pair by pair, timestep by timestep (convert.py:120-135)."""
+    from rrin_b200 import ClipInterpolator
+    sd = O.seeded_state_dict(stress_flow=50.0)
+    net = make_net(sd)
+    h, w = 48, 80
+    frames = torch.cat([O.seeded_frames(1, h, w, seed=40 + i, smooth=True)[0] for i in range(n_frames)]).pin_memory()
+    pipe = ClipInterpolator(net, h, w, batch=batch, sf=sf)
+    got = pipe.run(frames)
+    assert got.shape == ((n_frames - 1) * sf, 3, h, w) and got.is_pinned()
+    want = []
+    for i in range(n_frames - 1):
+        for k in range(1, sf + 1):
+            want.append(net(frames[i:i + 1].cuda(), frames[i + 1:i + 2].cuda(), t=k / (sf + 1)).cpu())
+    assert torch.equal(got, torch.cat(want))
+    assert pipe.h2d_bytes == n_frames * 3 * h * w * 4, "every source frame crosses PCIe exactly once"
+    got2 = pipe.run(frames)                                  # buffers and events are reusable
+    assert torch.equal(got2, got)
