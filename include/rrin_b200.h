@@ -123,6 +123,15 @@ RRIN_API int rrin_blend_pack(const float* mask4, const float* xt8, const float* 
 /* K5: final residue add + clamp(0,1) (model.py:62-63) -> fp32 NCHW result. */
 RRIN_API int rrin_residue_clamp(const float* res4, const float* out4, int n_samples, int H, int W, float* out_nchw, void* stream);
 
+/* ---- uint8 frame I/O for the streaming pipeline (frames cross PCIe as bytes) ----------------
+ * K8: transforms.Pad((0, top_pad, 0, right_pad), 'edge') + ToTensor() + drop alpha (dataloader.py:93-118).
+ *     src: uint8 HWC [H0,W0,C], C = 3 or 4 (device); dst: fp32 NCHW [3, top_pad+H0+bottom_pad, W0].
+ *     torchvision's Pad order is (left, top, right, bottom): the reference's "right_pad" is a BOTTOM pad.
+ * K9: to_pil_image (mul(255).byte(), truncating) + crop((0, H-H0, W0, H)) (utils.py:51-58).
+ *     src: fp32 NCHW [3,H,W]; dst: uint8 HWC [H0,W0,3], rows H-H0..H-1 and columns 0..W0-1 of src. */
+RRIN_API int rrin_frame_from_u8(const uint8_t* src_hwc, int H0, int W0, int C, int top_pad, int bottom_pad, float* dst_nchw, void* stream);
+RRIN_API int rrin_frame_to_u8(const float* src_nchw, int H, int W, int H0, int W0, uint8_t* dst_hwc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

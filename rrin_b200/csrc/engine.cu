@@ -515,6 +515,12 @@ int rrin_blend_pack(const float* mask4, const float* xt8, const float* in0, cons
                     int pair_mul, int H, int W, float* out4, void* f16, void* stream) {
     return blend_pack(mask4, xt8, in0, in1, coef, n, pair_mul, H, W, out4, f16, static_cast<cudaStream_t>(stream));
 }
+int rrin_frame_from_u8(const uint8_t* src_hwc, int H0, int W0, int C, int top_pad, int bottom_pad, float* dst_nchw, void* stream) {
+    return frame_from_u8(src_hwc, H0, W0, C, top_pad, bottom_pad, dst_nchw, static_cast<cudaStream_t>(stream));
+}
+int rrin_frame_to_u8(const float* src_nchw, int H, int W, int H0, int W0, uint8_t* dst_hwc, void* stream) {
+    return frame_to_u8(src_nchw, H, W, H0, W0, dst_hwc, static_cast<cudaStream_t>(stream));
+}
 int rrin_residue_clamp(const float* res4, const float* out4, int n, int H, int W, float* out_nchw, void* stream) {
     return residue_clamp(res4, out4, n, H, W, out_nchw, static_cast<cudaStream_t>(stream));
 }

@@ -219,6 +219,38 @@ __global__ void __launch_bounds__(kGlueThreads) residue_clamp_kernel(const float
     }
 }
 
+// ------------------------------------------------------------------ K8 / K9: uint8 frame I/O on the device
+// K8 = transforms.Pad((0, top_pad, 0, right_pad), 'edge') + ToTensor() + drop alpha (dataloader.py:93-118): uint8 HWC
+// [H0,W0,C] -> fp32 NCHW [3,H,W0] with H = top + H0 + bottom; padded rows replicate the first / last image row.
+// (torchvision's Pad order is (left, top, right, bottom): the reference's "right_pad" lands on the BOTTOM.)
+__global__ void __launch_bounds__(kGlueThreads) frame_from_u8_kernel(const uint8_t* __restrict__ src, int H0, int W0, int C, int top,
+                                                                      int H, float* __restrict__ dst) {
+    const long total = (long)H * W0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
+        const int sy = min(max(y - top, 0), H0 - 1);
+        const uint8_t* p = src + ((long)sy * W0 + x) * C;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[(long)c * total + i] = __fdiv_rn((float)p[c], 255.f);    // ToTensor: byte -> float, div(255)
+    }
+}
+// K9 = to_pil_image (pic.mul(255).byte(): truncation) + crop((0, H - H0, W0, H)) (utils.py:51-58): fp32 NCHW [3,H,W] ->
+// uint8 HWC [H0,W0,3], dropping the top H - H0 rows.
+__global__ void __launch_bounds__(kGlueThreads) frame_to_u8_kernel(const float* __restrict__ src, int H, int W, int H0, int W0,
+                                                                    uint8_t* __restrict__ dst) {
+    const long total = (long)H0 * W0, plane = (long)H * W;
+    const int crop = H - H0;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
+        const float* p = src + (long)(y + crop) * W + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fmul_rn(p[c * plane], 255.f);
+            dst[i * 3 + c] = (uint8_t)(int)v;                      // float -> integer truncation, then the low byte (torch .byte())
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host launchers
 static int check_dims(const char* who, int N, int H, int W) {
     if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) { set_error("%s: bad shape N=%d H=%d W=%d (H, W must be even)", who, N, H, W); return RRIN_ERR_BAD_SHAPE; }
@@ -255,6 +287,19 @@ int blend_pack(const float* mask4, const float* xt8, const float* in0, const flo
     RRIN_CUDA_CHECK(launch_pdl(blend_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
                                                                            in0, in1, coef, Nt, pair_mul, H, W, reinterpret_cast<float4*>(out4),
                                                                            reinterpret_cast<__nv_bfloat16*>(f16)));
+    RRIN_CUDA_CHECK(cudaGetLastError());
+    return RRIN_OK;
+}
+int frame_from_u8(const uint8_t* src, int H0, int W0, int C, int top, int bottom, float* dst, cudaStream_t s) {
+    if (!src || !dst || H0 <= 0 || W0 <= 0 || (C != 3 && C != 4) || top < 0 || bottom < 0) { set_error("frame_from_u8: bad argument"); return RRIN_ERR_BAD_ARG; }
+    const int H = top + H0 + bottom;
+    frame_from_u8_kernel<<<glue_grid((long)H * W0), kGlueThreads, 0, s>>>(src, H0, W0, C, top, H, dst);
+    RRIN_CUDA_CHECK(cudaGetLastError());
+    return RRIN_OK;
+}
+int frame_to_u8(const float* src, int H, int W, int H0, int W0, uint8_t* dst, cudaStream_t s) {
+    if (!src || !dst || H0 <= 0 || W0 <= 0 || H0 > H || W0 > W) { set_error("frame_to_u8: bad argument"); return RRIN_ERR_BAD_ARG; }
+    frame_to_u8_kernel<<<glue_grid((long)H0 * W0), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }

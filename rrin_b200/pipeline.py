@@ -12,8 +12,12 @@ next pair.  Here:
   * ``sf > 1`` intermediate frames per pair go through ``Net.forward_multi`` (Flow U-Net once
     per pair, model.py:33-35).
 
+  * with ``uint8=True`` frames cross PCIe as bytes (HWC, as PIL decodes them) and the reference's
+    ``Pad(edge) + ToTensor`` (dataloader.py:93-118) and ``to_pil_image + crop`` (utils.py:51-58) run
+    on the device (``rrin_frame_from_u8`` / ``rrin_frame_to_u8``): 4x fewer PCIe bytes.
+
 PyTorch is used for pinned/device buffers, streams and events only; all arithmetic is in the
-CUDA library.  Frames are fp32 ``[3,H,W]`` in [0,1] like ``dataloader.py:116-118`` produces them.
+CUDA library.  fp32 frames are ``[3,H,W]`` in [0,1] like ``dataloader.py:116-118`` produces them.
 """
 from __future__ import annotations
 
@@ -21,15 +25,24 @@ from typing import List, Optional
 
 import torch
 
+from . import io as rio
+from ._lib import check, lib
 from .sharding import timesteps
 
 
 class ClipInterpolator:
     """Interpolates ``sf`` frames between every two consecutive frames of a host-resident clip."""
 
-    def __init__(self, net, h: int, w: int, batch: int = 2, sf: int = 1, device: Optional[torch.device] = None):
+    def __init__(self, net, h: int, w: int, batch: int = 2, sf: int = 1, device: Optional[torch.device] = None,
+                 uint8: bool = False, channels: int = 3):
+        """``h, w``: frame size as the model sees it (fp32 mode), or the ORIGINAL image size (``uint8=True``; the pipeline
+        then pads like dataloader.py:93-108 and crops like utils.py:56-57)."""
         if batch < 1 or sf < 1:
             raise ValueError("batch and sf must be >= 1")
+        self.uint8, self.h0, self.w0, self.c = uint8, h, w, channels
+        if uint8:
+            self.top, self.bottom = rio.pad_amounts(h, w)
+            h, w = rio.padded_shape(h, w)
         self.net, self.h, self.w, self.batch, self.sf = net, h, w, batch, sf
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.ts = timesteps(sf)
@@ -41,18 +54,35 @@ class ClipInterpolator:
             self.ev_in = [torch.cuda.Event() for _ in range(2)]        # upload of the slot finished
             self.ev_done = [torch.cuda.Event() for _ in range(2)]      # forward of the slot finished (frames reusable)
             self.ev_out = [torch.cuda.Event() for _ in range(2)]       # download of the slot finished (outs reusable)
+            if uint8:
+                self.u8_in = [torch.empty(batch + 1, self.h0, self.w0, channels, dtype=torch.uint8, device=self.device) for _ in range(2)]
+                self.u8_out = [torch.empty(batch * sf, self.h0, self.w0, 3, dtype=torch.uint8, device=self.device) for _ in range(2)]
         self.h2d_bytes = self.d2h_bytes = 0
+
+    def _upload(self, dst: torch.Tensor, u8: torch.Tensor, src_host: torch.Tensor, stream) -> int:
+        """Host frames -> fp32 device frames ``dst`` on ``stream``; returns the PCIe bytes."""
+        if not self.uint8:
+            dst.copy_(src_host, non_blocking=True)
+            return src_host.numel() * 4
+        u8.copy_(src_host, non_blocking=True)
+        for i in range(u8.shape[0]):
+            check(lib().rrin_frame_from_u8(u8[i].data_ptr(), self.h0, self.w0, self.c, self.top, self.bottom, dst[i].data_ptr(),
+                                           stream.cuda_stream), "rrin_frame_from_u8")
+        return src_host.numel()
 
     @torch.no_grad()
     def run(self, frames_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``frames_host``: pinned fp32 ``[F,3,H,W]``.  Returns pinned fp32 ``[(F-1)*sf,3,H,W]``: the interpolated frames
         in output order (pair 0 t_1..t_sf, pair 1 ...); originals are not copied back (convert.py:124 copies the files)."""
         f = frames_host.shape[0]
-        if frames_host.shape[1:] != (3, self.h, self.w) or frames_host.dtype != torch.float32:
-            raise RuntimeError(f"expected fp32 [F,3,{self.h},{self.w}] frames, got {tuple(frames_host.shape)} {frames_host.dtype}")
+        want = (self.h0, self.w0, self.c) if self.uint8 else (3, self.h, self.w)
+        if tuple(frames_host.shape[1:]) != want or frames_host.dtype != (torch.uint8 if self.uint8 else torch.float32):
+            raise RuntimeError(f"expected {'uint8 [F,H,W,C]' if self.uint8 else 'fp32 [F,3,H,W]'} frames of shape [F,{want}], "
+                               f"got {tuple(frames_host.shape)} {frames_host.dtype}")
         n_pairs = max(f - 1, 0)
         if out_host is None:
-            out_host = torch.empty(n_pairs * self.sf, 3, self.h, self.w).pin_memory()
+            out_host = (torch.empty(n_pairs * self.sf, self.h0, self.w0, 3, dtype=torch.uint8) if self.uint8
+                        else torch.empty(n_pairs * self.sf, 3, self.h, self.w)).pin_memory()
         cur = torch.cuda.current_stream(self.device)
         B, sf = self.batch, self.sf
         self.h2d_bytes = self.d2h_bytes = 0
@@ -68,13 +98,12 @@ class ClipInterpolator:
                 if b >= 2:
                     self.s_in.wait_event(self.ev_done[slot])           # the forward that read this slot two batches ago
                 if b == 0:
-                    fr[0].copy_(frames_host[0], non_blocking=True)
-                    self.h2d_bytes += fbytes
+                    self.h2d_bytes += self._upload(fr[0:1], self.u8_in[slot][0:1] if self.uint8 else None, frames_host[0:1], self.s_in)
                 else:
                     self.s_in.wait_event(self.ev_in[slot ^ 1])
                     fr[0].copy_(self.frames[slot ^ 1][min(B, n_pairs - (p0 - B))], non_blocking=True)   # last frame of the previous batch
-                fr[1:nb + 1].copy_(frames_host[p0 + 1:p0 + nb + 1], non_blocking=True)
-                self.h2d_bytes += nb * fbytes
+                self.h2d_bytes += self._upload(fr[1:nb + 1], self.u8_in[slot][1:nb + 1] if self.uint8 else None,
+                                               frames_host[p0 + 1:p0 + nb + 1], self.s_in)
                 self.ev_in[slot].record(self.s_in)
             # ---- forward on the caller's stream
             cur.wait_event(self.ev_in[slot])
@@ -89,8 +118,16 @@ class ClipInterpolator:
             # ---- download
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_done[slot])
-                out_host[p0 * sf:(p0 + nb) * sf].copy_(out[:nb * sf], non_blocking=True)
-                self.d2h_bytes += nb * sf * fbytes
+                if self.uint8:
+                    u8o = self.u8_out[slot]
+                    for i in range(nb * sf):
+                        check(lib().rrin_frame_to_u8(out[i].data_ptr(), self.h, self.w, self.h0, self.w0, u8o[i].data_ptr(),
+                                                     self.s_out.cuda_stream), "rrin_frame_to_u8")
+                    out_host[p0 * sf:(p0 + nb) * sf].copy_(u8o[:nb * sf], non_blocking=True)
+                    self.d2h_bytes += nb * sf * self.h0 * self.w0 * 3
+                else:
+                    out_host[p0 * sf:(p0 + nb) * sf].copy_(out[:nb * sf], non_blocking=True)
+                    self.d2h_bytes += nb * sf * fbytes
                 self.ev_out[slot].record(self.s_out)
         self.s_out.synchronize()
         cur.synchronize()

@@ -234,3 +234,50 @@ def test_clip_pipeline_matches_per_pair_calls(n_frames, batch, sf):
     assert pipe.h2d_bytes == n_frames * 3 * h * w * 4, "every source frame crosses PCIe exactly once"
     got2 = pipe.run(frames)                                  # buffers and events are reusable
     assert torch.equal(got2, got)
+
+
+def test_uint8_frame_io_matches_torchvision_semantics():
+    """K8 / K9 against the reference's host ops: Pad(edge) + ToTensor + drop alpha (dataloader.py:93-118) and
+    to_pil_image (mul(255).byte()) + crop (utils.py:51-58), bit for bit."""
+    import torch.nn.functional as F
+    from rrin_b200 import io as rio
+    from rrin_b200._lib import check, lib
+    l = lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(3)
+    for (h0, w0, c) in [(40, 32, 3), (1080, 1920, 4), (50, 112, 3)]:
+        img = torch.randint(0, 256, (h0, w0, c), dtype=torch.uint8, generator=g)
+        top, bottom = rio.pad_amounts(h0, w0)
+        h = h0 + top + bottom
+        dst = torch.full((3, h, w0), float("nan"), device="cuda")
+        check(l.rrin_frame_from_u8(img.cuda().data_ptr(), h0, w0, c, top, bottom, dst.data_ptr(), s))
+        want = F.pad(img.permute(2, 0, 1)[:3].float().div(255).unsqueeze(0), (0, 0, top, bottom), mode="replicate")[0]
+        assert torch.equal(dst.cpu(), want)
+        x = torch.rand(3, h, w0, generator=g)
+        x[0, -1, :5] = torch.tensor([0.0, 1.0, 0.999999, 0.5, 1.0 / 255])
+        out = torch.zeros(h0, w0, 3, dtype=torch.uint8, device="cuda")
+        check(l.rrin_frame_to_u8(x.cuda().data_ptr(), h, w0, h0, w0, out.data_ptr(), s))
+        want8 = x.mul(255).byte()[:, h - h0:, :].permute(1, 2, 0)
+        assert torch.equal(out.cpu(), want8)
+
+
+def test_clip_pipeline_uint8_mode():
+    """uint8 HWC frames in, uint8 HWC frames out, pad / crop on the device: equals the fp32 path fed with the reference's
+    host-side transforms."""
+    import torch.nn.functional as F
+    from rrin_b200 import ClipInterpolator, io as rio
+    sd = O.seeded_state_dict(stress_flow=50.0)
+    net = make_net(sd)
+    h0, w0 = 72, 96                                  # 72 -> padded to 80 rows (8 on top)
+    frames = (torch.cat([O.seeded_frames(1, h0, w0, seed=60 + i, smooth=True)[0] for i in range(5)]) * 255).byte()
+    frames_hwc = frames.permute(0, 2, 3, 1).contiguous().pin_memory()
+    pipe = ClipInterpolator(net, h0, w0, batch=2, sf=1, uint8=True)
+    got = pipe.run(frames_hwc)
+    assert got.shape == (4, h0, w0, 3) and got.dtype == torch.uint8
+    top, bottom = rio.pad_amounts(h0, w0)
+    fl = F.pad(frames.float().div(255), (0, 0, top, bottom), mode="replicate")
+    for i in range(4):
+        y = net(fl[i:i + 1].cuda(), fl[i + 1:i + 2].cuda(), t=0.5).cpu()[0]
+        want = y.mul(255).byte()[:, top + bottom:, :].permute(1, 2, 0)
+        assert torch.equal(got[i], want)
+    assert pipe.h2d_bytes == 5 * h0 * w0 * 3 and pipe.d2h_bytes == 4 * h0 * w0 * 3

@@ -148,3 +148,50 @@ def test_two_rank_gloo_shards_reassemble():
         assert p.exitcode == 0
     assert got == [2 * i + 1 for i in range(n_frames - 1)]
     assert ms == 6.0                                                    # 11 pairs over 2 ranks: 6 and 5
+
+
+# ----------------------------------------------------------------------------- reference file / pad conventions
+def test_pad_amounts_follow_the_reference_quirk():
+    from rrin_b200 import io as rio
+    assert rio.pad_amounts(1080, 1920) == (8, 0) and rio.padded_shape(1080, 1920) == (1088, 1920)
+    assert rio.pad_amounts(720, 1280) == (0, 0)
+    assert rio.pad_amounts(360, 640) == (8, 0) and rio.padded_shape(360, 640) == (368, 640)       # README.md:19 training size
+    # a width that is not a multiple of 16 pads the BOTTOM (torchvision Pad order) and the model cannot run: 100x50 -> 100x76
+    assert rio.pad_amounts(50, 100) == (14, 12)
+    with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
+        rio.padded_shape(50, 100)
+    assert rio.crop_rows(1088, 1080) == 8
+
+
+def test_pad_matches_torchvision_pad_semantics():
+    """dataloader.py:108: transforms.Pad((0, top_pad, 0, right_pad), 'edge') == F.pad(replicate) with (left, right, top, bottom)."""
+    import torch.nn.functional as F
+    from rrin_b200 import io as rio
+    x = torch.arange(3 * 40 * 32, dtype=torch.float32).reshape(1, 3, 40, 32)
+    top, bottom = rio.pad_amounts(40, 32)
+    assert (top, bottom) == (8, 0)
+    y = F.pad(x, (0, 0, top, bottom), mode="replicate")
+    assert y.shape[2:] == rio.padded_shape(40, 32) and torch.equal(y[:, :, :top], x[:, :, :1].expand(-1, -1, top, -1))
+
+
+def test_output_names_and_resume():
+    from rrin_b200 import io as rio
+    names = rio.output_names(3, 2)
+    assert [n for n, _ in names] == [f"{i:09d}.png" for i in range(1, 8)]
+    assert [s for _, s in names] == [None, (0, 1), (0, 2), None, (1, 1), (1, 2), None]
+    assert rio.resume_index(0, 2) == 0 and rio.resume_index(4, 2) == 1 and rio.resume_index(7, 2) == 2
+
+
+def test_checkpoint_lookup_and_load(tmp_path):
+    from rrin_b200 import Net, io as rio
+    (tmp_path / "other0001.pth").write_bytes(b"x")
+    sd = Net().state_dict()
+    for ep in (3, 12):
+        torch.save({"model": sd, "optim": {}, "epoch": ep}, tmp_path / f"MyModel{ep:04d}.pth")
+    got = rio.find_checkpoint(str(tmp_path), "mymodel")
+    listing = [n for n in reversed(os.listdir(tmp_path)) if n.lower().startswith("mymodel")]
+    assert os.path.basename(got) == listing[0]
+    loaded = rio.load_checkpoint(got)
+    Net().load_state_dict(loaded, strict=True)
+    with pytest.raises(FileNotFoundError):
+        rio.find_checkpoint(str(tmp_path), "absent")
