@@ -34,39 +34,42 @@ namespace rrin {
     X(7, 64, 64, 64, 1, 3, 6, 1)   \
     X(8, 64, 16, 128, 1, 3, 12, 1)
 
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>
-// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
-// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
-// 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
-// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0, 1>  level-0 `last` 32->{2,3,4}, fp32 output
-// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1>  level-1 64->64, weights resident
-// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
-//                                                 the next tile's MMAs start as soon as the first slots are drained)
-// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0, 1>  same tile, per-thread stores: folded upsample conv scattering into level 1
-// 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
-#define RRIN_CONV2_CONFIGS(X)                \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2) \
-    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2) \
-    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2)  \
-    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 1)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1)   \
-    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)  \
-    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0, 1)  \
-    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2)
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>
+// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
+// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
+// 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
+// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0, 1, 1>  level-0 `last` 32->{2,3,4}, fp32 output
+// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1, 1>  level-1 64->64, weights resident
+// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1, 1>  level-1 cat(64+64)->64
+// 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
+//                                                    the next tile's MMAs start as soon as the first slots are drained)
+// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0, 1, 1>  same tile, per-thread stores: folded upsample conv scattering into level 1
+// 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
+// 19 : < 64, 64, 128, 3, 2,  6, TAPS9, 0, 1, 2, 2>  levels >= 2 plain / cat on CTA PAIRS (cta_group::2, M = 256): half of every
+//                                                    weight block per CTA
+#define RRIN_CONV2_CONFIGS(X)                   \
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1) \
+    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1) \
+    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1)  \
+    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 1, 1)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1)   \
+    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
+    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0, 1, 1)  \
+    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
+    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2)
 
 constexpr int kV2Base = 10;
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg; };
 static const CfgInfo kCfg1[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB, STRIP) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP, 1},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>::PW, SCHED, RES, ETMA, 0},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>::PW, SCHED, RES, ETMA, 0, CG},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -123,9 +126,16 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
         const int t = (int)r;
         const int k = k8 * 8 + e8, col = t * nt + n;
         float v = 0.f;
-        if (kind == PACK_NORMAL) {
+        if (kind == PACK_NORMAL || kind == PACK_NORMAL_CG2) {
             const int ci = st * kcs + k;
             if (ci < cin && col < cout) v = w[((long)col * cin + ci) * 9 + ent];
+            if (kind == PACK_NORMAL_CG2) {
+                // CTA pairs: each block is stored as two halves [n / (nt/2)][KB/8][nt/2][8] -- one per CTA of the pair
+                const int hn = nt / 2, half = n / hn, nn = n - half * hn;
+                const long blk = i - (((long)k8 * nt + n) * 8 + e8);
+                wp[blk + (long)half * (kb * hn) + ((long)k8 * hn + nn) * 8 + e8] = __float2bfloat16_rn(v);
+                continue;
+            }
         } else if (kind == PACK_S2D || kind == PACK_S2D8) {
             const int cpp = nt / 4, ph = n / cpp, co = n - ph * cpp;
             int u, rr, vv, cc, ci;
@@ -159,7 +169,7 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ntiles * nt; i += gridDim.x * blockDim.x) {
         float v = 0.f;
-        if (kind == PACK_NORMAL) { if (i < cout) v = b[i]; }
+        if (kind == PACK_NORMAL || kind == PACK_NORMAL_CG2) { if (i < cout) v = b[i]; }
         else if (kind == PACK_S2D || kind == PACK_S2D8) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
         else { if (i < 4 * cout) v = b[i % cout]; }
         bp[i] = v;
@@ -183,7 +193,11 @@ int conv_pack_weights(int kind, const float* w, const float* b, int cout, int ci
     if (!cfg_valid(cfg)) { set_error("conv_pack_weights: bad config %d", cfg); return RRIN_ERR_BAD_ARG; }
     const CfgInfo& c = cfg_info(cfg);
     int n_cols, n_ent, kspan;
-    if (kind == PACK_NORMAL) { n_cols = cout; n_ent = 9; kspan = c.kcs; if (c.kb != c.kcs) { set_error("pack: config %d is space-to-depth only", cfg); return RRIN_ERR_BAD_ARG; } }
+    if (kind == PACK_NORMAL || kind == PACK_NORMAL_CG2) {
+        n_cols = cout; n_ent = 9; kspan = c.kcs;
+        if (c.kb != c.kcs) { set_error("pack: config %d is space-to-depth only", cfg); return RRIN_ERR_BAD_ARG; }
+        if ((kind == PACK_NORMAL_CG2) != (c.cg == 2)) { set_error("pack: kind %d does not match config %d (CTA-pair layout)", kind, cfg); return RRIN_ERR_BAD_ARG; }
+    }
     else if (kind == PACK_S2D) { n_cols = c.nt; n_ent = 16; kspan = c.kb; if (cout > c.nt / 4) { set_error("pack(s2d): cout %d > %d", cout, c.nt / 4); return RRIN_ERR_BAD_SHAPE; } }
     else if (kind == PACK_S2D8) {
         n_cols = c.nt; n_ent = 8; kspan = c.kb;
@@ -220,20 +234,20 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    RRIN_CUDA_CHECK(launch_pdl(kern, grid, kConvThreads, C::SMEM_BYTES, stream, p));
+    RRIN_CUDA_CHECK(launch_pdl(kern, grid, kConvThreads, C::SMEM_BYTES, stream, 1, p));
     return RRIN_OK;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
-static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo, int grid,
-                       cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG>
+static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
+                       const CUtensorMap& tmw, int grid, cudaStream_t stream) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
     if (!g_attr_set[id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         g_attr_set[id] = true;
     }
-    RRIN_CUDA_CHECK(launch_pdl(kern, grid, C::THREADS, C::SMEM_BYTES, stream, p, tm0, tm1, tmo));
+    RRIN_CUDA_CHECK(launch_pdl(kern, grid, C::THREADS, C::SMEM_BYTES, stream, CG, p, tm0, tm1, tmo, tmw));
     return RRIN_OK;
 }
 
@@ -328,9 +342,24 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     } else tmo = tm0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
-    // at least one full-size tile per CTA when the launch is small
-    const long want = (total + c.msub - 1) / c.msub;
-    const int grid = (int)(want < sms ? (want > 0 ? want : 1) : sms);
+    CUtensorMap tmw = tm0;
+    if (c.cg == 2) {
+        // packed weights as a 2-D tensor of 128-byte rows: a CTA's half of a block is a box of (bytes / 128) rows
+        EncodeTiledFn fn = encode_fn();
+        const size_t wbytes = conv_packed_weight_bytes(cfg, d.n_cols, p.n_stages, d.sched);
+        const cuuint64_t dims[2] = {64, (cuuint64_t)(wbytes / 128)};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(c.nt * c.kb * 2 / 2 / 128)};
+        const cuuint32_t estr[2] = {1, 1};
+        if (!fn || (reinterpret_cast<uintptr_t>(d.wpack) & 15)) { set_error("conv3x3(tma): cannot map the packed weights"); return RRIN_ERR_UNSUPPORTED; }
+        CUresult r = fn(&tmw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.wpack), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for the packed weights", (int)r); return RRIN_ERR_CUDA; }
+    }
+    // at least one full-size tile per CTA (pair) when the launch is small
+    const long want = (total + c.cg * c.msub - 1) / (c.cg * c.msub);
+    const int workers = sms / c.cg;
+    const int grid = c.cg * (int)(want < workers ? (want > 0 ? want : 1) : workers);
     // diagnostics only: RRIN_CONV_PROF=1 prints block 0's per-role wait cycles after every launch (synchronises)
     static const int dbg = getenv("RRIN_CONV_DBG") ? atoi(getenv("RRIN_CONV_DBG")) : 0;
     p.dbg = dbg;
@@ -343,7 +372,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     int rc = RRIN_ERR_BAD_ARG;
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>(id, p, tm0, tm1, tmo, grid, stream); break;
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>(id, p, tm0, tm1, tmo, tmw, grid, stream); break;
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }

@@ -65,15 +65,20 @@ constexpr int v2_threads(int ew) { return (4 * ew + 3) * 32; }     // EW epilogu
 //        sequence number is congruent to g, so two accumulator slots are drained concurrently when EW = 2
 // Half entries (SCHED 2, NT = 128): an entry whose block shift is +-1 row feeds only one output phase row a, i.e.
 //        one 64-column half of the accumulator: it runs as an N = 64 MMA on a half-size weight block.
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
+// CG   : 1 = one CTA per tile.  2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the leader's MMA thread issues M = 256
+//        MMAs over both CTAs' sub-tiles; each CTA stages its own activation halo but only HALF of every weight block
+//        (N/2 rows), so the per-SM shared-memory operand traffic of an MMA drops from 8 KB to 6 KB per 64 cycles and the
+//        weight stream per SM halves.  Streamed 9-tap schedule only.
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1>
 struct ConvCfgV2 {
     static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
     static constexpr int BOX_BYTES = (kTileH + 2) * PW * 128;
     static constexpr int BOX_STRIDE = (BOX_BYTES + 1023) / 1024 * 1024;
     static constexpr int A_STAGE = BOXES * BOX_STRIDE;
-    static constexpr int B_BLOCK = NT * KB * 2;
+    static constexpr int B_BLOCK = NT * KB * 2 / CG;   // bytes of a weight block held by ONE CTA
     static constexpr bool HALF = (SCHED == 2 && NT == 128);
+    static_assert(CG == 1 || (CG == 2 && SCHED == 0 && !RES && NT == 128), "CTA pairs: streamed 9-tap schedule, N = 128");
     static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
     static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;
     static constexpr int THREADS = v2_threads(EW);
@@ -121,9 +126,12 @@ struct TileV2 { int nt, n, ty, sx0, m; };
 struct TileWalkV2 {
     int u, u_end;
     int nt, n, ty, sx0;          // decomposition of u
-    __device__ __forceinline__ void init(const ConvParamsV2& p) {
-        u = (int)((long long)p.total_units * blockIdx.x / gridDim.x);
-        u_end = (int)((long long)p.total_units * (blockIdx.x + 1) / gridDim.x);
+    int rank;                    // CTA pairs: rank in the pair (0 otherwise)
+    __device__ __forceinline__ void init(const ConvParamsV2& p, int cg = 1, int cta_rank = 0) {
+        const unsigned wid = blockIdx.x / cg, nw = gridDim.x / cg;     // work-sharing entity: CTA or CTA pair
+        rank = cta_rank;
+        u = (int)((long long)p.total_units * wid / nw);
+        u_end = (int)((long long)p.total_units * (wid + 1) / nw);
         nt = u / p.units_per_nt;
         int r = u - nt * p.units_per_nt;
         const int band = r / p.sx;
@@ -131,13 +139,21 @@ struct TileWalkV2 {
         n = band / p.tiles_y;
         ty = band - n * p.tiles_y;
     }
-    template <int MSUB>
+    // CG = 2: a pair's tile is up to 2*MSUB sub-tiles; rank r takes sub-tiles [sx0 + r*m, sx0 + (r+1)*m) with m = ceil(mt/2)
+    // (rank 1's last sub-tile may lie past the tile: it is computed redundantly -- identical values -- or is out of range)
+    template <int MSUB, int CG = 1>
     __device__ __forceinline__ bool next(const ConvParamsV2& p, TileV2& t) {
         if (u >= u_end) return false;
-        t.nt = nt; t.n = n; t.ty = ty; t.sx0 = sx0;
-        t.m = min(MSUB, min(p.sx - sx0, u_end - u));
-        u += t.m;
-        sx0 += t.m;
+        t.nt = nt; t.n = n; t.ty = ty;
+        // equal-size tiles within the run of units up to the band / range end (7 units -> 3+2+2, not 3+3+1): a 1-sub-tile
+        // remainder tile would stream a full set of weight blocks for a quarter of the MMAs
+        const int run = min(p.sx - sx0, u_end - u);
+        const int nt_run = (run + CG * MSUB - 1) / (CG * MSUB);
+        const int mt = (run + nt_run - 1) / nt_run;
+        t.m = (mt + CG - 1) / CG;
+        t.sx0 = sx0 + rank * t.m;
+        u += mt;
+        sx0 += mt;
         if (sx0 == p.sx) {                      // next band / image / n-tile
             sx0 = 0;
             if (++ty == p.tiles_y) { ty = 0; if (++n == p.N) { n = 0; ++nt; } }
@@ -146,12 +162,14 @@ struct TileWalkV2 {
     }
 };
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG>
 __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
-                                                                     const __grid_constant__ CUtensorMap tmo) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW>;
+                                                                     const __grid_constant__ CUtensorMap tmo,
+                                                                     const __grid_constant__ CUtensorMap tmw) {
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;       // CTA pair: rank 0 is the leader (issues the MMAs)
     constexpr int N_ENT = C::N_ENT;
     constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
     extern __shared__ uint8_t smem_raw[];
@@ -178,24 +196,25 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     if (threadIdx.x == 0) {
         for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), kEpiWarps * 32); }
+        for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), CG * kEpiWarps * 32); }   // both CTAs' epilogues
         mbar_fence_init();
     }
-    if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); }
+    if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); if (CG == 2) tma_prefetch_desc(&tmw); }
     for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
     if (warp == W_MMA) {
-        tmem_alloc(smem_u32(tmem_slot), 512);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_cg2(smem_u32(tmem_slot), 512); tmem_relinquish_cg2(); }
+        else { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();          // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
     if (warp != W_B) pdl_wait();      // activations (reads and writes) only after the previous kernel has finished; weights are constant
 
     TileWalkV2 walk;
-    walk.init(p);
+    walk.init(p, CG, (int)cta_rank);
     TileV2 t;
     // Streamed weights: every CTA walks the same (stage, entry) block sequence, so in lock-step all 148 SMs would ask L2
     // for the same 8-16 KB block at the same moment.  Rotating the stage order per CTA (K-sum order is free) spreads the
@@ -206,13 +225,15 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     // bit pattern of the result -- does not depend on the batch size or the grid.
     auto rot_of = [&](const TileV2& tt) { return RES ? 0 : (int)((unsigned)(tt.ty + tt.nt) % (unsigned)nst) & (C::HALF ? ~1 : ~0); };
     const bool prof = p.prof != nullptr && blockIdx.x == 0;
+    // CTA pairs: "full" barriers (activations, weights) and the accumulator "empty" barriers live in the leader
+    auto leader_bar = [&](uint32_t bar) { return (CG == 2) ? mapa_shared(bar, 0) : bar; };
 
     if (warp == W_A) {
         // =========================================================== activation halo tiles (TMA), one elected thread
         if (elect_one()) {
             int it = 0;
             long long tw = 0, t00 = clock64();
-            while (walk.next<MSUB>(p, t)) {
+            while (walk.next<MSUB, CG>(p, t)) {
                 const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;          // halo origin; OOB -> zero fill
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
@@ -222,9 +243,15 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
                     if (prof) tw += clock64() - c0;
                     if (p.dbg & 1) { mbar_arrive(a_full(stage)); continue; }
-                    mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
                     const bool first = st < p.c0_chunks;
-                    tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n, a_full(stage));
+                    if (CG == 2) {      // both CTAs' tiles complete the leader's barrier, armed by the leader for 2 boxes
+                        if (cta_rank == 0) mbar_arrive_expect_tx(a_full(stage), 2 * C::BOX_BYTES);
+                        tma_load_4d_cg2(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n,
+                                        leader_bar(a_full(stage)));
+                    } else {
+                        mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
+                        tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n, a_full(stage));
+                    }
                 }
             }
             if (prof) { p.prof[0] = tw; p.prof[1] = clock64() - t00; p.prof[2] = it; }
@@ -250,7 +277,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 // block would be a DRAM-latency miss for everyone: spread one L2 prefetch of the whole packed layer
                 // over the CTAs first (each takes a 16 KB-granular slice).
                 {
-                    const size_t total = (size_t)p.n_ntiles * nblk * C::B_BLOCK, gran = 16384;
+                    const size_t total = (size_t)p.n_ntiles * nblk * C::B_BLOCK * CG, gran = 16384;
                     const size_t nchunk = (total + gran - 1) / gran;
                     for (size_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
                         const size_t off = ch * gran;
@@ -258,7 +285,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     }
                 }
                 int cnt = 0;
-                while (walk.next<MSUB>(p, t)) {
+                while (walk.next<MSUB, CG>(p, t)) {
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);
                     const int st_rot = rot_of(t);
                     for (int bi = 0; bi < nblk; ++bi, ++cnt) {
@@ -270,8 +297,16 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                         if (C::HALF && ((st & 1) ? (e < 4) : (e >= 4))) bytes = C::B_BLOCK / 2;
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
                         if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
-                        mbar_arrive_expect_tx(b_full(slot), bytes);
-                        bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), bytes, b_full(slot));
+                        if (CG == 2) {
+                            // this CTA's half (N/2 rows) of block b, as a 64-row x 128-byte box of the packed weights viewed
+                            // as a 2-D tensor of 128-byte rows; both halves complete the leader's barrier
+                            if (cta_rank == 0) mbar_arrive_expect_tx(b_full(slot), 2 * C::B_BLOCK);
+                            const int row = ((t.nt * nblk + b) * 2 + (int)cta_rank) * (C::B_BLOCK / 128);
+                            tma_load_2d_cg2(s_b + slot * C::B_BLOCK, &tmw, 0, row, leader_bar(b_full(slot)));
+                        } else {
+                            mbar_arrive_expect_tx(b_full(slot), bytes);
+                            bulk_g2s(s_b + slot * C::B_BLOCK, wsrc + (size_t)b * (NT * KB), bytes, b_full(slot));
+                        }
                     }
                 }
             }
@@ -280,10 +315,16 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     } else if (warp == W_MMA) {
         // =========================================================== MMA issuer: ONE elected thread runs the whole role
         // (no per-entry warp re-convergence; entries, K steps and their descriptor offsets are compile-time)
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NT), idesc_h = make_idesc_bf16(128, 64);
+        // CTA pairs: only the leader issues (M = 256 over both CTAs); its commits arrive on both CTAs' barriers.
+        if (cta_rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128 * CG, NT), idesc_h = make_idesc_bf16(128, 64);
+            constexpr int NB = NT / CG;                 // weight-block rows (N) held per CTA
             const uint64_t a_desc0 = make_smem_desc_sw128(0, C::PW * 128);
-            const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128), b_desc0h = make_smem_desc(0, 64 * 16, 128);
+            const uint64_t b_desc0 = make_smem_desc(0, NB * 16, 128), b_desc0h = make_smem_desc(0, 64 * 16, 128);
+            auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t id, uint32_t acc) {
+                if (CG == 2) umma_bf16_lh_cg2(d, alo, ahi, blo, bhi, id, acc); else umma_bf16_lh(d, alo, ahi, blo, bhi, id, acc);
+            };
+            auto commit = [&](uint32_t bar) { if (CG == 2) umma_commit_cg2(bar); else umma_commit(bar); };
             const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
             const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0 + (s_b >> 4);
             const uint32_t b_lo0h = (uint32_t)b_desc0h + (s_b >> 4);          // half entries: [KB/8][64][8] blocks
@@ -320,7 +361,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                         b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
                     }
                     const uint32_t a_e = a_st + C::ent_off(PAR, e);
-                    const uint32_t b_ks = hf ? 2 * 64 : 2 * NT;               // descriptor step per K=16: two core-matrix planes
+                    const uint32_t b_ks = hf ? 2 * 64 : 2 * (NT / CG);        // descriptor step per K=16: two core-matrix planes
                     const uint32_t id = hf ? idesc_h : idesc;
                     const uint32_t dcol = (hf == 2) ? 64 : 0;
                     const long long cm0 = prof ? clock64() : 0;
@@ -336,14 +377,14 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
 #pragma unroll
                         for (int s = 0; s < KB / 16; ++s)
                             if (!(p.dbg & 16) || (e | s) == 0)                 // diagnostics: one MMA per (stage, sub-tile) only
-                                umma_bf16_lh(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
-                                             (e | s) != 0 || !first_stage);
+                                mma(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
+                                    (e | s) != 0 || !first_stage);
                     }
                     const long long cm1 = prof ? clock64() : 0;
-                    if (!RES) umma_commit(b_empty(slot));
+                    if (!RES) commit(b_empty(slot));
                     if (prof) { tmma += cm1 - cm0; tcom += clock64() - cm1; }
                 }
-                umma_commit(a_empty(stage));
+                commit(a_empty(stage));
             };
             auto run_m = [&](auto par_c, const int m, const int st, const bool first_stage, const int stage) {
                 if (m == 1) run_stage(par_c, std::integral_constant<int, 1>{}, st, first_stage, stage);
@@ -351,7 +392,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 if constexpr (MSUB >= 3) { if (m == 3) run_stage(par_c, std::integral_constant<int, 3>{}, st, first_stage, stage); }
                 if constexpr (MSUB >= 4) { if (m == 4) run_stage(par_c, std::integral_constant<int, 4>{}, st, first_stage, stage); }
             };
-            while (walk.next<MSUB>(p, t)) {
+            while (walk.next<MSUB, CG>(p, t)) {
                 const int m = t.m;
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
@@ -371,7 +412,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 }
                 for (int j = 0; j < m; ++j) {
                     const int ts = (slot0 + j) % C::SLOTS;
-                    umma_commit(acc_full(ts));
+                    commit(acc_full(ts));
                     use_bits ^= 1u << ts;
                 }
                 slot0 = (slot0 + m) % C::SLOTS;
@@ -388,7 +429,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
         int slot0 = 0, seq = 0;                         // seq: running sub-tile number; group grp drains seq % EW == grp
         uint32_t use_bits = 0;
         long long twf = 0, t00 = clock64();
-        while (walk.next<MSUB>(p, t)) {
+        while (walk.next<MSUB, CG>(p, t)) {
             const int gy = t.ty * kTileH + ly;
             const float* bsrc = bias_s + t.nt * NT;
 #pragma unroll 1
@@ -403,7 +444,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * NT;
-                if (p.dbg & 8) { tc_fence_before(); mbar_arrive(acc_empty(ts)); continue; }   // diagnostics: no epilogue work at all
+                if (p.dbg & 8) { tc_fence_before(); if (CG == 2) mbar_arrive_cluster(leader_bar(acc_empty(ts))); else mbar_arrive(acc_empty(ts)); continue; }   // diagnostics
                 if constexpr (ETMA != 0) {
                     // bf16 NHWC via this warp's 4 KB staging buffer (32 pixels x 128 B, 16-byte chunk k of row r at
                     // k ^ (r & 7)) and one TMA tensor store per 64 columns; the box {64 ch, 8 px, 4 rows} is clipped
@@ -557,7 +598,8 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(acc_empty(ts));
+                if (CG == 2) mbar_arrive_cluster(leader_bar(acc_empty(ts)));      // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(acc_empty(ts));
             }
             for (int j = 0; j < t.m; ++j) use_bits ^= 1u << ((slot0 + j) % C::SLOTS);
             slot0 = (slot0 + t.m) % C::SLOTS;
@@ -570,9 +612,10 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     // ---------------- teardown
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();          // no CTA of the pair leaves while the other may still signal its barriers / TMEM
     if (warp == W_MMA) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 

@@ -63,10 +63,11 @@ struct Schedule {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// diagnostics: RRIN_BIG_CFG=17 selects the per-thread-store variant of the levels >= 2 tile (A/B timing runs)
+// levels >= 2 plain / cat convs: single-CTA tile (config 16).  RRIN_BIG_CFG=19 selects the CTA-pair (cta_group::2) variant, which
+// is parity-tested but measured ~10 % slower at 1080p (profiles/README.md)
 static int big_cfg() {
     const char* e = getenv("RRIN_BIG_CFG");
-    return (e && atoi(e) == 17) ? 17 : 16;
+    return (e && atoi(e) == 19) ? 19 : 16;
 }
 
 static Schedule build_schedule() {
@@ -96,7 +97,10 @@ static Schedule build_schedule() {
             if (level == 1) {
                 if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }                // 32 channels: cp.async producers (KCS = 32)
                 else { m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
-            } else { m.cfg = (src == K_UP) ? 5 : big_cfg(); m.n_stages = cin / 64; }
+            } else {
+                m.cfg = (src == K_UP) ? 5 : big_cfg(); m.n_stages = cin / 64;
+                if (m.cfg == 19) m.kind = PACK_NORMAL_CG2;
+            }
         }
         place(m);
         if (src == K_UP && level <= 1) {        // folded bilinear x2: runs on the coarser grid with 4*cout columns

@@ -260,14 +260,14 @@ static inline long nblocks(int N, int H, int W) { return (long)N * (H / 2) * (W 
 
 int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s) {
     if (int e = check_dims("pack_pair", N, H, W)) return e;
-    RRIN_CUDA_CHECK(launch_pdl(pack_pair_kernel, glue_grid(nblocks(N, H, W)), kGlueThreads, 0, s, in0, in1, N, H, W, reinterpret_cast<__nv_bfloat16*>(x16)));
+    RRIN_CUDA_CHECK(launch_pdl(pack_pair_kernel, glue_grid(nblocks(N, H, W)), kGlueThreads, 0, s, 1, in0, in1, N, H, W, reinterpret_cast<__nv_bfloat16*>(x16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
 int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, const float* coef, int Nt, int pair_mul,
                      int H, int W, void* r16, cudaStream_t s) {
     if (int e = check_dims("flow_tscale_pack", Nt, H, W)) return e;
-    RRIN_CUDA_CHECK(launch_pdl(flow_tscale_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, reinterpret_cast<const float4*>(flow4), in0, in1, coef, Nt,
+    RRIN_CUDA_CHECK(launch_pdl(flow_tscale_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(flow4), in0, in1, coef, Nt,
                                                                                  pair_mul, H, W, reinterpret_cast<__nv_bfloat16*>(r16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
@@ -275,7 +275,7 @@ int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, con
 int warp_pack(const float* flow4, const float* res4, const float* in0, const float* in1, const float* coef, int Nt,
               int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s) {
     if (int e = check_dims("warp_pack", Nt, H, W)) return e;
-    RRIN_CUDA_CHECK(launch_pdl(warp_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s,
+    RRIN_CUDA_CHECK(launch_pdl(warp_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1,
         reinterpret_cast<const float4*>(flow4), reinterpret_cast<const float4*>(res4), in0, in1, coef, Nt, pair_mul, H, W,
         reinterpret_cast<__nv_bfloat16*>(m16), reinterpret_cast<float4*>(xt8)));
     RRIN_CUDA_CHECK(cudaGetLastError());
@@ -284,7 +284,7 @@ int warp_pack(const float* flow4, const float* res4, const float* in0, const flo
 int blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef, int Nt,
                int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s) {
     if (int e = check_dims("blend_pack", Nt, H, W)) return e;
-    RRIN_CUDA_CHECK(launch_pdl(blend_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
+    RRIN_CUDA_CHECK(launch_pdl(blend_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
                                                                            in0, in1, coef, Nt, pair_mul, H, W, reinterpret_cast<float4*>(out4),
                                                                            reinterpret_cast<__nv_bfloat16*>(f16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
@@ -305,7 +305,7 @@ int frame_to_u8(const float* src, int H, int W, int H0, int W0, uint8_t* dst, cu
 }
 int residue_clamp(const float* res4, const float* out4, int Nt, int H, int W, float* out_nchw, cudaStream_t s) {
     if (int e = check_dims("residue_clamp", Nt, H, W)) return e;
-    RRIN_CUDA_CHECK(launch_pdl(residue_clamp_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, reinterpret_cast<const float4*>(res4), reinterpret_cast<const float4*>(out4),
+    RRIN_CUDA_CHECK(launch_pdl(residue_clamp_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(res4), reinterpret_cast<const float4*>(out4),
                                                                               Nt, H, W, out_nchw));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;

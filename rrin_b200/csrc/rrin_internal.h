@@ -23,7 +23,7 @@ enum ConvEpilogue : int {
     EPI_SCATTER = 2,   // folded upsample: column (a,b,co) -> bf16 NHWC [N,2H,2W,cout_stride] at (2y+a,2x+b)
 };
 enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1, SCHED_S2D8 = 2 };   // S2D8: half-phase stages of the TMA kernel
-enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3 };
+enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3, PACK_NORMAL_CG2 = 4 };   // CG2: per-CTA halves of every block
 
 // One 3x3 convolution launch (see conv3x3.cuh for the data layouts).
 struct ConvDesc {
@@ -52,14 +52,24 @@ struct ConvDesc {
 // Launch with programmatic stream serialization (see common.cuh: pdl_wait / pdl_launch_dependents).
 // RRIN_PDL=0 in the environment falls back to plain stream order (A/B timing).
 bool pdl_enabled();
+// `cluster` > 1 launches thread-block clusters of that many CTAs (CTA pairs of the cta_group::2 conv).
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, int cluster, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 

@@ -11,12 +11,12 @@ from rrin_b200._lib import check, lib
 SRC_PLAIN, SRC_CAT, SRC_POOL, SRC_UP, SRC_POOL_S2D, SRC_UP_S2D = range(6)
 EPI_BF16, EPI_F32X16, EPI_SCATTER = range(3)
 SCHED_TAPS9, SCHED_S2D16, SCHED_S2D8 = 0, 1, 2
-PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8 = 0, 1, 2, 3
+PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8, PACK_NORMAL_CG2 = 0, 1, 2, 3, 4
 # transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
-T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0 = range(10, 19)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR = range(10, 20)
 
 
 def stream():
@@ -53,7 +53,7 @@ def pack(kind, cfg, weight, bias, n_stages, sched):
     l = lib()
     cout, cin = weight.shape[:2]
     _, _, nt, _ = cfg_info(cfg)
-    n_cols = {PACK_NORMAL: cout, PACK_S2D: nt, PACK_S2D8: nt, PACK_FOLD: 4 * cout}[kind]
+    n_cols = {PACK_NORMAL: cout, PACK_NORMAL_CG2: cout, PACK_S2D: nt, PACK_S2D8: nt, PACK_FOLD: 4 * cout}[kind]
     n_cols = (n_cols + nt - 1) // nt * nt
     wp = torch.zeros(l.rrin_conv_packed_weight_bytes(cfg, n_cols, n_stages, sched), dtype=torch.uint8, device="cuda")
     bp = torch.zeros(l.rrin_conv_packed_bias_count(cfg, n_cols), dtype=torch.float32, device="cuda")
@@ -77,7 +77,7 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
     cout, cin = weight.shape[:2]
     c0 = src0.shape[-1] * (src0.shape[-2] if mode == SRC_POOL_S2D else 1)
     c1 = src1.shape[-1] if src1 is not None else 0
-    wp, bp, n_cols = pack(PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
+    wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg == T_BIG_PAIR else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if out is None:
         out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg, pool_out)

@@ -66,6 +66,13 @@ NORMAL_CASES = [
     ("tma_many_tiles_l3_ntiles", 16, "plain", 256, 256, True, 2, 100, 72),
     ("tma_direct_l2_cat", 17, "cat", 128, 128, True, 1, 12, 20),
     ("tma_msub3_many_tiles", 18, "plain", 64, 128, False, 1, 120, 200),
+    # CTA pairs (cta_group::2)
+    ("pair_l2_128_128", 19, "plain", 128, 128, True, 2, 12, 20),
+    ("pair_l2_cat", 19, "cat", 128, 128, True, 1, 12, 20),
+    ("pair_l3_256_256", 19, "plain", 256, 256, True, 1, 6, 10),
+    ("pair_many_tiles_l2", 19, "plain", 128, 128, True, 1, 208, 208),
+    ("pair_many_tiles_l3_ntiles", 19, "plain", 256, 256, True, 2, 100, 72),
+    ("pair_odd_width", 19, "plain", 64, 128, False, 1, 120, 200),
     ("tma_direct_many_tiles_l3", 17, "plain", 256, 256, True, 1, 100, 72),
 ]
 
