@@ -215,24 +215,31 @@ int conv_pack_weights(int kind, const float* w, const float* b, int cout, int ci
 }
 
 // ------------------------------------------------------------------ launchers
-static int g_num_sms = 0;
-static bool g_attr_set[kV2Base + kNumCfg2] = {};
+// per-device state (a process may drive several GPUs): SM count and "dynamic shared memory limit raised" flags
+constexpr int kMaxDevices = 64;
+static int g_num_sms[kMaxDevices] = {};
+static bool g_attr_set[kMaxDevices][kV2Base + kNumCfg2] = {};
 
+static int current_device() {
+    int dev = 0;
+    return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices) ? dev : -1;
+}
 static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms = 0;
-    }
-    return g_num_sms;
+    const int dev = current_device();
+    if (dev < 0) return 0;
+    if (g_num_sms[dev] == 0 && cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_num_sms[dev] = 0;
+    return g_num_sms[dev];
 }
 
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP>
 static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream) {
     using C = ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>;
     auto kern = conv3x3_umma_kernel<KCS, KB, NT, MSUB, SA, SB, STRIP>;
-    if (!g_attr_set[id]) {
+    const int dev = current_device();
+    if (dev < 0) { set_error("conv3x3: no current CUDA device"); return RRIN_ERR_CUDA; }
+    if (!g_attr_set[dev][id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        g_attr_set[id] = true;
+        g_attr_set[dev][id] = true;
     }
     RRIN_CUDA_CHECK(launch_pdl(kern, grid, kConvThreads, C::SMEM_BYTES, stream, 1, p));
     return RRIN_OK;
@@ -243,9 +250,11 @@ static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, co
                        const CUtensorMap& tmw, int grid, cudaStream_t stream) {
     using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
     auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
-    if (!g_attr_set[id]) {
+    const int dev = current_device();
+    if (dev < 0) { set_error("conv3x3: no current CUDA device"); return RRIN_ERR_CUDA; }
+    if (!g_attr_set[dev][id]) {
         RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        g_attr_set[id] = true;
+        g_attr_set[dev][id] = true;
     }
     RRIN_CUDA_CHECK(launch_pdl(kern, grid, C::THREADS, C::SMEM_BYTES, stream, CG, p, tm0, tm1, tmo, tmw));
     return RRIN_OK;
@@ -366,8 +375,8 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     static const bool prof_on = getenv("RRIN_CONV_PROF") != nullptr;
     static unsigned long long* prof_buf = nullptr;
     if (prof_on) {
-        if (!prof_buf) RRIN_CUDA_CHECK(cudaMalloc(&prof_buf, 16 * sizeof(unsigned long long)));
-        RRIN_CUDA_CHECK(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(unsigned long long), stream));
+        if (!prof_buf) RRIN_CUDA_CHECK(cudaMalloc(&prof_buf, (16 + 4 * 160) * sizeof(unsigned long long)));
+        RRIN_CUDA_CHECK(cudaMemsetAsync(prof_buf, 0, (16 + 4 * 160) * sizeof(unsigned long long), stream));
         p.prof = prof_buf;
     }
     int rc = RRIN_ERR_BAD_ARG;
@@ -377,9 +386,16 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
 #undef X
     }
     if (prof_on && rc == RRIN_OK) {
-        unsigned long long h[16];
+        unsigned long long h[16 + 4 * 160];
         RRIN_CUDA_CHECK(cudaStreamSynchronize(stream));
         RRIN_CUDA_CHECK(cudaMemcpy(h, prof_buf, sizeof h, cudaMemcpyDeviceToHost));
+        {   // per-CTA timeline: cycles from kernel entry to {roles start, MMA role end, epilogue end, CTA end}: max and mean over CTAs
+            unsigned long long mx[4] = {0, 0, 0, 0}; double av[4] = {0, 0, 0, 0};
+            for (int b = 0; b < grid && b < 160; ++b)
+                for (int k = 0; k < 4; ++k) { const unsigned long long v = h[16 + 4 * b + k]; if (v > mx[k]) mx[k] = v; av[k] += (double)v / grid; }
+            fprintf(stderr, "[conv cta  cfg %d] grid %d | roles start max %llu avg %.0f | mma end max %llu avg %.0f | epi end max %llu avg %.0f | cta end max %llu avg %.0f\n",
+                    cfg, grid, mx[0], av[0], mx[1], av[1], mx[2], av[2], mx[3], av[3]);
+        }
         fprintf(stderr, "[conv prof cfg %d %dx%dx%d nst %d ent %d nt %d] block0: tiles %llu stages %llu | tma total %llu wait_empty %llu | "
                         "mma total %llu wait_a %llu wait_b %llu wait_acc %llu issue %llu commit %llu | epi total %llu wait_full %llu\n",
                 cfg, d.N, d.H, d.W, p.n_stages, n_ent_of(d.sched), p.n_ntiles, h[7], h[2], h[1], h[0], h[6], h[3], h[4], h[5], h[10], h[11], h[9], h[8]);

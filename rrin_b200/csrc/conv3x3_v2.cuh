@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     const int lane = threadIdx.x & 31;
     const int nst = p.n_stages;
     const int nblk = nst * N_ENT;
+    const long long t_begin = p.prof ? clock64() : 0;      // diagnostics: per-CTA timeline (prof[16 + 4*cta + k])
 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 ++ntile;
             }
             if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; p.prof[10] = tmma; p.prof[11] = tcom; }
+            if (p.prof) { p.prof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; p.prof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
         }
         __syncwarp();
     } else if (warp < 4 * EW) {
@@ -607,6 +609,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
         }
         if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed
         if (prof && threadIdx.x == 0) { p.prof[8] = twf; p.prof[9] = clock64() - t00; }
+        if (p.prof && warp == 4 * EW - 4 && lane == 0) p.prof[16 + 4 * blockIdx.x + 2] = clock64() - t_begin;                       // last epilogue group done
     }
 
     // ---------------- teardown
@@ -616,6 +619,7 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     if (warp == W_MMA) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+        if (p.prof && lane == 0) p.prof[16 + 4 * blockIdx.x + 3] = clock64() - t_begin;                                              // CTA end
     }
 }
 
