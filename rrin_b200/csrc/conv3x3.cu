@@ -321,6 +321,12 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     p.bias = d.bias;
     p.out = d.out; p.epi = d.epi; p.cout_stride = d.cout_stride; p.act = d.act;
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d.pool_out);
+    if (d.fuse.mode) {
+        if (d.epi != EPI_F32X16 || d.fuse.mode < 1 || d.fuse.mode > 4 || d.fuse.H != 2 * d.H || d.fuse.W != 2 * d.W) { set_error("conv3x3(tma): bad fused glue request"); return RRIN_ERR_BAD_ARG; }
+        p.fz.mode = d.fuse.mode; p.fz.H = d.fuse.H; p.fz.W = d.fuse.W; p.fz.Nt = d.fuse.Nt; p.fz.pair_mul = d.fuse.pair_mul;
+        p.fz.in0 = d.fuse.in0; p.fz.in1 = d.fuse.in1; p.fz.coef = d.fuse.coef;
+        p.fz.aux = reinterpret_cast<const float4*>(d.fuse.aux); p.fz.h16 = reinterpret_cast<__nv_bfloat16*>(d.fuse.h16); p.fz.dst = d.fuse.dst;
+    }
     if (d.pool_out) {
         if (!c.etma) { set_error("conv3x3(tma): config %d has no pooled second output", cfg); return RRIN_ERR_BAD_ARG; }
         if (c.sched == SCHED_S2D8 ? (c.nt != 128 || d.n_cols != 128) : ((d.H | d.W) & 1)) { set_error("conv3x3(tma): pooled output needs an even grid (or the 4-phase level-0 grid)"); return RRIN_ERR_BAD_SHAPE; }
@@ -410,7 +416,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     if (d.N <= 0 || d.H <= 0 || d.W <= 0) { set_error("conv3x3: empty shape %dx%dx%d", d.N, d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
     if (d.mode < 0 || d.mode > SRC_UP_S2D || !d.src0 || (d.mode == SRC_CAT && !d.src1)) { set_error("conv3x3: bad source mode %d", d.mode); return RRIN_ERR_BAD_ARG; }
     if (cfg_is_v2(cfg)) return conv_launch_v2(d, stream);
-    if (d.pool_out) { set_error("conv3x3: config %d has no pooled second output", cfg); return RRIN_ERR_BAD_ARG; }
+    if (d.pool_out || d.fuse.mode) { set_error("conv3x3: config %d has no pooled second output / fused glue", cfg); return RRIN_ERR_BAD_ARG; }
     if (d.sched == SCHED_S2D8) { set_error("conv3x3: the half-phase schedule needs a TMA config"); return RRIN_ERR_BAD_ARG; }
     if ((d.sched == SCHED_TAPS9) != (c.kb == c.kcs)) { set_error("conv3x3: config %d runs the %s schedule", cfg, c.kb == c.kcs ? "9-tap" : "space-to-depth"); return RRIN_ERR_BAD_ARG; }
     ConvParams p{};

@@ -29,9 +29,26 @@
 
 #include "common.cuh"
 #include "conv3x3.cuh"
+#include "glue_device.cuh"
 #include "rrin_internal.h"
 
 namespace rrin {
+
+// Glue of Net.process / Net.forward fused into the epilogue of a U-Net's `last` conv (fp32 [.,16] epilogue, one thread per
+// 2x2 block pixel = exactly the mapping of the stand-alone glue kernels, whose per-block functions are reused):
+//   1 Flow.last        -> writes flow4 and, per sample of the pair, the refine_flow head input   (model.py:37-41)
+//   2 refine_flow.last -> residue add + both warps + Mask head input + xt8                       (model.py:44-50)
+//   3 Mask.last        -> sigmoid, blend -> out4 + final head input                              (model.py:52-55,61)
+//   4 final.last       -> residue add + clamp -> fp32 NCHW result                                (model.py:62-63)
+struct FuseParams {
+    int mode;                    // 0 = none (plain fp32 [.,16] store)
+    int H, W;                    // full-resolution frame size
+    int Nt, pair_mul;            // samples; pair of sample n = n * pair_mul
+    const float* in0; const float* in1; const float* coef;
+    const float4* aux;           // mode 2: flow4 | mode 3: xt8 | mode 4: out4
+    __nv_bfloat16* h16;          // modes 1-3: packed head input of the next U-Net
+    float* dst;                  // mode 2: xt8 | mode 3: out4 | mode 4: NCHW result
+};
 
 struct ConvParamsV2 {
     int c0_chunks;               // 64-channel chunks taken from tensor map 0 (the rest from map 1: cat)
@@ -49,6 +66,7 @@ struct ConvParamsV2 {
     int sx;                      // 8-pixel column groups per band
     int units_per_nt;            // N * tiles_y * sx
     int total_units;             // n_ntiles * units_per_nt
+    FuseParams fz;
     int dbg;                     // diagnostics (RRIN_CONV_DBG, timing only, wrong results): 1 skip activation loads, 2 skip weight loads,
                                  // 4 skip stores, 8 skip the whole epilogue, 16 issue one MMA per (stage, sub-tile)
     unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
@@ -552,11 +570,42 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                     tmem_ld16(t0, r16);
                     tmem_ld_wait();
                     if (ok) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out) + pix * 4;
+                        float4 v[4];                     // this block pixel: 4 phases x 4 classes
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            o4[q] = make_float4(__uint_as_float(r16[4 * q]) + bsrc[4 * q], __uint_as_float(r16[4 * q + 1]) + bsrc[4 * q + 1],
-                                                __uint_as_float(r16[4 * q + 2]) + bsrc[4 * q + 2], __uint_as_float(r16[4 * q + 3]) + bsrc[4 * q + 3]);
+                            v[q] = make_float4(__uint_as_float(r16[4 * q]) + bsrc[4 * q], __uint_as_float(r16[4 * q + 1]) + bsrc[4 * q + 1],
+                                               __uint_as_float(r16[4 * q + 2]) + bsrc[4 * q + 2], __uint_as_float(r16[4 * q + 3]) + bsrc[4 * q + 3]);
+                        const FuseParams& fz = p.fz;
+                        const long HW = (long)fz.H * fz.W, nb = (long)p.H * p.W;    // conv grid = block-pixel grid [H/2, W/2]
+                        const long q = (long)gy * p.W + gx;
+                        if (fz.mode == 0 || fz.mode == 1) {
+                            float4* o4 = reinterpret_cast<float4*>(p.out) + pix * 4;
+#pragma unroll
+                            for (int ph = 0; ph < 4; ++ph) o4[ph] = v[ph];
+                        }
+                        if (fz.mode == 1) {              // t.n = pair; every sample of that pair gets its refine_flow head input
+                            const int s0 = fz.pair_mul ? t.n : 0, s1 = fz.pair_mul ? t.n + 1 : fz.Nt;
+                            for (int sn = s0; sn < s1; ++sn)
+                                glue_tscale_block(v, fz.in0 + (long)t.n * 3 * HW, fz.in1 + (long)t.n * 3 * HW, fz.coef + sn * 6, HW, fz.W, gy, gx,
+                                                  fz.h16 + ((long)sn * nb + q) * 64);
+                        } else if (fz.mode == 2) {       // t.n = sample
+                            const long pn = (long)t.n * fz.pair_mul;
+                            float4 f[4];
+#pragma unroll
+                            for (int ph = 0; ph < 4; ++ph) f[ph] = fz.aux[(pn * nb + q) * 4 + ph];
+                            glue_warp_block(f, v, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
+                                            fz.h16 + ((long)t.n * nb + q) * 64, reinterpret_cast<float4*>(fz.dst) + ((long)t.n * nb + q) * 8);
+                        } else if (fz.mode == 3) {
+                            const long pn = (long)t.n * fz.pair_mul, i = (long)t.n * nb + q;
+                            glue_blend_block(v, fz.aux + i * 8, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef[t.n * 6 + 4], fz.coef[t.n * 6 + 5],
+                                             HW, fz.W, gy, gx, reinterpret_cast<float4*>(fz.dst) + i * 4, fz.h16 + i * 64);
+                        } else if (fz.mode == 4) {
+                            const long i = (long)t.n * nb + q;
+                            float4 o[4];
+#pragma unroll
+                            for (int ph = 0; ph < 4; ++ph) o[ph] = fz.aux[i * 4 + ph];
+                            glue_clamp_block(v, o, HW, fz.W, gy, gx, fz.dst + (long)t.n * 3 * HW);
+                        }
                     }
                 } else {
 #pragma unroll 1

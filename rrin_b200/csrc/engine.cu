@@ -155,6 +155,7 @@ struct Launch {
     int glue = -1;           // >= 0: glue kernel id (0 pack_pair .. 4 residue_clamp)
     int layer = -1;          // conv: index into schedule().layers
     int use_fold = 0;        // conv: which Pack (0 main, 1 fold, 2 strip)
+    int fuse_mode = 0;       // `last` convs: glue fused into the epilogue (conv3x3_v2.cuh FuseParams::mode), 0 = none
     ConvDesc cd;             // pointers hold workspace OFFSETS (+1 so that 0 stays "null") until launch
     alignas(64) unsigned char tmap[3][128];   // TMA configs: tensor maps of src0 / src1 / out, encoded for `tmap_ws`
     std::string name;
@@ -365,15 +366,23 @@ int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** o
     e->off_xt8 = take((size_t)n_samples * px * 32);
     e->ws_bytes = off;
     // launch sequence of Net.forward
+    // The glue between the U-Nets (K2-K5) runs fused in the epilogue of the preceding `last` conv; RRIN_FUSE=0 launches
+    // the stand-alone glue kernels instead (same per-block device functions: bit-identical results).
+    static const bool fuse = [] { const char* v = getenv("RRIN_FUSE"); return !(v && v[0] == '0'); }();
+    static const double glue_bytes_px[5] = {56, 72, 120, 120, 44};
     plan_glue(e, 0);                                              // model.py:33
-    plan_unet(e, 0, n_pairs, e->off_h16, e->off_flow4);           // model.py:35
-    plan_glue(e, 1);                                              // model.py:37-41
-    plan_unet(e, 1, n_samples, e->off_h16, e->off_u4);            // model.py:42
-    plan_glue(e, 2);                                              // model.py:44-50
-    plan_unet(e, 2, n_samples, e->off_h16, e->off_u4);            // model.py:52
-    plan_glue(e, 3);                                              // model.py:52-55,61
-    plan_unet(e, 3, n_samples, e->off_h16, e->off_u4);            // model.py:62
-    plan_glue(e, 4);                                              // model.py:62-63
+    for (int u = 0; u < 4; ++u) {
+        // Flow (model.py:35) | refine_flow (:42) | Mask (:52) | final (:62)
+        plan_unet(e, u, u == 0 ? n_pairs : n_samples, e->off_h16, u == 0 ? e->off_flow4 : e->off_u4);
+        if (fuse) {
+            Launch& last = e->launches.back();
+            last.fuse_mode = u + 1;
+            last.name += " +glue";
+            last.bytes += glue_bytes_px[u + 1] * (double)H * W * n_samples - 16.0 * H * W * n_samples;   // the fp32 hand-over tensor is not materialised
+        } else {
+            plan_glue(e, u + 1);                                  // model.py:37-41 | 44-50 | 52-55,61 | 62-63
+        }
+    }
     *out = e;
     return RRIN_OK;
 }
@@ -426,6 +435,14 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             cd.wpack = blob + pk.w_off;
             cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
             if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; cd.tmap_out = ln.tmap[2]; }
+            if (ln.fuse_mode) {
+                ConvFuse& f = cd.fuse;
+                f.mode = ln.fuse_mode; f.H = H; f.W = W; f.Nt = Nt; f.pair_mul = pm;
+                f.in0 = in0; f.in1 = in1; f.coef = coef; f.h16 = h16;
+                if (ln.fuse_mode == 2) { f.aux = flow4; f.dst = xt8; }
+                else if (ln.fuse_mode == 3) { f.aux = xt8; f.dst = out4; }
+                else if (ln.fuse_mode == 4) { f.aux = out4; f.dst = out; f.h16 = nullptr; }
+            }
             r = conv_launch(cd, st);
         }
         if (r != RRIN_OK) return r;

@@ -1,0 +1,147 @@
+// Per-block-pixel device functions of the glue of Net.process / Net.forward (model.py:32-65).  One "block pixel" is a
+// 2x2 group of pixels (phase = 2*a + b for pixel (2y+a, 2x+b)).  The stand-alone glue kernels (glue.cu) and the fused
+// epilogues of the four `last` convs (conv3x3_v2.cuh) both call these, so the two paths are bit-identical.
+#pragma once
+#include "common.cuh"
+
+namespace rrin {
+
+__device__ __forceinline__ void store_bf16x16(void* dst, const float (&v)[16]) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    d[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+}
+
+// 2x2 block of a 3-channel fp32 NCHW frame: f[c][phase]
+__device__ __forceinline__ void load_block3(const float* __restrict__ img, long HW, int W, int by, int bx, float (&f)[3][4]) {
+    const float* p = img + (long)(2 * by) * W + 2 * bx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float2 r0 = *reinterpret_cast<const float2*>(p + c * HW);
+        const float2 r1 = *reinterpret_cast<const float2*>(p + c * HW + W);
+        f[c][0] = r0.x; f[c][1] = r0.y; f[c][2] = r1.x; f[c][3] = r1.y;
+    }
+}
+
+// t-scaled bidirectional flows, exactly as model.py:38-39 evaluates them in fp32
+// (scalar coefficients formed in double on the host, then one rounding to fp32;
+//  separate multiplies and one add/sub, no FMA contraction).
+__device__ __forceinline__ void tscale(const float4 f, const float* __restrict__ cf, float& a0, float& a1, float& b0, float& b1) {
+    const float c00 = cf[0], c01 = cf[1], c10 = cf[2], c11 = cf[3];
+    a0 = __fadd_rn(__fmul_rn(c00, f.x), __fmul_rn(c01, f.z));   // Flow_t_0 = -(1-t)t F01 + t^2 F10
+    a1 = __fadd_rn(__fmul_rn(c00, f.y), __fmul_rn(c01, f.w));
+    b0 = __fsub_rn(__fmul_rn(c10, f.x), __fmul_rn(c11, f.z));   // Flow_t_1 = (1-t)^2 F01 - t(1-t) F10
+    b1 = __fsub_rn(__fmul_rn(c10, f.y), __fmul_rn(c11, f.w));
+}
+
+// warp() of model.py:8-21: sample img at (x+u-0.5, y+v-0.5), bilinear, zeros padding
+// (F.grid_sample defaults, align_corners=False).  The normalise/un-normalise round trip is
+// reproduced in the reference's fp32 op order (model.py:15-18, GridSampler.h:27-36).
+__device__ __forceinline__ float warp_coord(int g, float d, float size) {
+    const float x = __fadd_rn((float)g, d);
+    const float nrm = __fmul_rn(2.f, __fsub_rn(__fdiv_rn(x, size), 0.5f));
+    return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(nrm, 1.f), size), 1.f), 0.5f);
+}
+__device__ __forceinline__ void bilinear_gather3(const float* __restrict__ img, long HW, int H, int W, float ix, float iy, float (&o)[3]) {
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
+    const int x0 = (int)xw, y0 = (int)yn;
+    const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const float wnw = s * e, wne = s * w, wsw = nn * e, wse = nn * w;
+    const long base = (long)y0 * W + x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* p = img + c * HW + base;
+        float acc = 0.f;
+        if (yin0 && xin0) acc += __ldg(p) * wnw;
+        if (yin0 && xin1) acc += __ldg(p + 1) * wne;
+        if (yin1 && xin0) acc += __ldg(p + W) * wsw;
+        if (yin1 && xin1) acc += __ldg(p + W + 1) * wse;
+        o[c] = acc;
+    }
+}
+
+// ---- K2: cat(F_t0, F_t1, x) (model.py:37-41) for one block pixel.  flow[ph]: Flow U-Net output of the pair;
+// i0/i1: the pair's frames; cf: the sample's coefficients; r16: the sample's packed head input at this block pixel.
+__device__ __forceinline__ void glue_tscale_block(const float4 (&flow)[4], const float* __restrict__ i0, const float* __restrict__ i1,
+                                                  const float* __restrict__ cf, long HW, int W, int by, int bx, __nv_bfloat16* __restrict__ r16) {
+    float a[3][4], b[3][4];
+    load_block3(i0, HW, W, by, bx, a);
+    load_block3(i1, HW, W, by, bx, b);
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        float a0, a1, b0, b1;
+        tscale(flow[ph], cf, a0, a1, b0, b1);
+        float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], 0, 0, 0, 0, 0, 0};
+        store_bf16x16(r16 + ph * 16, v);
+    }
+}
+
+// ---- K3: residue add (model.py:44-45) + two backward warps (model.py:47-48) + cat (model.py:50) for one block pixel
+__device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const float4 (&res)[4], const float* __restrict__ i0,
+                                                const float* __restrict__ i1, const float* __restrict__ cf, long HW, int H, int W, int by,
+                                                int bx, __nv_bfloat16* __restrict__ m16, float4* __restrict__ xt8) {
+    const float fW = (float)W, fH = (float)H;
+    float a[3][4], b[3][4];
+    load_block3(i0, HW, W, by, bx, a);
+    load_block3(i1, HW, W, by, bx, b);
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const int gy = 2 * by + (ph >> 1), gx = 2 * bx + (ph & 1);
+        const float4 r = res[ph];
+        float a0, a1, b0, b1;
+        tscale(flow[ph], cf, a0, a1, b0, b1);
+        a0 = __fadd_rn(a0, r.x); a1 = __fadd_rn(a1, r.y);       // model.py:44
+        b0 = __fadd_rn(b0, r.z); b1 = __fadd_rn(b1, r.w);       // model.py:45
+        float xt1[3], xt2[3];
+        bilinear_gather3(i0, HW, H, W, warp_coord(gx, a0, fW), warp_coord(gy, a1, fH), xt1);   // model.py:47
+        bilinear_gather3(i1, HW, H, W, warp_coord(gx, b0, fW), warp_coord(gy, b1, fH), xt2);   // model.py:48
+        float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph],
+                       xt1[0], xt1[1], xt1[2], xt2[0], xt2[1], xt2[2]};                          // model.py:50
+        store_bf16x16(m16 + ph * 16, v);
+        xt8[ph * 2] = make_float4(xt1[0], xt1[1], xt1[2], xt2[0]);
+        xt8[ph * 2 + 1] = make_float4(xt2[1], xt2[2], 0.f, 0.f);
+    }
+}
+
+// ---- K4: sigmoid + occlusion-weighted blend (model.py:52-55) + cat (model.py:61) for one block pixel
+__device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const float4* __restrict__ xt8, const float* __restrict__ i0,
+                                                 const float* __restrict__ i1, float omt, float t, long HW, int W, int by, int bx,
+                                                 float4* __restrict__ out4, __nv_bfloat16* __restrict__ f16) {
+    float a[3][4], b[3][4];
+    load_block3(i0, HW, W, by, bx, a);
+    load_block3(i1, HW, W, by, bx, b);
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const float4 ta = xt8[ph * 2], tb = xt8[ph * 2 + 1];
+        const float m0 = 1.f / (1.f + expf(-mk[ph].x)), m1 = 1.f / (1.f + expf(-mk[ph].y));   // model.py:52
+        const float w1 = omt * m0, w2 = t * m1;                                                // model.py:54
+        const float den = (w1 + w2) + 1e-8f;
+        const float o0 = (w1 * ta.x + w2 * ta.w) / den;                                        // model.py:55
+        const float o1 = (w1 * ta.y + w2 * tb.x) / den;
+        const float o2 = (w1 * ta.z + w2 * tb.y) / den;
+        out4[ph] = make_float4(o0, o1, o2, 0.f);
+        float v[16] = {a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], o0, o1, o2, 0, 0, 0, 0, 0, 0, 0};   // model.py:61
+        store_bf16x16(f16 + ph * 16, v);
+    }
+}
+
+// ---- K5: final residue + clamp (model.py:62-63) -> the block pixel's 2x2 pixels of the fp32 NCHW result
+__device__ __forceinline__ void glue_clamp_block(const float4 (&r)[4], const float4 (&o)[4], long HW, int W, int by, int bx, float* __restrict__ y) {
+    float v[3][4];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        v[0][ph] = fminf(fmaxf(r[ph].x + o[ph].x, 0.f), 1.f);
+        v[1][ph] = fminf(fmaxf(r[ph].y + o[ph].y, 0.f), 1.f);
+        v[2][ph] = fminf(fmaxf(r[ph].z + o[ph].z, 0.f), 1.f);
+    }
+    float* d = y + (long)(2 * by) * W + 2 * bx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        *reinterpret_cast<float2*>(d + c * HW) = make_float2(v[c][0], v[c][1]);
+        *reinterpret_cast<float2*>(d + c * HW + W) = make_float2(v[c][2], v[c][3]);
+    }
+}
+
+}  // namespace rrin

@@ -25,6 +25,16 @@ enum ConvEpilogue : int {
 enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1, SCHED_S2D8 = 2 };   // S2D8: half-phase stages of the TMA kernel
 enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3, PACK_NORMAL_CG2 = 4 };   // CG2: per-CTA halves of every block
 
+// Glue fused into the fp32 epilogue of a `last` conv (conv3x3_v2.cuh FuseParams); mode 0 = none.
+struct ConvFuse {
+    int mode = 0;
+    int H = 0, W = 0, Nt = 0, pair_mul = 0;
+    const float* in0 = nullptr; const float* in1 = nullptr; const float* coef = nullptr;
+    const void* aux = nullptr;
+    void* h16 = nullptr;
+    float* dst = nullptr;
+};
+
 // One 3x3 convolution launch (see conv3x3.cuh for the data layouts).
 struct ConvDesc {
     const void* src0 = nullptr;
@@ -47,6 +57,7 @@ struct ConvDesc {
     const void* tmap0 = nullptr;  // TMA configs: pre-encoded CUtensorMap (128 bytes, host memory) of src0 / src1, or null
     const void* tmap1 = nullptr;
     const void* tmap_out = nullptr; // TMA-epilogue configs: pre-encoded map of `out`, or null
+    ConvFuse fuse;                // `last` convs (fp32 epilogue) only
 };
 
 // Launch with programmatic stream serialization (see common.cuh: pdl_wait / pdl_launch_dependents).
