@@ -262,8 +262,10 @@ def run_gpu(args):
         dom_name, dom = max(classes.items(), key=lambda kv: kv[1]["ms"])
         conv_ms = sum(c["ms"] for n, c in classes.items() if n.startswith("conv"))
         conv_fl = sum(c["flops"] for n, c in classes.items() if n.startswith("conv"))
-        glue_ms = sum(c["ms"] for n, c in classes.items() if not n.startswith("conv"))
-        glue_by = sum(c["bytes"] for n, c in classes.items() if not n.startswith("conv"))
+        # HBM-bound glue: pack_pair plus the four `last` convs whose epilogues carry the fused t-scale / warp / blend / clamp
+        is_glue = lambda n: (not n.startswith("conv")) or n.endswith("+glue")
+        glue_ms = sum(c["ms"] for n, c in classes.items() if is_glue(n))
+        glue_by = sum(c["bytes"] for n, c in classes.items() if is_glue(n))
         peak_tf = peaks["tf_sustained"]             # kernels timed inside a long step -> sustained peak
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
         traffic = None
@@ -278,7 +280,8 @@ def run_gpu(args):
                     "share_of_step": dom["ms"] / step_ms,
                     "all_convs": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12, "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf,
                                   "share_of_step": conv_ms / step_ms},
-                    "warp_blend_glue": {"bound": "hbm", "achieved": glue_by / (glue_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                    "warp_blend_glue": {"bound": "hbm", "kernels": sorted(n for n in classes if is_glue(n)),
+                                        "achieved": glue_by / (glue_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                         "unit": "GB/s", "frac": glue_by / (glue_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                         "share_of_step": glue_ms / step_ms},
                     "classes": {n: {"ms": round(c["ms"], 4), "launches": c["launches"],
