@@ -43,7 +43,7 @@ namespace rrin {
 // 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1, 1>  level-1 cat(64+64)->64
 // 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
 //                                                    the next tile's MMAs start as soon as the first slots are drained)
-// 17 : < 64, 64, 128, 4, 2,  4, TAPS9, 0, 0, 1, 1>  same tile, per-thread stores: folded upsample conv scattering into level 1
+// 17 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 0, 2, 1>  per-thread stores: folded upsample conv scattering into level 1
 // 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
 // 19 : < 64, 64, 128, 3, 2,  6, TAPS9, 0, 1, 2, 2>  levels >= 2 plain / cat on CTA PAIRS (cta_group::2, M = 256): half of every
 //                                                    weight block per CTA
@@ -55,7 +55,7 @@ namespace rrin {
     X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1)   \
     X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1)   \
     X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
-    X(17, 64, 64, 128, 4, 2, 4, 0, 0, 0, 1, 1)  \
+    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1)  \
     X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
     X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2)
 
