@@ -295,10 +295,10 @@ def run_gpu(args):
                "sample": f"one {strip_h}x{W} strip of the 1080p pair (= {strip_h / H:.4f} frame), fp32, t=0.5, {dt:.1f} s"}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 operands, f32 accumulate", "data": "synthetic",
+                "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"1080p (1920x1088) 2x interpolation of a synthetic clip, one batch of {B} consecutive frame pair(s) "
                                        "per step, t=0.5, random-init weights (torch.manual_seed(0))",
-                           "batch": B,
+                           "batch": B, "arithmetic": "bf16 operands on tcgen05 tensor cores, fp32 accumulation; flows / mask logits / blend in fp32",
                            "sharding": f"{world} rank(s), contiguous shards of the {CLIP_FRAMES}-frame clip, no collective",
                            "l2": f"per-step working set (~{0.75 * B:.1f} GB of activations) exceeds the 126 MB L2; no explicit flush",
                            "tflop_per_frame": FLOP_PER_PX * H * W / 1e12,
