@@ -34,7 +34,7 @@ namespace rrin {
     X(7, 64, 64, 64, 1, 3, 6, 1)   \
     X(8, 64, 16, 128, 1, 3, 12, 1)
 
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>  (XF = 0 unless noted)
 // 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
 // 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
 // 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
@@ -47,29 +47,32 @@ namespace rrin {
 // 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
 // 19 : < 64, 64, 128, 3, 2,  6, TAPS9, 0, 1, 2, 2>  levels >= 2 plain / cat on CTA PAIRS (cta_group::2, M = 256): half of every
 //                                                    weight block per CTA
+// 20 : < 64, 64, 128, 2, 2,  4, TAPS9, 0, 1, 2, 1, XF>  exact bilinear x2 source (up.1 convs of levels >= 2): TMA-staged raw coarse
+//                                                    tile + four transform warps
 #define RRIN_CONV2_CONFIGS(X)                   \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1) \
-    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1) \
-    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1)  \
-    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 2, 1)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1)   \
-    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
-    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1)  \
-    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1)  \
-    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2)
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
+    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
+    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1, 0)  \
+    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 2, 1, 0)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1, 0)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1, 0)   \
+    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
+    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1, 0)  \
+    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
+    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0) \
+    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1)
 
 constexpr int kV2Base = 10;
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf; };
 static const CfgInfo kCfg1[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB, STRIP) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP, 1},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP, 1, 0},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>::PW, SCHED, RES, ETMA, 0, CG},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>::PW, SCHED, RES, ETMA, 0, CG, XF},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -245,11 +248,11 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
     return RRIN_OK;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF>
 static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
                        const CUtensorMap& tmw, int grid, cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
     const int dev = current_device();
     if (dev < 0) { set_error("conv3x3: no current CUDA device"); return RRIN_ERR_CUDA; }
     if (!g_attr_set[dev][id]) {
@@ -291,9 +294,10 @@ int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int wh
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     const cuuint32_t box_in[4] = {64, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
     const cuuint32_t box_out[4] = {64, 8, 4, 1};
+    const cuuint32_t box_raw[4] = {64, (cuuint32_t)(4 * c.msub + 2), (cuuint32_t)(kTileH / 2 + 2), 1};   // which = 2: coarse tile of an upsample source
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                    which ? box_out : box_in, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    which == 2 ? box_raw : (which ? box_out : box_in), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, N, H, W, C); return RRIN_ERR_CUDA; }
     return RRIN_OK;
@@ -303,7 +307,8 @@ bool conv_config_tma_epilogue(int cfg) { return cfg_valid(cfg) && cfg_info(cfg).
 static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const int cfg = d.cfg;
     const CfgInfo& c = cfg_info(cfg);
-    if (d.mode != SRC_PLAIN && d.mode != SRC_CAT) { set_error("conv3x3(tma): source mode %d needs the transform kernel", d.mode); return RRIN_ERR_BAD_ARG; }
+    if (c.xf ? (d.mode != SRC_UP) : (d.mode != SRC_PLAIN && d.mode != SRC_CAT)) { set_error("conv3x3(tma): source mode %d does not fit config %d", d.mode, cfg); return RRIN_ERR_BAD_ARG; }
+    if (c.xf && ((d.H | d.W) & 1)) { set_error("conv3x3(up): odd output size %dx%d", d.H, d.W); return RRIN_ERR_BAD_SHAPE; }
     if (d.pad_clamp) { set_error("conv3x3(tma): replicate padding is not available (TMA zero-fills)"); return RRIN_ERR_BAD_ARG; }
     if (d.ring_only) { set_error("conv3x3(tma): ring_only is not available"); return RRIN_ERR_BAD_ARG; }
     const int ctot = d.c0 + (d.mode == SRC_CAT ? d.c1 : 0);
@@ -345,7 +350,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     CUtensorMap tm0, tm1, tmo;
     if (d.tmap0) memcpy(&tm0, d.tmap0, sizeof tm0);
-    else if (int r = conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, 0, &tm0)) return r;
+    else if (int r = c.xf ? conv_make_tmap(d.src0, d.N, d.H / 2, d.W / 2, d.c0, cfg, 2, &tm0) : conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, 0, &tm0)) return r;
     if (d.mode == SRC_CAT) {
         if (d.tmap1) memcpy(&tm1, d.tmap1, sizeof tm1);
         else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, 0, &tm1)) return r;
@@ -387,7 +392,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     int rc = RRIN_ERR_BAD_ARG;
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>(id, p, tm0, tm1, tmo, tmw, grid, stream); break;
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>(id, p, tm0, tm1, tmo, tmw, grid, stream); break;
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }

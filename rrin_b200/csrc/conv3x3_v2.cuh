@@ -72,7 +72,8 @@ struct ConvParamsV2 {
     unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
 };
 
-constexpr int v2_threads(int ew) { return (4 * ew + 3) * 32; }     // EW epilogue groups of 4 warps + MMA, weights, activations
+// EW epilogue groups of 4 warps + MMA, weights, activations (+ 4 transform warps when the A operand is computed: XF)
+constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32; }
 
 // SCHED: 0 nine taps | 1 sixteen (block shift, phase) entries over one 64-channel chunk holding 4 phases x 16 ch (packed heads)
 //        | 2 half-phase: chunk parity = input phase row r, eight entries per chunk (level-0 tensors, 4 phases x 32 ch)
@@ -87,7 +88,10 @@ constexpr int v2_threads(int ew) { return (4 * ew + 3) * 32; }     // EW epilogu
 //        MMAs over both CTAs' sub-tiles; each CTA stages its own activation halo but only HALF of every weight block
 //        (N/2 rows), so the per-SM shared-memory operand traffic of an MMA drops from 8 KB to 6 KB per 64 cycles and the
 //        weight stream per SM halves.  Streamed 9-tap schedule only.
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1>
+// XF   : 1 = the A operand is the exact bilinear x2 upsample (nn.Upsample, align_corners=False, unet.py:77) of a coarser
+//        NHWC tensor: TMA stages the raw coarse tile [10 rows][4*MSUB+2 px][64 ch] in shared memory, four transform
+//        warps interpolate it into the swizzled halo tile (shared-memory reads instead of global-load latency).
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0>
 struct ConvCfgV2 {
     static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
@@ -99,16 +103,22 @@ struct ConvCfgV2 {
     static_assert(CG == 1 || (CG == 2 && SCHED == 0 && !RES && NT == 128), "CTA pairs: streamed 9-tap schedule, N = 128");
     static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
     static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;
-    static constexpr int THREADS = v2_threads(EW);
+    static constexpr int THREADS = v2_threads(EW, XF);
+    static constexpr int RAW_W = 4 * MSUB + 2, RAW_H = kTileH / 2 + 2;            // raw coarse tile (XF)
+    static constexpr int RAW_BYTES = RAW_H * RAW_W * 128;
+    static constexpr int RAW_STRIDE = (RAW_BYTES + 1023) / 1024 * 1024;
+    static constexpr int RAW_SLOTS = XF ? 2 : 0;
+    static_assert(!XF || (CG == 1 && SCHED == 0), "transform stage: single CTA, 9-tap schedule");
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;
     static constexpr int EPI_STAGE = ETMA ? 4 * EW * 4096 : 0;         // per warp: 32 pixels x 64 channels bf16, SWIZZLE_128B
     static constexpr int OFF_EPI = OFF_B + B_BYTES;                     // 1024-byte aligned (A stages and weight blocks are)
-    static constexpr int OFF_BIAS = OFF_EPI + EPI_STAGE;
+    static constexpr int OFF_RAW = OFF_EPI + EPI_STAGE;                 // 1024-byte aligned
+    static constexpr int OFF_BIAS = OFF_RAW + RAW_SLOTS * RAW_STRIDE;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
-    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS;
+    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS;
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
     static_assert(KCS == 64, "one 64-channel TMA box per stage");
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
@@ -180,16 +190,17 @@ struct TileWalkV2 {
     }
 };
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG>
-__global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF>
+__global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tmo,
                                                                      const __grid_constant__ CUtensorMap tmw) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;       // CTA pair: rank 0 is the leader (issues the MMAs)
     constexpr int N_ENT = C::N_ENT;
     constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
+    constexpr int W_X = 4 * EW + 3;                                      // XF: four transform warps W_X .. W_X+3
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
     uint8_t* smem = smem_raw + (s_base - smem_u32(smem_raw));
@@ -203,6 +214,8 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
     auto b_empty = [&](int i) { return s_bar + 8u * (2 * SA + SB + i); };
     auto acc_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + i); };
     auto acc_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + C::SLOTS + i); };
+    auto raw_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + i); };
+    auto raw_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + C::RAW_SLOTS + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
 
     const int warp = threadIdx.x >> 5;
@@ -213,7 +226,8 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), XF ? 128 : 1); mbar_init(a_empty(i), 1); }      // XF: the transform threads fill A
+        for (int i = 0; i < C::RAW_SLOTS; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), CG * kEpiWarps * 32); }   // both CTAs' epilogues
         mbar_fence_init();
@@ -257,6 +271,13 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
+                    if (XF) {           // raw coarse tile of chunk st into the staging ring; the transform warps fill the A stage
+                        const int rs = it % C::RAW_SLOTS;
+                        mbar_wait(raw_empty(rs), ((it / C::RAW_SLOTS) & 1) ^ 1);
+                        mbar_arrive_expect_tx(raw_full(rs), C::RAW_BYTES);
+                        tma_load_4d(s_base + C::OFF_RAW + rs * C::RAW_STRIDE, &tm0, st * 64, t.sx0 * 4 - 1, t.ty * (kTileH / 2) - 1, t.n, raw_full(rs));
+                        continue;
+                    }
                     const int stage = it % SA;
                     const long long c0 = prof ? clock64() : 0;
                     mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
@@ -441,6 +462,47 @@ __global__ void __launch_bounds__(v2_threads(EW), 1) conv3x3_tma_kernel(const __
             if (p.prof) { p.prof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; p.prof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
         }
         __syncwarp();
+    } else if (XF && warp >= W_X) {
+        // =========================================================== transform warps: exact bilinear x2 of the raw coarse tile
+        // thread -> 16-byte channel chunk c8 of halo pixels q = px0, px0 + 16, ...; source taps / weights as ATen's
+        // upsample_bilinear2d (align_corners=False): src = max((o + 0.5) / 2 - 0.5, 0), i1 = i0 + (i0 < size - 1)
+        const int xt = threadIdx.x - W_X * 32, c8 = xt & 7, px0 = xt >> 3;
+        const int sh = p.H >> 1, sw = p.W >> 1;
+        int it = 0;
+        while (walk.next<MSUB, CG>(p, t)) {
+            const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;              // fine halo origin
+            const int cx0 = t.sx0 * 4 - 1, cy0 = t.ty * (kTileH / 2) - 1;      // raw coarse tile origin
+            for (int si = 0; si < nst; ++si, ++it) {
+                const int stage = it % SA, rs = it % C::RAW_SLOTS;
+                mbar_wait(raw_full(rs), (it / C::RAW_SLOTS) & 1);
+                mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
+                const uint32_t raw = s_base + C::OFF_RAW + rs * C::RAW_STRIDE, dst = s_a + stage * C::A_STAGE;
+#pragma unroll 2
+                for (int q = px0; q < (kTileH + 2) * C::PW; q += 16) {
+                    const int hy = q / C::PW, hx = q - hy * C::PW;
+                    const int gy = y0 + hy, gx = x0 + hx;
+                    uint4 o = make_uint4(0, 0, 0, 0);                          // outside the fine image: the conv's zero padding
+                    if ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
+                        int iy0, iy1, ix0, ix1; float wy, wx;
+                        up2_taps(gy, sh, iy0, iy1, wy);
+                        up2_taps(gx, sw, ix0, ix1, wx);
+                        const int r00 = (iy0 - cy0) * C::RAW_W + (ix0 - cx0), r01 = (iy0 - cy0) * C::RAW_W + (ix1 - cx0);
+                        const int r10 = (iy1 - cy0) * C::RAW_W + (ix0 - cx0), r11 = (iy1 - cy0) * C::RAW_W + (ix1 - cx0);
+                        auto lds = [&](int r) {
+                            uint4 v;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                         : "r"(raw + r * 128 + ((c8 ^ (r & 7)) << 4)));
+                            return v;
+                        };
+                        o = bilerp_bf16x8(lds(r00), lds(r01), lds(r10), lds(r11), wx, wy);
+                    }
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128 + ((c8 ^ (q & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                }
+                fence_proxy_async_smem();               // generic-proxy writes -> visible to the tensor core's operand reads
+                mbar_arrive(a_full(stage));
+                mbar_arrive(raw_empty(rs));
+            }
+        }
     } else if (warp < 4 * EW) {
         // =========================================================== epilogue: EW groups of 4 warps (quadrant = warp % 4)
         const int quad = warp & 3, grp = warp >> 2;

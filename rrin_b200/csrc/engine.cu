@@ -70,6 +70,13 @@ static int big_cfg() {
     return (e && atoi(e) == 19) ? 19 : 16;
 }
 
+// exact bilinear upsample convs of levels >= 2: TMA-staged transform (config 20); RRIN_UP_CFG=5 selects the register-computed
+// producer kernel (A/B timing runs)
+static int up_cfg() {
+    const char* e = getenv("RRIN_UP_CFG");
+    return (e && atoi(e) == 5) ? 5 : 20;
+}
+
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
@@ -98,7 +105,7 @@ static Schedule build_schedule() {
                 if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }                // 32 channels: cp.async producers (KCS = 32)
                 else { m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
             } else {
-                m.cfg = (src == K_UP) ? 5 : big_cfg(); m.n_stages = cin / 64;
+                m.cfg = (src == K_UP) ? up_cfg() : big_cfg(); m.n_stages = cin / 64;
                 if (m.cfg == 19) m.kind = PACK_NORMAL_CG2;
             }
         }
@@ -409,7 +416,8 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
         for (Launch& ln : e->launches) {
             if (ln.glue >= 0 || ln.cd.cfg < 10) continue;
             const ConvDesc& c = ln.cd;
-            int r = conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, 0, ln.tmap[0]);
+            int r = (c.mode == SRC_UP) ? conv_make_tmap(dec(c.src0), c.N, c.H / 2, c.W / 2, c.c0, c.cfg, 2, ln.tmap[0])   // raw coarse tile
+                                       : conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, 0, ln.tmap[0]);
             if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, 0, ln.tmap[1]);
             if (r == RRIN_OK && conv_config_tma_epilogue(c.cfg)) r = conv_make_tmap(dec(c.out), c.N, c.H, c.W, c.cout_stride, c.cfg, 1, ln.tmap[2]);
             if (r != RRIN_OK) return r;

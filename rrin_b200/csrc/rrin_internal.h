@@ -87,7 +87,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
 int conv_num_configs();
 bool conv_config_valid(int cfg);
 // TMA configs (id >= 10): encode the tensor map of a bf16 NHWC tensor [N,H,W,C] (C % 64 == 0) into tmap_out (128 bytes, host);
-// which = 0: A-operand source (halo box), 1: epilogue destination (one warp's 8x4-pixel box)
+// which = 0: A-operand source (halo box), 1: epilogue destination (one warp's 8x4-pixel box), 2: raw coarse tile of an
+// exact-upsample source (dims are those of the coarse tensor)
 int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out);
 bool conv_config_tma_epilogue(int cfg);
 int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);

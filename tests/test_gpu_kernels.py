@@ -66,6 +66,11 @@ NORMAL_CASES = [
     ("tma_many_tiles_l3_ntiles", 16, "plain", 256, 256, True, 2, 100, 72),
     ("tma_direct_l2_cat", 17, "cat", 128, 128, True, 1, 12, 20),
     ("tma_msub3_many_tiles", 18, "plain", 64, 128, False, 1, 120, 200),
+    # exact bilinear x2 source: TMA-staged coarse tile + transform warps
+    ("tma_up_l2", 20, "up", 256, 128, False, 1, 16, 16),
+    ("tma_up_l3_ntiles", 20, "up", 512, 256, False, 1, 12, 20),
+    ("tma_up_many_tiles", 20, "up", 256, 128, False, 2, 208, 104),
+    ("tma_up_odd_sizes", 20, "up", 128, 128, True, 1, 34, 50),
     # CTA pairs (cta_group::2)
     ("pair_l2_128_128", 19, "plain", 128, 128, True, 2, 12, 20),
     ("pair_l2_cat", 19, "cat", 128, 128, True, 1, 12, 20),
