@@ -3,7 +3,7 @@
 
 Contract: ``python bench.py --gpus N --steps K --warmup W`` (N>1: launched under torchrun,
 one rank per GPU).  A *step* is one pass of the hot path (``Net.forward``,
-/root/reference/model.py:59-65) over one batch of ``--batch`` (default 2) consecutive
+/root/reference/model.py:59-65) over one batch of ``--batch`` (default 4) consecutive
 1920x1088 frame pairs at t=0.5 -- the unit of BASELINE.json configs[2] ("1080p 2x
 interpolation of a 240-frame synthetic clip, sharded over 1/2/4/8 B200").  Each rank owns a
 contiguous shard of the synthetic clip (rrin_b200.sharding), device resident, and interpolates
@@ -15,6 +15,11 @@ device-timed region.  One JSON line is printed by rank 0; ``value`` counts inter
 (oracle/rrin_oracle.py: the same torch CPU operators at the same call sites as the reference,
 which is pure Python and cannot travel to the GPU box) on all host threads, each step a bounded
 strip of the same 1080p workload.
+
+``--impl library`` (not part of the driver's contract; context only) times the same oracle
+restatement as torch eager operators on cuda:0 -- cuDNN convolutions in fp32, TF32 and bf16
+autocast/channels_last -- the "GPU library baseline" of SURVEY.md 8(d): what the unmodified
+reference would execute on a B200.
 """
 from __future__ import annotations
 
@@ -129,6 +134,59 @@ def run_reference(args):
                        "reference_path": "oracle port of Net.forward on torch CPU operators (reference is Python; cannot travel)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU library arm
+def run_library(args):
+    """SURVEY.md 8(d) "GPU library baseline": the oracle's restatement of Net.forward issued as torch eager operators on
+    cuda:0 -- cuDNN convolutions, ATen grid_sample / upsample / pooling -- i.e. what the unmodified reference executes on a
+    B200 today (the reference itself cannot travel to the GPU box).  Three precisions; `value` is the fastest.  None of
+    rrin_b200's kernels run here; the line is context for the headline, not a product path."""
+    import torch
+    from oracle import rrin_oracle as O
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    sd32 = {k: v.to(dev) for k, v in O.seeded_state_dict().items()}
+    a, b = (x.to(dev) for x in O.seeded_frames(1, H, W, seed=1, smooth=True))
+    K, Wm = max(1, min(args.steps, 20)), max(args.warmup, 3)
+
+    def timed(fn):
+        for _ in range(Wm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return K * 1e3 / e0.elapsed_time(e1)
+
+    modes = {}
+    with torch.no_grad():
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        modes["fp32"] = timed(lambda: O.forward(sd32, a, b, 0.5))
+        torch.backends.cudnn.allow_tf32 = True                  # PyTorch's default for cuDNN convolutions
+        modes["tf32"] = timed(lambda: O.forward(sd32, a, b, 0.5))
+        sdcl = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd32.items()}
+        acl, bcl = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
+
+        def bf16():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.forward(sdcl, acl, bcl, 0.5)
+        modes["bf16_autocast_channels_last"] = timed(bf16)
+    best = max(modes, key=modes.get)
+    line = {"impl": "library", "metric": METRIC, "value": modes[best], "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+            "ms_per_step": 1e3 / modes[best], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": best,
+            "data": "synthetic",
+            "config": {"workload": "1080p (1920x1088) 2x interpolation, one frame pair per step, t=0.5, random-init weights",
+                       "path": "oracle restatement of Net.forward as torch eager operators on the GPU (cuDNN convolutions, "
+                               "cudnn.benchmark=True); device-resident inputs"},
+            "modes_frames_per_sec": modes}
     print(json.dumps(line), flush=True)
 
 
@@ -344,9 +402,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=2, help="frame pairs per step (per GPU)")
-    ap.add_argument("--impl", default="rrin_b200", choices=["rrin_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="frame pairs per step (per GPU)")
+    ap.add_argument("--impl", default="rrin_b200", choices=["rrin_b200", "reference", "library"])
     args = ap.parse_args()
+    if args.impl == "library":
+        return run_library(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,7 +1,7 @@
 """CPU oracle for the RRIN forward pass -- TEST INFRASTRUCTURE, NOT PRODUCT.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
-``--impl reference`` legs may import this module.  The product path
+``--impl reference`` / ``--impl library`` (baseline) legs may import this module.  The product path
 (``rrin_b200.model.Net``) never touches it and has no CPU fallback.
 
 What it is: a functional restatement of ``Net.forward`` of Thomasedv/RRIN
@@ -72,8 +72,8 @@ def unet_forward(sd: StateDict, prefix: str, x: torch.Tensor) -> torch.Tensor:
 def warp(img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
     """``warp`` -- model.py:8-21 (same fp32 op order; meshgrid built with torch)."""
     _, _, H, W = img.shape
-    gx = torch.arange(W).view(1, 1, W).expand(1, H, W)
-    gy = torch.arange(H).view(1, H, 1).expand(1, H, W)
+    gx = torch.arange(W, device=img.device).view(1, 1, W).expand(1, H, W)
+    gy = torch.arange(H, device=img.device).view(1, H, 1).expand(1, H, W)
     u, v = flow[:, 0], flow[:, 1]
     x = gx.expand_as(u).float() + u              # model.py:15
     y = gy.expand_as(v).float() + v              # model.py:16
