@@ -344,13 +344,20 @@ def run_gpu(args):
         glue_by = sum(c["bytes"] for n, c in classes.items() if is_glue(n))
         peak_tf = peaks["tf_sustained"]             # kernels timed inside a long step -> sustained peak
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from an ncu --set full capture
+        traffic, traffic_of = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes of one launch of the class (ncu --set full capture)
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom_name)
+                tj = json.load(f)
+            ent = tj.get(dom_name)
+            if isinstance(ent, dict):
+                traffic = ent["traffic"]
+                traffic_of = {k: ent[k] for k in ("launch", "algorithmic", "ratio") if k in ent}
+                traffic_of["capture"] = tj.get("_note", "")
+            else:
+                traffic = ent
         roofline = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": traffic,
+                    "frac": ach / peak_tf, "traffic": traffic, "traffic_of": traffic_of,
                     "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                     "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                     "share_of_step": dom["ms"] / step_ms,

@@ -15,7 +15,7 @@ import sys, os
 sys.path.insert(0, os.getcwd())
 from rrin_b200 import engine
 import torch
-e = engine.Engine(torch.device("cuda", 0), 1, 1088, 1920)
+e = engine.Engine(torch.device("cuda", 0), int(os.environ.get("BATCH", "4")), 1088, 1920)
 print(sum(1 for n, *_ in e.launch_table() if n.startswith("conv")))
 PY
 )

@@ -1,5 +1,5 @@
 """Minimal program for ncu: W warm-up forwards + 1 forward of the 1080p step (no timing, no CPU work).
-Usage: python tools/profile_step.py [H W [warmups]]"""
+Usage: [BATCH=b] python tools/profile_step.py [H W [warmups]]     (BATCH defaults to bench.py's 4 frame pairs per step)"""
 import os
 import sys
 
@@ -16,7 +16,8 @@ net = Net()
 net.load_state_dict(O.seeded_state_dict(), strict=True)
 net = net.cuda().eval()
 a, b = O.seeded_frames(1, h, w, seed=2, smooth=True)
-a, b = a.cuda(), b.cuda()
+nb = int(os.environ.get("BATCH", "4"))
+a, b = a.cuda().expand(nb, -1, -1, -1).contiguous(), b.cuda().expand(nb, -1, -1, -1).contiguous()
 for _ in range(warm + 1):
     y = net(a, b, t=0.5)
 torch.cuda.synchronize()
