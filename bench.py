@@ -134,7 +134,7 @@ def run_reference(args):
                        "reference_path": "oracle port of Net.forward on torch CPU operators (reference is Python; cannot travel)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU library arm
@@ -187,7 +187,7 @@ def run_library(args):
                        "path": "oracle restatement of Net.forward as torch eager operators on the GPU (cuDNN convolutions, "
                                "cudnn.benchmark=True); device-resident inputs"},
             "modes_frames_per_sec": modes}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -205,7 +205,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")              # keep stdout to the one JSON line (no version banner)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
@@ -401,10 +400,33 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries print there too (NCCL's version banner at communicator init goes
+    through C stdio), so file descriptor 1 is pointed at stderr for the whole run and the line is written to the saved
+    descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

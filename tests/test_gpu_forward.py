@@ -72,6 +72,26 @@ def test_forward_368_config1_matches_oracle_and_kat(golden_dir):
     assert (y - ref).abs().max().item() <= 1e-3 and psnr(y, ref) >= 70
 
 
+SHAPES = [(1, 16, 16), (1, 16, 64), (1, 64, 16), (1, 48, 112), (1, 80, 272), (1, 144, 32), (1, 16, 528), (3, 32, 80), (2, 128, 144)]
+
+
+@pytest.mark.parametrize("n,h,w", SHAPES, ids=[f"{n}x{h}x{w}" for n, h, w in SHAPES])
+def test_forward_shape_sweep_matches_oracle(n, h, w):
+    """Edge geometry: the smallest legal frame (level 4 of `Flow` is 1x1), single-tile and partial-tile widths /
+    heights at every level, frames too small for the folded-upsample border ring, batches.  Oracle on the host."""
+    sd = O.seeded_state_dict()
+    net = make_net(sd)
+    a, b = O.seeded_frames(n, h, w, seed=10 + h + w)
+    for t in (0.5, 0.2):
+        y = net(a.cuda(), b.cuda(), t=t).cpu()
+        ref = O.forward(sd, a, b, t)
+        err = (y - ref).abs().max().item()
+        assert err <= 1e-3, f"{n}x{h}x{w} t={t}: max-abs {err}"
+    sds = O.seeded_state_dict(stress_flow=100.0)
+    ys = make_net(sds)(a.cuda(), b.cuda(), t=0.5).cpu()
+    assert psnr(ys, O.forward(sds, a, b, 0.5)) >= 50
+
+
 def test_batch_tensor_t_and_multi_t_agree():
     sd = O.seeded_state_dict(stress_flow=100.0)
     net = make_net(sd)
