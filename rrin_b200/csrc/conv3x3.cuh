@@ -78,8 +78,9 @@ constexpr int kTileH = 16;
 // 16 x 8 tile: halo = 3 lines x (L+2) positions, accumulator row m = position m along the strip.  Used to recompute the
 // outermost ring after a weight-folded upsample conv: only those pixels differ (zero padding vs folded halo).
 // A strip covers kStripLen positions; the accumulator still has 128 rows (rows >= kStripLen read past the 3 halo lines and
-// are discarded): short strips spread the latency-bound halo construction over many more CTAs than 128-pixel ones.
-constexpr int kStripLen = 32;
+// are discarded): shorter strips spread the latency-bound halo construction over more CTAs than 128-pixel ones, longer ones
+// re-stream the weight blocks less often; 64 measured best at batch 1 and 4 (32: +0.4 %, 128: +1 % at batch 1).
+constexpr int kStripLen = 64;
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP = 0>
 struct ConvCfg {
     static constexpr int CH8 = KCS / 8;                // 16-byte channel groups (planes) per stage
