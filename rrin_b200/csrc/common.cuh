@@ -290,6 +290,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t addr, uint32_t
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
            (1ull << 46) | (2ull << 61);
 }
+// Same for 64-byte rows (32 bf16 channels per pixel, TMA SWIZZLE_64B): 16-byte chunk index bits [4,6) XOR-ed with
+// address bits [7,9); an 8-row group is 512 bytes.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t addr, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           (1ull << 46) | (4ull << 61);
+}
 // Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4)      // D format  : f32

@@ -49,6 +49,8 @@ namespace rrin {
 //                                                    weight block per CTA
 // 20 : < 64, 64, 128, 2, 2,  4, TAPS9, 0, 1, 2, 1, XF>  exact bilinear x2 source (up.1 convs of levels >= 2): TMA-staged raw coarse
 //                                                    tile + four transform warps
+// 21 : < 32, 32,  64, 4, 3,  9, TAPS9, 1, 1, 1, 1>     level-1 block.0 on the pooled 32-channel level-0 tensor: 64-byte pixel rows
+//                                                    (TMA SWIZZLE_64B boxes, 64-byte-swizzle A descriptors), weights resident
 #define RRIN_CONV2_CONFIGS(X)                   \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
     X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
@@ -60,7 +62,8 @@ namespace rrin {
     X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1, 0)  \
     X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
     X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0) \
-    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1)
+    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1) \
+    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0)
 
 constexpr int kV2Base = 10;
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf; };
@@ -283,21 +286,23 @@ static EncodeTiledFn encode_fn() {
 // box {64 ch, 8 pixels, 4 rows, 1 image} (one epilogue warp's share of a sub-tile), out-of-bounds elements not written.
 int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out) {
     if (!cfg_valid(cfg) || !cfg_is_v2(cfg)) { set_error("conv_make_tmap: config %d is not a TMA config", cfg); return RRIN_ERR_BAD_ARG; }
-    if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || C % 64 || N <= 0 || H <= 0 || W <= 0) {
-        set_error("conv_make_tmap: bad tensor (C=%d must be a multiple of 64, base 16-byte aligned)", C);
+    const CfgInfo& c = cfg_info(cfg);
+    const int box_ch = (which == 0 && c.kcs == 32) ? 32 : 64;          // input boxes of the 32-channel config: 64-byte rows
+    if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || C % box_ch || N <= 0 || H <= 0 || W <= 0) {
+        set_error("conv_make_tmap: bad tensor (C=%d must be a multiple of %d, base 16-byte aligned)", C, box_ch);
         return RRIN_ERR_BAD_SHAPE;
     }
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return RRIN_ERR_UNSUPPORTED; }
-    const CfgInfo& c = cfg_info(cfg);
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box_in[4] = {64, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
+    const cuuint32_t box_in[4] = {(cuuint32_t)box_ch, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
     const cuuint32_t box_out[4] = {64, 8, 4, 1};
     const cuuint32_t box_raw[4] = {64, (cuuint32_t)(4 * c.msub + 2), (cuuint32_t)(kTileH / 2 + 2), 1};   // which = 2: coarse tile of an upsample source
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(reinterpret_cast<CUtensorMap*>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                    which == 2 ? box_raw : (which ? box_out : box_in), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    which == 2 ? box_raw : (which ? box_out : box_in), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    box_ch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d]", (int)r, N, H, W, C); return RRIN_ERR_CUDA; }
     return RRIN_OK;
@@ -312,9 +317,10 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     if (d.pad_clamp) { set_error("conv3x3(tma): replicate padding is not available (TMA zero-fills)"); return RRIN_ERR_BAD_ARG; }
     if (d.ring_only) { set_error("conv3x3(tma): ring_only is not available"); return RRIN_ERR_BAD_ARG; }
     const int ctot = d.c0 + (d.mode == SRC_CAT ? d.c1 : 0);
-    if (d.c0 % 64 || (d.mode == SRC_CAT && d.c1 % 64) || ctot % c.kcs) { set_error("conv3x3(tma): %d(+%d) stored channels not a multiple of 64 / stage width %d", d.c0, d.c1, c.kcs); return RRIN_ERR_BAD_SHAPE; }
+    const int box_ch = c.kcs < 64 ? c.kcs : 64;
+    if (d.c0 % box_ch || (d.mode == SRC_CAT && d.c1 % box_ch) || ctot % c.kcs) { set_error("conv3x3(tma): %d(+%d) stored channels not a multiple of %d / stage width %d", d.c0, d.c1, box_ch, c.kcs); return RRIN_ERR_BAD_SHAPE; }
     ConvParamsV2 p{};
-    p.c0_chunks = d.c0 / 64;
+    p.c0_chunks = d.c0 / box_ch;
     p.N = d.N; p.H = d.H; p.W = d.W;
     p.n_stages = ctot / c.kcs;
     if (d.sched != c.sched) { set_error("conv3x3(tma): config %d runs schedule %d, not %d", cfg, c.sched, d.sched); return RRIN_ERR_BAD_ARG; }

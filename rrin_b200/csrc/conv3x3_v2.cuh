@@ -51,7 +51,7 @@ struct FuseParams {
 };
 
 struct ConvParamsV2 {
-    int c0_chunks;               // 64-channel chunks taken from tensor map 0 (the rest from map 1: cat)
+    int c0_chunks;               // box-wide (64-channel; 32 for KCS = 32) chunks taken from tensor map 0 (the rest from map 1: cat)
     int N, H, W;                 // conv grid
     int n_stages;                // 64-channel-chunk groups per tile (KCS channels each)
     const __nv_bfloat16* wpack;  // [n_ntiles][n_stages][n_ent][KB/8][NT][8]
@@ -93,9 +93,11 @@ constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32
 //        warps interpolate it into the swizzled halo tile (shared-memory reads instead of global-load latency).
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0>
 struct ConvCfgV2 {
-    static constexpr int BOXES = KCS / 64;             // TMA boxes (64-channel chunks) per stage
+    static constexpr int BOXES = 1;                    // TMA boxes per stage
+    static constexpr int BOX_CH = KCS;                 // channels per box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte, SWIZZLE_64B)
+    static constexpr int ROWB = BOX_CH * 2;            // bytes per pixel row of a box
     static constexpr int PW = 8 * MSUB + 2;            // halo row pitch in pixels
-    static constexpr int BOX_BYTES = (kTileH + 2) * PW * 128;
+    static constexpr int BOX_BYTES = (kTileH + 2) * PW * ROWB;
     static constexpr int BOX_STRIDE = (BOX_BYTES + 1023) / 1024 * 1024;
     static constexpr int A_STAGE = BOXES * BOX_STRIDE;
     static constexpr int B_BLOCK = NT * KB * 2 / CG;   // bytes of a weight block held by ONE CTA
@@ -120,10 +122,10 @@ struct ConvCfgV2 {
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
     static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS;
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
-    static_assert(KCS == 64, "one 64-channel TMA box per stage");
+    static_assert(KCS == 64 || (KCS == 32 && SCHED == 0 && CG == 1 && !XF), "one 64-channel TMA box per stage (32: a 32-channel NHWC source)");
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
     static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
-    static_assert((SCHED == 0 && KB == 64) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
+    static_assert((SCHED == 0 && KB == KCS) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
     static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32 && SLOTS % EW == 0, "accumulator slots");
     static_assert(!RES || SB % N_ENT == 0, "resident weights: SB counts whole stages of blocks");
     // half entry? (parity, e) -> 0 full | 1 lower columns [0,64) (a = 0) | 2 upper columns [64,128) (a = 1)
@@ -141,7 +143,7 @@ struct ConvCfgV2 {
     __host__ __device__ static constexpr int us(int i) { return (i + 1) / 2 - 1; }     // {-1, 0, 0, 1}
     __host__ __device__ static constexpr int ps(int i) { return (i + 1) & 1; }         // { 1, 0, 1, 0}
     __host__ __device__ static constexpr uint32_t ent_off(int parity, int e) {
-        if (SCHED == 0) return ((e / 3) * PW + (e % 3)) * 8;
+        if (SCHED == 0) return ((e / 3) * PW + (e % 3)) * (ROWB / 16);
         if (SCHED == 1) return ((us(e >> 2) + 1) * PW + (us(e & 3) + 1)) * 8 + (ps(e >> 2) * 2 + ps(e & 3)) * (KB * 2 / 16);
         return (((parity == 0 ? (e >> 2) : (e >> 2) - 1) + 1) * PW + (us(e & 3) + 1)) * 8 + ps(e & 3) * (KB * 2 / 16);
     }
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                         leader_bar(a_full(stage)));
                     } else {
                         mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
-                        tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * 64, x0, y0, t.n, a_full(stage));
+                        tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * C::BOX_CH, x0, y0, t.n, a_full(stage));
                     }
                 }
             }
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
         if (cta_rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128 * CG, NT), idesc_h = make_idesc_bf16(128, 64);
             constexpr int NB = NT / CG;                 // weight-block rows (N) held per CTA
-            const uint64_t a_desc0 = make_smem_desc_sw128(0, C::PW * 128);
+            const uint64_t a_desc0 = (KCS == 32) ? make_smem_desc_sw64(0, C::PW * 64) : make_smem_desc_sw128(0, C::PW * 128);
             const uint64_t b_desc0 = make_smem_desc(0, NB * 16, 128), b_desc0h = make_smem_desc(0, 64 * 16, 128);
             auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t id, uint32_t acc) {
                 if (CG == 2) umma_bf16_lh_cg2(d, alo, ahi, blo, bhi, id, acc); else umma_bf16_lh(d, alo, ahi, blo, bhi, id, acc);
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
 #pragma unroll
                         for (int s = 0; s < KB / 16; ++s)
                             if (!(p.dbg & 16) || (e | s) == 0)                 // diagnostics: one MMA per (stage, sub-tile) only
-                                mma(tmem_base + ts * NT + dcol, a_e + j * 64 + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
+                                mma(tmem_base + ts * NT + dcol, a_e + j * (C::ROWB / 2) + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
                                     (e | s) != 0 || !first_stage);
                     }
                     const long long cm1 = prof ? clock64() : 0;

@@ -77,6 +77,12 @@ static int up_cfg() {
     return (e && atoi(e) == 5) ? 5 : 20;
 }
 
+// level-1 block.0 conv on the pooled 32-channel level-0 tensor: TMA config 21 (RRIN_POOL1_CFG=3: the cp.async-fed v1 kernel)
+static int pool1_cfg() {
+    static const int c = getenv("RRIN_POOL1_CFG") ? atoi(getenv("RRIN_POOL1_CFG")) : 21;
+    return c == 3 ? 3 : 21;
+}
+
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
@@ -102,7 +108,7 @@ static Schedule build_schedule() {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
             // K_POOL sources are read from the pooled copy the previous level's block.2 epilogue wrote: plain convs
             if (level == 1) {
-                if (src == K_POOL) { m.cfg = 3; m.n_stages = 1; }                // 32 channels: cp.async producers (KCS = 32)
+                if (src == K_POOL) { m.cfg = pool1_cfg(); m.n_stages = 1; }      // 32 stored channels: 64-byte TMA rows (config 21)
                 else { m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
             } else {
                 m.cfg = (src == K_UP) ? up_cfg() : big_cfg(); m.n_stages = cin / 64;

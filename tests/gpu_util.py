@@ -16,7 +16,7 @@ PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8, PACK_NORMAL_CG2 = 0, 1, 2, 3, 4
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
-T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP = range(10, 21)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP, T_POOL32 = range(10, 22)
 
 
 def stream():

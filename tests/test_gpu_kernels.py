@@ -66,6 +66,10 @@ NORMAL_CASES = [
     ("tma_many_tiles_l3_ntiles", 16, "plain", 256, 256, True, 2, 100, 72),
     ("tma_direct_l2_cat", 17, "cat", 128, 128, True, 1, 12, 20),
     ("tma_msub3_many_tiles", 18, "plain", 64, 128, False, 1, 120, 200),
+    # 32 stored channels (pooled level-0 tensor): 64-byte TMA rows, SWIZZLE_64B descriptors
+    ("tma_pool32_small", 21, "plain", 32, 64, True, 1, 24, 40),
+    ("tma_pool32_partial_n2", 21, "plain", 32, 64, False, 2, 36, 52),
+    ("tma_pool32_many_tiles", 21, "plain", 32, 64, True, 1, 184, 328),
     # exact bilinear x2 source: TMA-staged coarse tile + transform warps
     ("tma_up_l2", 20, "up", 256, 128, False, 1, 16, 16),
     ("tma_up_l3_ntiles", 20, "up", 512, 256, False, 1, 12, 20),
