@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         tmem_ld16(t0 + c, ra);
                         tmem_ld16(t0 + c + 16, rb);
                         tmem_ld_wait();
+                        if (EARLY && c == NT - 32) { release_slot(); released = true; }
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
