@@ -479,26 +479,38 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 mbar_wait(raw_full(rs), (it / C::RAW_SLOTS) & 1);
                 mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
                 const uint32_t raw = s_base + C::OFF_RAW + rs * C::RAW_STRIDE, dst = s_a + stage * C::A_STAGE;
-#pragma unroll 2
-                for (int q = px0; q < (kTileH + 2) * C::PW; q += 16) {
-                    const int hy = q / C::PW, hx = q - hy * C::PW;
-                    const int gy = y0 + hy, gx = x0 + hx;
-                    uint4 o = make_uint4(0, 0, 0, 0);                          // outside the fine image: the conv's zero padding
-                    if ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
-                        int iy0, iy1, ix0, ix1; float wy, wx;
-                        up2_taps(gy, sh, iy0, iy1, wy);
-                        up2_taps(gx, sw, ix0, ix1, wx);
-                        const int r00 = (iy0 - cy0) * C::RAW_W + (ix0 - cx0), r01 = (iy0 - cy0) * C::RAW_W + (ix1 - cx0);
-                        const int r10 = (iy1 - cy0) * C::RAW_W + (ix0 - cx0), r11 = (iy1 - cy0) * C::RAW_W + (ix1 - cx0);
-                        auto lds = [&](int r) {
-                            uint4 v;
-                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                                         : "r"(raw + r * 128 + ((c8 ^ (r & 7)) << 4)));
-                            return v;
-                        };
-                        o = bilerp_bf16x8(lds(r00), lds(r01), lds(r10), lds(r11), wx, wy);
+                // One item = a 2x2 cell of fine halo pixels x one 16-byte channel chunk.  The halo origin is odd, so the cell
+                // rows are fine rows (2y+1, 2y+2): both interpolate coarse rows (y, y+1) -- 4 shared-memory loads serve 4
+                // outputs.  (Shared-memory bandwidth is what the MMAs run out of; per-pixel taps cost 4x the loads.)
+                // Indices are clamped like ATen's (i1 = i0 + (i0 < size-1), src < 0 -> 0); the weights come from up2_taps,
+                // so every output is bit-identical to the per-pixel formulation (a clamped-away tap has weight 0).
+                constexpr int CXN = C::PW / 2, CELLS = ((kTileH + 2) / 2) * CXN;
+#pragma unroll 1
+                for (int cell = px0; cell < CELLS; cell += 16) {
+                    const int cyl = cell / CXN, cxl = cell - cyl * CXN;
+                    const int ra = min(max(cy0 + cyl, 0), sh - 1) - cy0, rb = min(max(cy0 + cyl + 1, 0), sh - 1) - cy0;
+                    const int ca = min(max(cx0 + cxl, 0), sw - 1) - cx0, cb = min(max(cx0 + cxl + 1, 0), sw - 1) - cx0;
+                    auto lds = [&](int r) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                     : "r"(raw + r * 128 + ((c8 ^ (r & 7)) << 4)));
+                        return v;
+                    };
+                    const uint4 v00 = lds(ra * C::RAW_W + ca), v01 = lds(ra * C::RAW_W + cb);
+                    const uint4 v10 = lds(rb * C::RAW_W + ca), v11 = lds(rb * C::RAW_W + cb);
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int hy = 2 * cyl + (d >> 1), hx = 2 * cxl + (d & 1), q = hy * C::PW + hx;
+                        const int gy = y0 + hy, gx = x0 + hx;
+                        uint4 o = make_uint4(0, 0, 0, 0);                      // outside the fine image: the conv's zero padding
+                        if ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
+                            int i0, i1; float wy, wx;
+                            up2_taps(gy, sh, i0, i1, wy);
+                            up2_taps(gx, sw, i0, i1, wx);
+                            o = bilerp_bf16x8(v00, v01, v10, v11, wx, wy);
+                        }
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128 + ((c8 ^ (q & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128 + ((c8 ^ (q & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                 }
                 fence_proxy_async_smem();               // generic-proxy writes -> visible to the tensor core's operand reads
                 mbar_arrive(a_full(stage));
