@@ -162,6 +162,10 @@ struct TileWalkV2 {
         rank = cta_rank;
         u = (int)((long long)p.total_units * wid / nw);
         u_end = (int)((long long)p.total_units * (wid + 1) / nw);
+        if (cg == 2) {                           // pairs: even range boundaries (see next())
+            u &= ~1;
+            if (wid + 1 < nw) u_end &= ~1;
+        }
         nt = u / p.units_per_nt;
         int r = u - nt * p.units_per_nt;
         const int band = r / p.sx;
@@ -179,7 +183,8 @@ struct TileWalkV2 {
         // remainder tile would stream a full set of weight blocks for a quarter of the MMAs
         const int run = min(p.sx - sx0, u_end - u);
         const int nt_run = (run + CG * MSUB - 1) / (CG * MSUB);
-        const int mt = (run + nt_run - 1) / nt_run;
+        int mt = (run + nt_run - 1) / nt_run;
+        if (CG == 2) mt = min((mt + 1) & ~1, run);     // pairs: even tiles -- an odd one computes a sub-tile twice (M = 256)
         t.m = (mt + CG - 1) / CG;
         t.sx0 = sx0 + rank * t.m;
         u += mt;
