@@ -23,8 +23,12 @@ for i in "$@"; do
   ncu --set full --clock-control none --import-source on -k regex:conv3x3 -s $((nconv + i)) -c 1 \
       -o gpurun_out/${tag}_conv${i} -f python tools/profile_step.py 1088 1920 1 > gpurun_out/${tag}_ncu_conv${i}.log 2>&1
 done
-for g in warp_pack blend_pack; do
-  ncu --set full --clock-control none --import-source on -k regex:${g} -s 1 -c 1 \
-      -o gpurun_out/${tag}_${g} -f python tools/profile_step.py 1088 1920 1 > gpurun_out/${tag}_ncu_${g}.log 2>&1
-done
+# gpurun brings back at most 64 MiB: summarise the captures here and keep only the text (KEEP_REPS=1 keeps the reports)
+reps=$(ls gpurun_out/${tag}_conv*.ncu-rep 2>/dev/null)
+if [ -n "$reps" ]; then
+  python tools/ncu_summary.py rep $reps > gpurun_out/${tag}_ncu_full_summary.txt 2>&1
+  python tools/traffic_json.py ${tag} ${BATCH:-4} gpurun_out/${tag}_traffic.json > /dev/null 2>&1
+  python tools/ncu_summary.py launches gpurun_out/${tag}_launches.csv 91 > gpurun_out/${tag}_launches_summary.csv 2>&1
+  [ "${KEEP_REPS:-0}" = "1" ] || rm -f gpurun_out/${tag}_conv*.ncu-rep
+fi
 ls -la gpurun_out | tail -20

@@ -1,7 +1,8 @@
 """profiles/traffic.json from `ncu --set full` captures: DRAM bytes (read + write) of one representative launch per
 kernel class, next to that launch's algorithmic bytes.  bench.py copies the dominant class's figure into `roofline.traffic`.
 
-  python tools/traffic_json.py <tag> <batch>      (reads gpurun_out/<tag>_conv<i>.ncu-rep, writes profiles/traffic.json)
+  python tools/traffic_json.py <tag> <batch> [out.json]     (reads gpurun_out/<tag>_conv<i>.ncu-rep; default output
+                                                             profiles/traffic.json)
 
 Launch index i -> (class name as bench.py prints it, layer): fixed by the engine's schedule (tools/step_table.py -v)."""
 import csv
@@ -17,6 +18,7 @@ P = 1088 * 1920
 LAUNCHES = {
     5: ("conv3x3_tma<KCS64,KB64,NT128,MSUB3>", "Flow.down_path.2.block.2 (128->128, level 2)", (128 + 128) * 2 * P / 16, 9 * 128 * 128 * 2),
     12: ("conv3x3_tma<KCS64,KB64,NT128,MSUB3> (cat)", "Flow.up_path.0.conv_block.block.0 (cat 256+256->256, level 3)", (512 + 256) * 2 * P / 64, 9 * 512 * 256 * 2),
+    2: ("conv3x3_tma<KCS32,KB32,NT64,MSUB4>", "Flow.down_path.1.block.0 (pooled 32->64, level 1)", (32 + 64) * 2 * P / 4, 9 * 32 * 64 * 2),
     1: ("conv3x3_tma<KCS64,KB32,NT128,MSUB1>", "Flow.down_path.0.block.2 (32->32, level 0, + pooled output)", (32 + 32 + 8) * 2 * P, 96 * 1024),
     3: ("conv3x3_tma<KCS64,KB64,NT64,MSUB2>", "Flow.down_path.1.block.2 (64->64, level 1, + pooled output)", (64 + 64 + 16) * 2 * P / 4, 9 * 64 * 64 * 2),
     23: ("conv3x3_tma<KCS64,KB32,NT128,MSUB3>", "Flow.up_path.3.conv_block.block.0 (cat 32+32->32, level 0)", (64 + 32) * 2 * P, 192 * 1024),
@@ -51,7 +53,8 @@ def main():
         alg = act * batch + wts
         res[cls] = {"traffic": int(tr), "algorithmic": int(alg), "ratio": round(tr / alg, 3), "launch": layer,
                     "dram_read": int(m["dram__bytes_read.sum"]), "dram_write": int(m["dram__bytes_write.sum"])}
-    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+    out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "traffic.json")
+    with open(out, "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res, indent=1))
 
