@@ -613,13 +613,9 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                     else { pacc[2 * i] = (pacc[2 * i] + a.x) + b.x; pacc[2 * i + 1] = (pacc[2 * i + 1] + a.y) + b.y; }
                                 }
                                 if (c == NT - 64 && ok) {
-                                    uint4* d4 = reinterpret_cast<uint4*>(p.pool_out + pix * (size_t)(NT / 4));
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        d4[k] = make_uint4(pack_bf16x2(pacc[8 * k] * 0.25f, pacc[8 * k + 1] * 0.25f),
-                                                           pack_bf16x2(pacc[8 * k + 2] * 0.25f, pacc[8 * k + 3] * 0.25f),
-                                                           pack_bf16x2(pacc[8 * k + 4] * 0.25f, pacc[8 * k + 5] * 0.25f),
-                                                           pack_bf16x2(pacc[8 * k + 6] * 0.25f, pacc[8 * k + 7] * 0.25f));
+                                    __nv_bfloat16* d = p.pool_out + pix * (size_t)(NT / 4);        // 64 bytes per pooled pixel
+                                    stg256_bf16x16(d, pacc, 0.25f);
+                                    stg256_bf16x16(d + 16, pacc + 16, 0.25f);
                                 }
                             } else {
                                 // 2x2 mean over this warp's 4 x 8 pixels from the staged bf16 tile: lane -> pooled pixel
@@ -645,14 +641,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                 }
                                 const int py = (t.ty * kTileH + 4 * quad) / 2 + pyl, px = (t.sx0 + j) * 4 + pxl;
                                 if (py < (p.H >> 1) && px < (p.W >> 1)) {
-                                    uint4* d4 = reinterpret_cast<uint4*>(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride +
-                                                                         t.nt * NT + c + 16 * q);
-#pragma unroll
-                                    for (int k = 0; k < 2; ++k)
-                                        d4[k] = make_uint4(pack_bf16x2(acc[8 * k] * 0.25f, acc[8 * k + 1] * 0.25f),
-                                                           pack_bf16x2(acc[8 * k + 2] * 0.25f, acc[8 * k + 3] * 0.25f),
-                                                           pack_bf16x2(acc[8 * k + 4] * 0.25f, acc[8 * k + 5] * 0.25f),
-                                                           pack_bf16x2(acc[8 * k + 6] * 0.25f, acc[8 * k + 7] * 0.25f));
+                                    stg256_bf16x16(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride + t.nt * NT + c + 16 * q,
+                                                   acc, 0.25f);
                                 }
                             }
                         }
@@ -673,8 +663,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         const long q = (long)gy * p.W + gx;
                         if (fz.mode == 0 || fz.mode == 1) {
                             float4* o4 = reinterpret_cast<float4*>(p.out) + pix * 4;
-#pragma unroll
-                            for (int ph = 0; ph < 4; ++ph) o4[ph] = v[ph];
+                            stg256(o4, v[0], v[1]);
+                            stg256(o4 + 2, v[2], v[3]);
                         }
                         if (fz.mode == 1) {              // t.n = pair; every sample of that pair gets its refine_flow head input
                             const int s0 = fz.pair_mul ? t.n : 0, s1 = fz.pair_mul ? t.n + 1 : fz.Nt;
@@ -734,11 +724,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                             } else {
                                 op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout_stride + t.nt * NT + c;
                             }
-                            uint4* o4 = reinterpret_cast<uint4*>(op);
-                            o4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                            o4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                            o4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-                            o4[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                            stg256(op, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                            stg256(op + 16, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
                         }
                     }
                 }

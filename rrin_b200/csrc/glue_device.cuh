@@ -6,10 +6,23 @@
 
 namespace rrin {
 
+// One 256-bit store (sm_100: STG.256): a thread's 32 bytes fill a whole sector, where two 16-byte stores from different
+// instructions reach L2 as two half-sector writes.  dst must be 32-byte aligned.
+__device__ __forceinline__ void stg256(void* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+__device__ __forceinline__ void stg256(void* dst, const float4& a, const float4& b) {
+    stg256(dst, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w),
+           __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+}
+__device__ __forceinline__ void stg256_bf16x16(void* dst, const float* v, float scale) {       // 16 floats * scale -> 16 bf16
+    stg256(dst, pack_bf16x2(v[0] * scale, v[1] * scale), pack_bf16x2(v[2] * scale, v[3] * scale), pack_bf16x2(v[4] * scale, v[5] * scale),
+           pack_bf16x2(v[6] * scale, v[7] * scale), pack_bf16x2(v[8] * scale, v[9] * scale), pack_bf16x2(v[10] * scale, v[11] * scale),
+           pack_bf16x2(v[12] * scale, v[13] * scale), pack_bf16x2(v[14] * scale, v[15] * scale));
+}
 __device__ __forceinline__ void store_bf16x16(void* dst, const float (&v)[16]) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    d[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    d[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+    stg256(dst, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
+           pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
 
 // 2x2 block of a 3-channel fp32 NCHW frame: f[c][phase]
@@ -100,8 +113,8 @@ __device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const f
         float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph],
                        xt1[0], xt1[1], xt1[2], xt2[0], xt2[1], xt2[2]};                          // model.py:50
         store_bf16x16(m16 + ph * 16, v);
-        xt8[ph * 2] = make_float4(xt1[0], xt1[1], xt1[2], xt2[0]);
-        xt8[ph * 2 + 1] = make_float4(xt2[1], xt2[2], 0.f, 0.f);
+        stg256(xt8 + ph * 2, __float_as_uint(xt1[0]), __float_as_uint(xt1[1]), __float_as_uint(xt1[2]), __float_as_uint(xt2[0]),
+               __float_as_uint(xt2[1]), __float_as_uint(xt2[2]), 0u, 0u);
     }
 }
 
@@ -110,6 +123,7 @@ __device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const fl
                                                  const float* __restrict__ i1, float omt, float t, long HW, int W, int by, int bx,
                                                  float4* __restrict__ out4, __nv_bfloat16* __restrict__ f16) {
     float a[3][4], b[3][4];
+    float4 ob[4];
     load_block3(i0, HW, W, by, bx, a);
     load_block3(i1, HW, W, by, bx, b);
 #pragma unroll
@@ -121,10 +135,12 @@ __device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const fl
         const float o0 = (w1 * ta.x + w2 * ta.w) / den;                                        // model.py:55
         const float o1 = (w1 * ta.y + w2 * tb.x) / den;
         const float o2 = (w1 * ta.z + w2 * tb.y) / den;
-        out4[ph] = make_float4(o0, o1, o2, 0.f);
+        ob[ph] = make_float4(o0, o1, o2, 0.f);
         float v[16] = {a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], o0, o1, o2, 0, 0, 0, 0, 0, 0, 0};   // model.py:61
         store_bf16x16(f16 + ph * 16, v);
     }
+    stg256(out4, ob[0], ob[1]);
+    stg256(out4 + 2, ob[2], ob[3]);
 }
 
 // ---- K5: final residue + clamp (model.py:62-63) -> the block pixel's 2x2 pixels of the fp32 NCHW result
