@@ -334,6 +334,9 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     p.pool_out = reinterpret_cast<__nv_bfloat16*>(d.pool_out);
     if (d.fuse.mode) {
         if (d.epi != EPI_F32X16 || d.fuse.mode < 1 || d.fuse.mode > 4 || d.fuse.H != 2 * d.H || d.fuse.W != 2 * d.W) { set_error("conv3x3(tma): bad fused glue request"); return RRIN_ERR_BAD_ARG; }
+        if ((reinterpret_cast<uintptr_t>(d.fuse.h16) | reinterpret_cast<uintptr_t>(d.fuse.aux) | (d.fuse.mode == 4 ? 0 : reinterpret_cast<uintptr_t>(d.fuse.dst))) & 31) {
+            set_error("conv3x3(tma): fused glue tensors must be 32-byte aligned"); return RRIN_ERR_BAD_ARG;
+        }
         p.fz.mode = d.fuse.mode; p.fz.H = d.fuse.H; p.fz.W = d.fuse.W; p.fz.Nt = d.fuse.Nt; p.fz.pair_mul = d.fuse.pair_mul;
         p.fz.in0 = d.fuse.in0; p.fz.in1 = d.fuse.in1; p.fz.coef = d.fuse.coef;
         p.fz.aux = reinterpret_cast<const float4*>(d.fuse.aux); p.fz.h16 = reinterpret_cast<__nv_bfloat16*>(d.fuse.h16); p.fz.dst = d.fuse.dst;
@@ -345,6 +348,9 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     if (d.epi == EPI_F32X16 && c.nt != 16) { set_error("conv3x3: fp32 epilogue needs NT=16"); return RRIN_ERR_BAD_ARG; }
     if (d.epi == EPI_SCATTER && (d.cout_stride % 32 || d.n_cols != 4 * d.cout_stride)) { set_error("conv3x3: bad scatter epilogue shape"); return RRIN_ERR_BAD_SHAPE; }
     if (d.epi == EPI_BF16 && d.cout_stride < d.n_cols) { set_error("conv3x3: cout_stride %d < columns %d", d.cout_stride, d.n_cols); return RRIN_ERR_BAD_SHAPE; }
+    if (((reinterpret_cast<uintptr_t>(d.out) | reinterpret_cast<uintptr_t>(d.pool_out)) & 31) || (d.epi == EPI_BF16 && d.cout_stride % 16)) {
+        set_error("conv3x3(tma): outputs must be 32-byte aligned with a multiple of 16 channels per pixel (256-bit stores)"); return RRIN_ERR_BAD_ARG;
+    }
     p.tiles_y = (d.H + kTileH - 1) / kTileH;
     p.sx = (d.W + 7) / 8;
     const long upn = (long)d.N * p.tiles_y * p.sx, total = upn * p.n_ntiles;

@@ -10,6 +10,7 @@
 // pixel (2y+a, 2x+b)): head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs (flow, residues, mask
 // logits) fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8] = [xt1(3), xt2(3), 0, 0].
 // One thread handles one block pixel (4 pixels): 8-byte frame loads, 32/64/128-byte stores.
+#include <initializer_list>
 #include "common.cuh"
 #include "glue_device.cuh"
 #include "rrin_internal.h"
@@ -152,9 +153,16 @@ static int check_dims(const char* who, int N, int H, int W) {
     return RRIN_OK;
 }
 static inline long nblocks(int N, int H, int W) { return (long)N * (H / 2) * (W / 2); }
+// packed outputs are written with 256-bit stores
+static int check_align32(const char* who, std::initializer_list<const void*> ptrs) {
+    for (const void* p : ptrs)
+        if (p && (reinterpret_cast<uintptr_t>(p) & 31)) { set_error("%s: packed tensors must be 32-byte aligned", who); return RRIN_ERR_BAD_ARG; }
+    return RRIN_OK;
+}
 
 int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s) {
     if (int e = check_dims("pack_pair", N, H, W)) return e;
+    if (int e = check_align32("pack_pair", {x16})) return e;
     RRIN_CUDA_CHECK(launch_pdl(pack_pair_kernel, glue_grid(nblocks(N, H, W)), kGlueThreads, 0, s, 1, in0, in1, N, H, W, reinterpret_cast<__nv_bfloat16*>(x16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
@@ -162,6 +170,7 @@ int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16
 int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, const float* coef, int Nt, int pair_mul,
                      int H, int W, void* r16, cudaStream_t s) {
     if (int e = check_dims("flow_tscale_pack", Nt, H, W)) return e;
+    if (int e = check_align32("flow_tscale_pack", {r16, flow4})) return e;
     RRIN_CUDA_CHECK(launch_pdl(flow_tscale_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(flow4), in0, in1, coef, Nt,
                                                                                  pair_mul, H, W, reinterpret_cast<__nv_bfloat16*>(r16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
@@ -170,6 +179,7 @@ int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, con
 int warp_pack(const float* flow4, const float* res4, const float* in0, const float* in1, const float* coef, int Nt,
               int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s) {
     if (int e = check_dims("warp_pack", Nt, H, W)) return e;
+    if (int e = check_align32("warp_pack", {m16, xt8, flow4, res4})) return e;
     RRIN_CUDA_CHECK(launch_pdl(warp_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1,
         reinterpret_cast<const float4*>(flow4), reinterpret_cast<const float4*>(res4), in0, in1, coef, Nt, pair_mul, H, W,
         reinterpret_cast<__nv_bfloat16*>(m16), reinterpret_cast<float4*>(xt8)));
@@ -179,6 +189,7 @@ int warp_pack(const float* flow4, const float* res4, const float* in0, const flo
 int blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef, int Nt,
                int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s) {
     if (int e = check_dims("blend_pack", Nt, H, W)) return e;
+    if (int e = check_align32("blend_pack", {f16, out4, mask4, xt8})) return e;
     RRIN_CUDA_CHECK(launch_pdl(blend_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
                                                                            in0, in1, coef, Nt, pair_mul, H, W, reinterpret_cast<float4*>(out4),
                                                                            reinterpret_cast<__nv_bfloat16*>(f16)));
