@@ -119,9 +119,29 @@ __global__ void __launch_bounds__(kGlueThreads) residue_clamp_kernel(const float
 // K8 = transforms.Pad((0, top_pad, 0, right_pad), 'edge') + ToTensor() + drop alpha (dataloader.py:93-118): uint8 HWC
 // [H0,W0,C] -> fp32 NCHW [3,H,W0] with H = top + H0 + bottom; padded rows replicate the first / last image row.
 // (torchvision's Pad order is (left, top, right, bottom): the reference's "right_pad" lands on the BOTTOM.)
+template <int VEC>
 __global__ void __launch_bounds__(kGlueThreads) frame_from_u8_kernel(const uint8_t* __restrict__ src, int H0, int W0, int C, int top,
                                                                       int H, float* __restrict__ dst) {
     const long total = (long)H * W0;
+    if (VEC == 4) {
+        // 4 pixels per thread: 12 (RGB) or 16 (RGBA) source bytes as 32-bit words, one float4 per plane (W0 % 4 == 0, aligned bases)
+        const long groups = total / 4;
+        const int Wg = W0 / 4;
+        for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+            const int y = (int)(g / Wg), x = (int)(g - (long)y * Wg) * 4;
+            const int sy = min(max(y - top, 0), H0 - 1);
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(src + ((long)sy * W0 + x) * C);
+            uint8_t b[16];
+            if (C == 3) { const uint32_t w0 = p[0], w1 = p[1], w2 = p[2]; memcpy(b, &w0, 4); memcpy(b + 4, &w1, 4); memcpy(b + 8, &w2, 4); }
+            else { const uint4 w = *reinterpret_cast<const uint4*>(p); memcpy(b, &w, 16); }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                *reinterpret_cast<float4*>(dst + (long)c * total + (long)y * W0 + x) =
+                    make_float4(__fdiv_rn((float)b[c], 255.f), __fdiv_rn((float)b[C + c], 255.f), __fdiv_rn((float)b[2 * C + c], 255.f),
+                                __fdiv_rn((float)b[3 * C + c], 255.f));                          // ToTensor: byte -> float, div(255)
+        }
+        return;
+    }
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
         const int sy = min(max(y - top, 0), H0 - 1);
@@ -132,10 +152,32 @@ __global__ void __launch_bounds__(kGlueThreads) frame_from_u8_kernel(const uint8
 }
 // K9 = to_pil_image (pic.mul(255).byte(): truncation) + crop((0, H - H0, W0, H)) (utils.py:51-58): fp32 NCHW [3,H,W] ->
 // uint8 HWC [H0,W0,3], dropping the top H - H0 rows.
+template <int VEC>
 __global__ void __launch_bounds__(kGlueThreads) frame_to_u8_kernel(const float* __restrict__ src, int H, int W, int H0, int W0,
                                                                     uint8_t* __restrict__ dst) {
     const long total = (long)H0 * W0, plane = (long)H * W;
     const int crop = H - H0;
+    if (VEC == 4) {
+        // 4 pixels per thread: one float4 per plane in, 12 bytes out as three 32-bit words (W, W0 % 4 == 0, aligned bases)
+        const long groups = total / 4;
+        const int Wg = W0 / 4;
+        for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+            const int y = (int)(g / Wg), x = (int)(g - (long)y * Wg) * 4;
+            const float* p = src + (long)(y + crop) * W + x;
+            uint8_t b[12];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(p + c * plane);
+                b[c] = (uint8_t)(int)__fmul_rn(v.x, 255.f); b[3 + c] = (uint8_t)(int)__fmul_rn(v.y, 255.f);
+                b[6 + c] = (uint8_t)(int)__fmul_rn(v.z, 255.f); b[9 + c] = (uint8_t)(int)__fmul_rn(v.w, 255.f);
+            }
+            uint32_t w[3];
+            memcpy(w, b, 12);
+            uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((long)y * W0 + x) * 3);
+            d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
+        }
+        return;
+    }
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
         const float* p = src + (long)(y + crop) * W + x;
@@ -199,13 +241,19 @@ int blend_pack(const float* mask4, const float* xt8, const float* in0, const flo
 int frame_from_u8(const uint8_t* src, int H0, int W0, int C, int top, int bottom, float* dst, cudaStream_t s) {
     if (!src || !dst || H0 <= 0 || W0 <= 0 || (C != 3 && C != 4) || top < 0 || bottom < 0) { set_error("frame_from_u8: bad argument"); return RRIN_ERR_BAD_ARG; }
     const int H = top + H0 + bottom;
-    frame_from_u8_kernel<<<glue_grid((long)H * W0), kGlueThreads, 0, s>>>(src, H0, W0, C, top, H, dst);
+    if (W0 % 4 == 0 && !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15))
+        frame_from_u8_kernel<4><<<glue_grid((long)H * W0 / 4), kGlueThreads, 0, s>>>(src, H0, W0, C, top, H, dst);
+    else
+        frame_from_u8_kernel<1><<<glue_grid((long)H * W0), kGlueThreads, 0, s>>>(src, H0, W0, C, top, H, dst);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
 int frame_to_u8(const float* src, int H, int W, int H0, int W0, uint8_t* dst, cudaStream_t s) {
     if (!src || !dst || H0 <= 0 || W0 <= 0 || H0 > H || W0 > W) { set_error("frame_to_u8: bad argument"); return RRIN_ERR_BAD_ARG; }
-    frame_to_u8_kernel<<<glue_grid((long)H0 * W0), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
+    if (W0 % 4 == 0 && W % 4 == 0 && !((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15))
+        frame_to_u8_kernel<4><<<glue_grid((long)H0 * W0 / 4), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
+    else
+        frame_to_u8_kernel<1><<<glue_grid((long)H0 * W0), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }

@@ -265,7 +265,7 @@ def test_uint8_frame_io_matches_torchvision_semantics():
     l = lib()
     s = torch.cuda.current_stream().cuda_stream
     g = torch.Generator().manual_seed(3)
-    for (h0, w0, c) in [(40, 32, 3), (1080, 1920, 4), (50, 112, 3)]:
+    for (h0, w0, c) in [(40, 32, 3), (1080, 1920, 4), (50, 112, 3), (46, 50, 4), (30, 18, 3)]:      # last two: scalar path (W % 4 != 0)
         img = torch.randint(0, 256, (h0, w0, c), dtype=torch.uint8, generator=g)
         top, bottom = rio.pad_amounts(h0, w0)
         h = h0 + top + bottom
