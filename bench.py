@@ -322,13 +322,12 @@ def run_gpu(args):
     if rank == 0:
         eng = net._engines[next(iter(net._engines))]
         w = net._weights(dev)
-        # per-launch device times (CUDA events on the launching stream), 3 profiled forwards
+        # per-launch device times (CUDA events on the launching stream): per-launch median over 5 profiled forwards
+        # (a mean lets one stall -- a clock dip under the power cap -- land on whichever launch it hit)
         table = eng.launch_table()
-        acc = [0.0] * len(table)
-        reps = 3
-        for r in range(reps):
-            for i, v in enumerate(eng.profile(w, *batch(r), 0.5)):
-                acc[i] += v / reps
+        reps = 5
+        samples = [eng.profile(w, *batch(r), 0.5) for r in range(reps)]
+        acc = [statistics.median(s[i] for s in samples) for i in range(len(table))]
         classes = {}
         for (name, layer, fl, by), t in zip(table, acc):
             c = classes.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})

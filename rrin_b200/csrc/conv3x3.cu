@@ -38,7 +38,7 @@ namespace rrin {
 // 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
 // 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
 // 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
-// 13 : < 64, 32,  16, 2, 3, 16, S2D8 , 1, 0, 2, 1>  level-0 `last` 32->{2,3,4}, fp32 output + fused glue (two epilogue groups: the warps gather)
+// 13 : < 64, 32,  16, 2, 2, 16, S2D8 , 1, 0, 2, 1>  level-0 `last` 32->{2,3,4}, fp32 output + fused glue (two epilogue groups: the warps gather)
 // 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1, 1>  level-1 64->64, weights resident
 // 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1, 1>  level-1 cat(64+64)->64
 // 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
@@ -55,7 +55,7 @@ namespace rrin {
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
     X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
     X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1, 0)  \
-    X(13, 64, 32, 16, 2, 3, 16, 2, 1, 0, 2, 1, 0)  \
+    X(13, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0)  \
     X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1, 0)   \
     X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1, 0)   \
     X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
