@@ -194,7 +194,6 @@ def run_library(args):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from oracle import rrin_oracle as O
     from rrin_b200 import Net
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,8 +207,10 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
-    # weights: random init of the reference architecture (torch.manual_seed(0)), loaded via state_dict
-    sd = O.seeded_state_dict()
+    # weights: random init of the reference architecture -- torch.manual_seed(0); Net() draws the same RNG stream as the
+    # reference's model.Net() (tests/test_oracle.py pins the sha256) -- loaded via state_dict like convert.py:100-104
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone().float() for k, v in Net().state_dict().items()}
     net = Net()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
@@ -369,6 +370,8 @@ def run_gpu(args):
                                     "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 1) if c["flops"] else 0,
                                     "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)} for n, c in classes.items()}}
         # CPU baseline: oracle port on a bounded strip of the same workload, this box's host cores
+        # (the only place the GPU arm touches oracle/)
+        from oracle import rrin_oracle as O
         threads = os.cpu_count() or 1
         sdc, a, b, strip_h = cpu_reference_throughput(15.0, threads)
         t0 = time.perf_counter(); O.forward(sdc, a, b, 0.5); dt = time.perf_counter() - t0

@@ -6,17 +6,18 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import rrin_oracle as O
 from rrin_b200 import Net
 
 h = int(sys.argv[1]) if len(sys.argv) > 1 else 1088
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
 reps = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 5
 nb = int(os.environ.get("BATCH", "1"))
-net = Net()
-net.load_state_dict(O.seeded_state_dict(), strict=True)
-net = net.cuda().eval()
-a, b = O.seeded_frames(1, h, w, seed=2, smooth=True)
+torch.manual_seed(0)
+net = Net().cuda().eval()          # random-init weights of the reference architecture
+g = torch.Generator().manual_seed(2)
+lo = torch.rand(1, 3, h // 8 + 2, w // 8 + 2, generator=g)          # smooth synthetic content, second frame shifted
+big = torch.nn.functional.interpolate(lo, size=(h + 16, w + 16), mode="bicubic", align_corners=False).clamp(0, 1)
+a, b = big[:, :, 8:8 + h, 8:8 + w].contiguous(), big[:, :, 5:5 + h, 3:3 + w].contiguous()
 a, b = a.cuda().expand(nb, -1, -1, -1).contiguous(), b.cuda().expand(nb, -1, -1, -1).contiguous()
 for _ in range(3):
     net(a, b, t=0.5)
