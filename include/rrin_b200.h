@@ -94,8 +94,10 @@ RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int wh
  *   sched 2  : half-phase schedule of the TMA-fed kernel for level-0 tensors (pack kind 3)
  *   pool_out : optional second output of the TMA-epilogue configs: F.avg_pool2d(out, 2) (unet.py:46) written by the
  *              same epilogue, bf16 NHWC [N,H/2,W/2,cout_stride] (space-to-depth grid: [N,H,W,cout_stride/4]); or NULL
- *   cfg      : tile configuration: 0..8 transform kernel (pool / bilinear sources, border strips), 10..18 TMA-fed kernel
- *              (rrin_conv_config_info gives KCS, KB, NT, MSUB). */
+ *   cfg      : tile configuration: 0..8 transform kernel (pool / bilinear sources, border strips), 10..21 TMA-fed kernel
+ *              (rrin_conv_config_info gives KCS, KB, NT, MSUB; 21 = 32 stored channels per pixel).
+ *   alignment: activation / output / pooled tensors 32-byte aligned (TMA maps and 256-bit stores); a misaligned
+ *              pointer is rejected with RRIN_ERR_BAD_ARG. */
 RRIN_API int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
 RRIN_API size_t rrin_conv_packed_weight_bytes(int cfg, int n_cols, int n_stages, int sched);
 RRIN_API int rrin_conv_packed_bias_count(int cfg, int n_cols);
@@ -106,7 +108,8 @@ RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, in
                  int act, int ring_only, int cfg, void* pool_out, void* stream);
 
 /* Glue kernels.  Frames are fp32 NCHW; tensors exchanged with the U-Nets are space-to-depth on the half-res
- * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8]. */
+ * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8].
+ * The packed tensors (x16, r16, m16, f16, flow4, res4, mask4, xt8, out4) must be 32-byte aligned (256-bit stores). */
 /* K6: torch.cat((x0,x1),1) (model.py:33) -> packed 16-channel bf16 NHWC head input. */
 RRIN_API int rrin_pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, void* stream);
 /* K2: flow t-scaling (model.py:37-39) + cat((F_t0,F_t1,x),1) (model.py:41) -> refine head input. */

@@ -111,6 +111,7 @@ struct ConvCfgV2 {
     static constexpr int RAW_STRIDE = (RAW_BYTES + 1023) / 1024 * 1024;
     static constexpr int RAW_SLOTS = XF ? 2 : 0;
     static_assert(!XF || (CG == 1 && SCHED == 0), "transform stage: single CTA, 9-tap schedule");
+    static_assert(!XF || ((8 * MSUB + 2) % 2 == 0 && (kTileH + 2) % 2 == 0), "transform stage works on 2x2 cells of the halo tile");
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
