@@ -51,6 +51,8 @@ namespace rrin {
 //                                                    tile + four transform warps
 // 21 : < 32, 32,  64, 4, 3,  9, TAPS9, 1, 1, 1, 1>     level-1 block.0 on the pooled 32-channel level-0 tensor: 64-byte pixel rows
 //                                                    (TMA SWIZZLE_64B boxes, 64-byte-swizzle A descriptors), weights resident
+// 22 : < 64, 64,  64, 4, 2,  8, TAPS9, 0, 1, 2, 2>     level 1 on CTA pairs (experimental, RRIN_L1_PAIR=1): M = 256, each CTA holds 32 of the 64
+//                                                    weight rows, so an MMA reads 4 KB (A) + 1 KB (B) per SM instead of 4 + 2
 #define RRIN_CONV2_CONFIGS(X)                   \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
     X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
@@ -63,7 +65,8 @@ namespace rrin {
     X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
     X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0) \
     X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1) \
-    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0)
+    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0) \
+    X(22, 64, 64, 64, 4, 2, 8, 0, 0, 1, 2, 2, 0)
 
 constexpr int kV2Base = 10;
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf; };

@@ -83,6 +83,12 @@ static int pool1_cfg() {
     return c == 3 ? 3 : 21;
 }
 
+// level-1 plain / cat convs on CTA pairs (config 22): experimental, RRIN_L1_PAIR=1
+static bool l1_pair() {
+    static const bool on = getenv("RRIN_L1_PAIR") && atoi(getenv("RRIN_L1_PAIR")) != 0;
+    return on;
+}
+
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
@@ -109,7 +115,10 @@ static Schedule build_schedule() {
             // K_POOL sources are read from the pooled copy the previous level's block.2 epilogue wrote: plain convs
             if (level == 1) {
                 if (src == K_POOL) { m.cfg = pool1_cfg(); m.n_stages = 1; }      // 32 stored channels: 64-byte TMA rows (config 21)
-                else { m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64; }
+                else {
+                    m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64;
+                    if (src != K_UP && l1_pair()) { m.cfg = 22; m.kind = PACK_NORMAL_CG2; }
+                }
             } else {
                 m.cfg = (src == K_UP) ? up_cfg() : big_cfg(); m.n_stages = cin / 64;
                 if (m.cfg == 19) m.kind = PACK_NORMAL_CG2;

@@ -16,7 +16,7 @@ PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8, PACK_NORMAL_CG2 = 0, 1, 2, 3, 4
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
-T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP, T_POOL32 = range(10, 22)
+T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP, T_POOL32, T_L1_PAIR = range(10, 23)
 
 
 def stream():
@@ -77,7 +77,7 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
     cout, cin = weight.shape[:2]
     c0 = src0.shape[-1] * (src0.shape[-2] if mode == SRC_POOL_S2D else 1)
     c1 = src1.shape[-1] if src1 is not None else 0
-    wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg == T_BIG_PAIR else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
+    wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg in (T_BIG_PAIR, T_L1_PAIR) else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if out is None:
         out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg, pool_out)

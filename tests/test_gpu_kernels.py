@@ -83,6 +83,10 @@ NORMAL_CASES = [
     ("pair_many_tiles_l3_ntiles", 19, "plain", 256, 256, True, 2, 100, 72),
     ("pair_odd_width", 19, "plain", 64, 128, False, 1, 120, 200),
     ("tma_direct_many_tiles_l3", 17, "plain", 256, 256, True, 1, 100, 72),
+    # level-1 CTA pairs (N = 64)
+    ("pair64_l1_plain", 22, "plain", 64, 64, True, 2, 24, 40),
+    ("pair64_l1_cat", 22, "cat", 64, 64, True, 1, 36, 52),
+    ("pair64_many_tiles", 22, "cat", 64, 64, False, 1, 200, 136),
 ]
 
 
