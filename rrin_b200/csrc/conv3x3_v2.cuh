@@ -2,8 +2,10 @@
 // tcgen05 tensor cores with BOTH operands delivered by the TMA unit.
 //
 // Same GEMM view as conv3x3.cuh, used for every conv whose A operand is a stored tensor as-is
-// (plain, cat(up, skip), the packed head inputs, and the weight-folded upsample convs):
-//   nn.Conv2d (unet.py:29,38,59,62,78) + LeakyReLU (unet.py:47,60,63) + torch.cat (unet.py:93).
+// (plain, cat(up, skip), the packed head inputs, the pooled copies, the weight-folded upsample convs)
+// and, with the XF transform stage, for the exact bilinear x2 sources of levels >= 2:
+//   nn.Conv2d (unet.py:29,38,59,62,78) + LeakyReLU (unet.py:47,60,63) + torch.cat (unet.py:93)
+//   + F.avg_pool2d as a second output (unet.py:46) + nn.Upsample (unet.py:77).
 //
 // Differences to conv3x3.cuh:
 //   * A operand: one cp.async.bulk.tensor (4-D tiled TMA, SWIZZLE_128B, out-of-bounds = zero = the
@@ -20,8 +22,12 @@
 //   * space-to-depth level-0 tensors (4 phases x 32 ch = 128 ch per block pixel) are consumed as two
 //     64-channel stages; stage parity = input phase row r, 8 (block shift, phase) entries each.
 //
-// Warp roles (224 threads, 1 CTA / SM, persistent): warps 0-3 epilogue, warp 4 MMA issue,
-// warp 5 weight blocks (cp.async.bulk), warp 6 activation halo tiles (cp.async.bulk.tensor).
+//   * outputs leave by TMA tensor stores from a swizzled staging buffer (ETMA) or, for the fp32 `last` outputs with
+//     their fused glue, the pooled copies and the scatter epilogue, by 256-bit global stores.
+//
+// Warp roles (1 CTA / SM, persistent): 4*EW epilogue warps (EW groups, one warp per TMEM lane quadrant), then one
+// warp each for MMA issue (a single elected thread), weight blocks (cp.async.bulk) and activation halo tiles
+// (cp.async.bulk.tensor), then -- XF only -- four transform warps.  224 / 352 / 480 threads.
 #pragma once
 #include <cuda.h>
 
@@ -53,7 +59,7 @@ struct FuseParams {
 struct ConvParamsV2 {
     int c0_chunks;               // box-wide (64-channel; 32 for KCS = 32) chunks taken from tensor map 0 (the rest from map 1: cat)
     int N, H, W;                 // conv grid
-    int n_stages;                // 64-channel-chunk groups per tile (KCS channels each)
+    int n_stages;                // K stages per tile (KCS stored channels each)
     const __nv_bfloat16* wpack;  // [n_ntiles][n_stages][n_ent][KB/8][NT][8]
     const float* bias;
     void* out;
@@ -75,6 +81,8 @@ struct ConvParamsV2 {
 // EW epilogue groups of 4 warps + MMA, weights, activations (+ 4 transform warps when the A operand is computed: XF)
 constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32; }
 
+// KCS  : stored channels per K stage = channels per TMA box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte rows,
+//        SWIZZLE_64B: the pooled level-0 tensor)
 // SCHED: 0 nine taps | 1 sixteen (block shift, phase) entries over one 64-channel chunk holding 4 phases x 16 ch (packed heads)
 //        | 2 half-phase: chunk parity = input phase row r, eight entries per chunk (level-0 tensors, 4 phases x 32 ch)
 // RES  : all n_stages * n_ent weight blocks stay resident in shared memory (loaded once per CTA)
@@ -87,7 +95,8 @@ constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32
 // CG   : 1 = one CTA per tile.  2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the leader's MMA thread issues M = 256
 //        MMAs over both CTAs' sub-tiles; each CTA stages its own activation halo but only HALF of every weight block
 //        (N/2 rows), so the per-SM shared-memory operand traffic of an MMA drops from 8 KB to 6 KB per 64 cycles and the
-//        weight stream per SM halves.  Streamed 9-tap schedule only.
+//        weight stream per SM halves (N = 64: 6 KB -> 5 KB per 48 cycles).  Streamed 9-tap schedule only; pair tiles
+//        are even-sized (TileWalkV2).
 // XF   : 1 = the A operand is the exact bilinear x2 upsample (nn.Upsample, align_corners=False, unet.py:77) of a coarser
 //        NHWC tensor: TMA stages the raw coarse tile [10 rows][4*MSUB+2 px][64 ch] in shared memory, four transform
 //        warps interpolate it into the swizzled halo tile (shared-memory reads instead of global-load latency).
