@@ -63,6 +63,30 @@ def test_engine_create_rejects_bad_shapes_without_gpu():
     l.rrin_engine_destroy(h)
 
 
+def test_conv_config_table_is_consistent():
+    """Tile configurations behind rrin_conv3x3 (host-side queries only): ids, K-stage geometry, packed sizes."""
+    import ctypes as C
+    from rrin_b200._lib import lib
+    l = lib()
+    v = [C.c_int() for _ in range(4)]
+    valid = {}
+    for cfg in range(-1, 40):
+        if l.rrin_conv_config_info(cfg, *map(C.byref, v)) == 0:
+            valid[cfg] = tuple(x.value for x in v)                       # kcs, kb, nt, msub
+    assert set(valid) == set(range(0, 9)) | set(range(10, 23)), sorted(valid)
+    for cfg, (kcs, kb, nt, msub) in valid.items():
+        assert kcs in (32, 64, 128) and kb in (16, 32, 64) and kb <= kcs and nt in (16, 64, 128) and 1 <= msub <= 4
+        if cfg >= 10:
+            assert msub * nt <= 512, "a tile's accumulators fit TMEM"
+    assert valid[21][:3] == (32, 32, 64) and valid[22][:3] == (64, 64, 64)
+    # packed 9-tap weights: [n-tile][stage][9][KB x NT] bf16, independent of the CTA-pair split
+    assert l.rrin_conv_packed_weight_bytes(16, 256, 4, 0) == 2 * 4 * 9 * 64 * 128 * 2
+    assert l.rrin_conv_packed_weight_bytes(19, 256, 4, 0) == l.rrin_conv_packed_weight_bytes(16, 256, 4, 0)
+    assert l.rrin_conv_packed_weight_bytes(21, 64, 1, 0) == 9 * 32 * 64 * 2
+    assert l.rrin_conv_packed_weight_bytes(22, 64, 2, 0) == l.rrin_conv_packed_weight_bytes(15, 64, 2, 0)
+    assert l.rrin_conv_packed_bias_count(21, 64) == 64
+
+
 def test_dropin_module_is_importable_as_model():
     code = ("import sys; sys.path[:0] = [%r, %r]; from model import Net; import rrin_b200; "
             "assert Net is rrin_b200.Net; n = Net(); print(len(n.state_dict()))" % (os.path.join(ROOT, "dropin"), ROOT))
