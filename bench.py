@@ -92,9 +92,8 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_reference_throughput(budget_s: float, threads: int):
-    """Time the oracle port on a strip of the 1080p workload sized for ~budget_s; returns
-    (frames_per_sec_1080p_equivalent, strip_h, seconds, n_timed)."""
+def cpu_reference_throughput(budget_s: float, threads: int, H: int = H, W: int = W):
+    """Sizes a strip of the HxW workload for ~budget_s of the oracle port; returns (state_dict, frame0, frame1, strip_h)."""
     import torch
     from oracle import rrin_oracle as O
     torch.set_num_threads(threads)
@@ -115,9 +114,12 @@ def run_reference(args):
     if rank != 0:
         return                                                  # rank 0 alone runs the CPU arm
     threads = os.cpu_count() or 1
+    cfg = CONFIGS[args.config]
+    H, W = cfg["h"], cfg["w"]
+    B = args.batch if args.batch else cfg["batch"]
     budget_total = 150.0
     per_step = budget_total / max(1, args.steps + args.warmup)
-    sd, a, b, strip_h = cpu_reference_throughput(per_step, threads)
+    sd, a, b, strip_h = cpu_reference_throughput(per_step, threads, H, W)
     for _ in range(args.warmup):
         O.forward(sd, a, b, 0.5)
     t0 = time.perf_counter()
@@ -126,12 +128,14 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     frac = strip_h / H
     fps = args.steps * frac / dt
-    sample = f"{strip_h}x{W} strip of the 1080p pair (= {frac:.4f} frame) per step, fp32, t=0.5"
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+    sample = f"{strip_h}x{W} strip of one {H}x{W} frame pair (= {frac:.4f} frame) per step, fp32, t=0.5"
+    metric = METRIC if args.config in ("1080p", "clip") else f"{args.config}_interpolated_frames_per_sec"
+    line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "1080p (1920x1088) 2x interpolation, t=0.5, random-init weights",
-                       "reference_path": "oracle port of Net.forward on torch CPU operators (reference is Python; cannot travel)"},
+            "scaling": "strong" if cfg["clip"] else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["what"].format(B=B) + ", random-init weights (torch.manual_seed(0))", "name": args.config,
+                       "reference_path": "oracle port of Net.forward on torch CPU operators (the reference is Python and cannot travel to the GPU box); "
+                                         "each step is a bounded sample of the workload: " + sample},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -191,10 +195,39 @@ def run_library(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+FLOP_PER_PX_FLOW = 521_856              # the t-independent Flow U-Net's share of FLOP_PER_PX
+
+# BASELINE.json configs[1..4]; "1080p" (configs[2], the configuration the metric is quoted on) is the default line.
+CONFIGS = {
+    "1080p": dict(h=1088, w=1920, batch=4, ts=None, clip=False,
+                  what="1080p (1920x1088) 2x interpolation of a synthetic clip, one batch of {B} consecutive frame pair(s) per step, t=0.5"),
+    "720p_b8": dict(h=736, w=1280, batch=8, ts=None, clip=False,
+                    what="720p (1280x720 padded to 1280x736) batch of {B} frame pairs per step, t=0.5"),
+    "1080p_t7": dict(h=1088, w=1920, batch=1, ts=[k / 8 for k in range(1, 8)], clip=False,
+                     what="1080p (1920x1088) 8x slow motion: 7 timesteps t=k/8 of one frame pair per step, Flow U-Net computed once per pair"),
+    "4k": dict(h=2176, w=3840, batch=1, ts=None, clip=False,
+               what="4K (3840x2160 padded to 3840x2176) one frame pair per step, t=0.5"),
+    "clip": dict(h=1088, w=1920, batch=4, ts=None, clip=True,
+                 what="1080p (1920x1088) 2x interpolation of the whole 240-frame synthetic clip per step (239 frame pairs split into "
+                      "contiguous shards over the ranks, batches of {B} pairs), t=0.5"),
+}
+
+
+def synth_frames(n, h, w, dev, seed):
+    """n consecutive frames of a synthetic clip on the device: smooth content (bicubic-upsampled noise) shifted by (2, 3)
+    pixels per frame plus 5 % white noise, U[0,1)."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    lo = torch.rand(1, 3, h // 8 + 8 + n // 2, w // 8 + 8 + n // 2, generator=g, device=dev)
+    big = torch.nn.functional.interpolate(lo, scale_factor=8, mode="bicubic", align_corners=False).clamp_(0, 1)
+    noise = torch.rand(1, 3, h, w, generator=g, device=dev) * 0.05
+    return [(big[:, :, 8 + 2 * i: 8 + 2 * i + h, 8 + 3 * i: 8 + 3 * i + w] * 0.95 + noise).contiguous() for i in range(n)]
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from rrin_b200 import Net
+    from rrin_b200 import ClipInterpolator, Net, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,6 +239,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    cfg = CONFIGS[args.config]
+    H, W, ts, clip_mode = cfg["h"], cfg["w"], cfg["ts"], cfg["clip"]
+    B = args.batch if args.batch else cfg["batch"]
+    metric = METRIC if args.config in ("1080p", "clip") else f"{args.config}_interpolated_frames_per_sec"
 
     # weights: random init of the reference architecture -- torch.manual_seed(0); Net() draws the same RNG stream as the
     # reference's model.Net() (tests/test_oracle.py pins the sha256) -- loaded via state_dict like convert.py:100-104
@@ -214,126 +251,182 @@ def run_gpu(args):
     net = Net()
     net.load_state_dict(sd, strict=True)
     net = net.cuda().eval()
+    net.precision = args.precision
 
-    # this rank's shard of the synthetic 240-frame clip (contiguous pairs; one frame shared by
-    # consecutive pairs), generated on the device: smooth content + per-frame shift, U[0,1)
-    from rrin_b200 import sharding
-    K, Wm, B = args.steps, args.warmup, args.batch
+    K, Wm = args.steps, max(args.warmup, 3)
     lo_pair, hi_pair = sharding.pair_range(CLIP_FRAMES, rank, world)
     pairs_per_rank = hi_pair - lo_pair
-    n_frames = min(pairs_per_rank, 12) + 1                      # frames kept resident; steps cycle over them
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    lo = torch.rand(1, 3, H // 8 + 8, W // 8 + 8, generator=g, device=dev)
-    big = torch.nn.functional.interpolate(lo, scale_factor=8, mode="bicubic", align_corners=False).clamp_(0, 1)
-    frames = [big[:, :, 8 + 2 * i: 8 + 2 * i + H, 8 + 3 * i: 8 + 3 * i + W].contiguous() for i in range(n_frames)]
-    noise = torch.rand(1, 3, H, W, generator=g, device=dev) * 0.05
-    frames = [(f * 0.95 + noise).contiguous() for f in frames]
-    del big, lo
-
-    def pair(i):
-        """Batch i of this rank's shard: B consecutive frame pairs (frame j+1 of one pair is frame j of the next)."""
-        js = [(i * B + k) % (n_frames - 1) for k in range(B)]
-        if B == 1:
-            return frames[js[0]], frames[js[0] + 1]
-        return torch.cat([frames[j] for j in js]), torch.cat([frames[j + 1] for j in js])
-
-    batches = [pair(i) for i in range(max(1, min(K + max(Wm, 3), (n_frames - 1) // B + 1)))]   # assembled outside the timed region
-
-    def batch(i):
-        return batches[i % len(batches)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- the step
+    if clip_mode:
+        # strong scaling: this rank's contiguous shard of the 240-frame clip, device resident (its pairs + the boundary frame)
+        frames = synth_frames(pairs_per_rank + 1, H, W, dev, 1000)       # same clip on every rank; the rank takes its own range
+        stack = torch.cat(frames)
+        batches = [(stack[i:min(i + B, pairs_per_rank)], stack[i + 1:min(i + B, pairs_per_rank) + 1]) for i in range(0, pairs_per_rank, B)]
+        frames_per_step_rank = pairs_per_rank
+        frames_per_step_job = CLIP_FRAMES - 1
+
+        def step(i):
+            y = None
+            for a, b in batches:
+                y = net(a, b, t=0.5)
+            return y
+        flop_per_step_job = frames_per_step_job * FLOP_PER_PX * H * W
+    else:
+        n_frames = (min(pairs_per_rank, 12) if ts is None and H * W <= 1088 * 1920 else 4) + 1     # frames kept resident; steps cycle over them
+        frames = synth_frames(n_frames, H, W, dev, 1000 + rank)
+        if ts is None:
+            def pair(i):
+                js = [(i * B + k) % (n_frames - 1) for k in range(B)]
+                if B == 1:
+                    return frames[js[0]], frames[js[0] + 1]
+                return torch.cat([frames[j] for j in js]), torch.cat([frames[j + 1] for j in js])
+            batches = [pair(i) for i in range(max(1, min(K + Wm, (n_frames - 1) // B + 1)))]   # assembled outside the timed region
+            frames_per_step_rank = B
+
+            def step(i):
+                a, b = batches[i % len(batches)]
+                return net(a, b, t=0.5)
+            flop_per_step_job = world * B * FLOP_PER_PX * H * W
+        else:
+            batches = [(frames[j], frames[j + 1]) for j in range(n_frames - 1)]
+            frames_per_step_rank = len(ts)
+
+            def step(i):
+                a, b = batches[i % len(batches)]
+                return net.forward_multi(a, b, ts)
+            flop_per_step_job = world * H * W * (FLOP_PER_PX_FLOW + len(ts) * (FLOP_PER_PX - FLOP_PER_PX_FLOW))   # algorithmic: Flow once per pair
+        frames_per_step_job = world * frames_per_step_rank
+
     # ---------------- device-resident throughput (`value`)
-    for i in range(max(Wm, 3)):
-        net(*batch(i), t=0.5)
+    for i in range(Wm):
+        step(i)
     barrier()
     clocks = ClockSampler(local)
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        y = net(*batch(i), t=0.5)
+        y = step(i)
     e1.record()
     barrier()
     t_wall1 = time.time()
-    ms = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop(t_wall0, t_wall1)
-    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max = float(tmax.item())
-    value = world * K * B / (ms_max * 1e-3)
+    value = K * frames_per_step_job / (ms_max * 1e-3)
 
     # ---------------- end to end with host buffers (`e2e`): the streaming clip pipeline (rrin_b200.ClipInterpolator) over a
-    # pinned host clip of ke*B+1 frames -- every frame crosses PCIe once host->device, every interpolated frame once
-    # device->host, copies overlapped with compute; the timed region covers all copies and ends with a host sync.
-    from rrin_b200 import ClipInterpolator
-    ke = max(3, min(K, 20))
-    clip = torch.empty(ke * B + 1, 3, H, W).pin_memory()
-    for i in range(clip.shape[0]):
-        clip[i].copy_(frames[i % n_frames][0])
-    out_host = torch.empty(ke * B, 3, H, W).pin_memory()
-    pipe = ClipInterpolator(net, H, W, batch=B, sf=1)
-    pipe.run(clip[:2 * B + 1], out_host[:2 * B])                 # warm-up (engine, events)
+    # pinned host clip -- every frame crosses PCIe once host->device, every interpolated frame once device->host, copies
+    # overlapped with compute; the timed region covers all copies and ends with a host sync.
+    sf = 1 if ts is None else len(ts)
+    pb = B if ts is None else 2                                  # pairs per pipeline stage
+    ke = max(3, min(K, 80 * 1088 * 1920 // (H * W * pb * sf)))          # about 80 1080p-size output frames of pinned host memory
+    if clip_mode:
+        n_clip_pairs = pairs_per_rank
+    else:
+        n_clip_pairs = ke * pb
+    host_clip = torch.empty(n_clip_pairs + 1, 3, H, W).pin_memory()
+    for i in range(host_clip.shape[0]):
+        host_clip[i].copy_(frames[i % len(frames)][0])
+    out_host = torch.empty(n_clip_pairs * sf, 3, H, W).pin_memory()
+    pipe = ClipInterpolator(net, H, W, batch=pb, sf=sf)
+    nw = min(n_clip_pairs, 2 * pb)
+    pipe.run(host_clip[:nw + 1], out_host[:nw * sf])             # warm-up (engines, graphs, events)
     barrier()
     e0.record()
-    pipe.run(clip, out_host)
+    pipe.run(host_clip, out_host)
     e1.record()
     barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * ke * B / (float(t2.item()) * 1e-3)
-    frame_bytes = 3 * H * W * 4
-    h2d_step, d2h_step = pipe.h2d_bytes / ke, pipe.d2h_bytes / ke
-    # same pipeline fed with the bytes an image decoder produces (uint8 HWC 1920x1080; Pad + ToTensor and to_pil + crop of
-    # dataloader.py:93-118 / utils.py:51-58 on the device): 4x fewer PCIe bytes.  Reported beside `e2e`, not instead of it.
-    clip8 = torch.empty(ke * B + 1, 1080, W, 3, dtype=torch.uint8).pin_memory()
-    clip8.copy_((clip[:, :, 8:, :] * 255).to(torch.uint8).permute(0, 2, 3, 1))
-    out8 = torch.empty(ke * B, 1080, W, 3, dtype=torch.uint8).pin_memory()
-    pipe8 = ClipInterpolator(net, 1080, W, batch=B, sf=1, uint8=True)
-    pipe8.run(clip8[:2 * B + 1], out8[:2 * B])
-    barrier()
-    e0.record()
-    pipe8.run(clip8, out8)
-    e1.record()
-    barrier()
-    t3 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    e2e_u8 = world * ke * B / (float(t3.item()) * 1e-3)
-    u8_h2d, u8_d2h = pipe8.h2d_bytes / ke, pipe8.d2h_bytes / ke
-    del clip8, out8, pipe8
-    # the reference-shaped call (convert.py:130-133: upload both frames, forward, download, sync -- per step) for comparison
-    hp = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in batches[:2]]
-    oh = torch.empty(B, 3, H, W).pin_memory()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(5):
-        a, b = hp[i % len(hp)]
-        oh.copy_(net(a.cuda(non_blocking=True), b.cuda(non_blocking=True), t=0.5), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    e2e_sync_call = 5 * B / (time.perf_counter() - t0)
+    t_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_frames_job = (CLIP_FRAMES - 1) if clip_mode else world * n_clip_pairs * sf
+    e2e_steps = 1 if clip_mode else ke
+    e2e_value = e2e_frames_job / (t_e2e * 1e-3)
+    h2d_step, d2h_step = pipe.h2d_bytes / e2e_steps, pipe.d2h_bytes / e2e_steps
+    e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
+           "api": "rrin_b200.ClipInterpolator.run(pinned host clip) -> pinned host frames: each source frame uploaded once, "
+                  "H2D / forward / D2H of successive batches on three streams, one host sync at the end"}
+    del host_clip, out_host, pipe
+    if args.config == "1080p":
+        # same pipeline fed with the bytes an image decoder produces (uint8 HWC 1920x1080; Pad + ToTensor and to_pil + crop of
+        # dataloader.py:93-118 / utils.py:51-58 on the device): 4x fewer PCIe bytes.  Reported beside `e2e`, not instead of it.
+        clip8 = torch.empty(ke * B + 1, 1080, W, 3, dtype=torch.uint8).pin_memory()
+        for i in range(clip8.shape[0]):
+            clip8[i].copy_((frames[i % len(frames)][0, :, 8:, :] * 255).to(torch.uint8).permute(1, 2, 0))
+        out8 = torch.empty(ke * B, 1080, W, 3, dtype=torch.uint8).pin_memory()
+        pipe8 = ClipInterpolator(net, 1080, W, batch=B, sf=1, uint8=True)
+        pipe8.run(clip8[:2 * B + 1], out8[:2 * B])
+        barrier()
+        e0.record()
+        pipe8.run(clip8, out8)
+        e1.record()
+        barrier()
+        t3 = max_over_ranks(e0.elapsed_time(e1))
+        e2e["uint8_frames"] = {"value": world * ke * B / (t3 * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": pipe8.h2d_bytes / ke,
+                               "d2h_bytes_per_step": pipe8.d2h_bytes / ke,
+                               "api": "ClipInterpolator(uint8=True): 1920x1080x3 uint8 HWC frames in and out, pad/ToTensor/to_pil/crop on the device"}
+        del clip8, out8, pipe8
+        # the reference-shaped call (convert.py:130-133: upload both frames, forward, download, sync -- per step) for comparison
+        hp = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in batches[:2]]
+        oh = torch.empty(B, 3, H, W).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(5):
+            a, b = hp[i % len(hp)]
+            oh.copy_(net(a.cuda(non_blocking=True), b.cuda(non_blocking=True), t=0.5), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e["per_call_sync_frames_per_sec"] = 5 * B / (time.perf_counter() - t0) * world
+        e2e["per_call_sync_api"] = "Net.forward(img1.cuda(), img2.cuda(), t) then .cpu() and a sync per step (convert.py:130-133)"
+        del hp, oh
+
+    # ---------------- single-pair calls (what convert.py:95-97 issues: batch_size=1), device resident
+    batch1 = None
+    if args.config == "1080p" and B != 1:
+        a1, b1 = frames[0], frames[1]
+        for _ in range(3):
+            net(a1, b1, t=0.5)
+        barrier()
+        e0.record()
+        for i in range(20):
+            net(frames[i % (len(frames) - 1)], frames[i % (len(frames) - 1) + 1], t=0.5)
+        e1.record()
+        barrier()
+        batch1 = {"value": world * 20 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3), "unit": "frames/s",
+                  "what": "Net.forward on one frame pair per call (batch 1), device-resident inputs"}
 
     line = None
     if rank == 0:
-        eng = net._engines[next(iter(net._engines))]
+        key = next(k for k in net._engines if k[2] == (B if ts is None else len(ts)) and k[3] == H and k[4] == W)
+        eng = net._engines[key]
         w = net._weights(dev)
-        # per-launch device times (CUDA events on the launching stream): per-launch median over 5 profiled forwards
-        # (a mean lets one stall -- a clock dip under the power cap -- land on whichever launch it hit)
+        pa, pbt = batches[0]
+        tt = 0.5 if ts is None else list(ts)
+        # per-launch device times (CUDA events on the launching stream): per-launch median over 5 profiled forwards, each
+        # issued right behind two unprofiled ones so the clocks are those of the sustained step (a mean would let one stall --
+        # a clock dip under the power cap -- land on whichever launch it hit).  Events between launches disable the
+        # programmatic-dependent-launch overlap, so the sum of these is an upper bound of the kernel time inside a step.
         table = eng.launch_table()
-        reps = 5
-        samples = [eng.profile(w, *batch(r), 0.5) for r in range(reps)]
+        samples = []
+        one = (lambda: net(pa, pbt, t=0.5)) if ts is None else (lambda: net.forward_multi(pa, pbt, ts))
+        for r in range(5):
+            one(); one()
+            samples.append(eng.profile(w, pa[:eng.n_pairs], pbt[:eng.n_pairs], tt))
         acc = [statistics.median(s[i] for s in samples) for i in range(len(table))]
         classes = {}
         for (name, layer, fl, by), t in zip(table, acc):
             c = classes.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             c["ms"] += t; c["flops"] += fl; c["bytes"] += by; c["launches"] += 1
-        step_ms = sum(acc)
+        sum_ms = sum(acc)
         dom_name, dom = max(classes.items(), key=lambda kv: kv[1]["ms"])
         conv_ms = sum(c["ms"] for n, c in classes.items() if n.startswith("conv"))
         conv_fl = sum(c["flops"] for n, c in classes.items() if n.startswith("conv"))
@@ -343,9 +436,11 @@ def run_gpu(args):
         glue_by = sum(c["bytes"] for n, c in classes.items() if is_glue(n))
         peak_tf = peaks["tf_sustained"]             # kernels timed inside a long step -> sustained peak
         ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+        # layer-wise roofline of the whole forward: every launch at max(tensor time, HBM time) of its algorithmic work
+        roof_ms = sum(max(fl / (peak_tf * 1e12), by / (peaks["hbm_gbs"] * 1e9)) * 1e3 for (_, _, fl, by) in table)
         traffic, traffic_of = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes of one launch of the class (ncu --set full capture)
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.config == "1080p":
             with open(tp) as f:
                 tj = json.load(f)
             ent = tj.get(dom_name)
@@ -355,53 +450,96 @@ def run_gpu(args):
                 traffic_of["capture"] = tj.get("_note", "")
             else:
                 traffic = ent
+        per_launch = [{"i": i, "kernel": n, "layer": ly, "ms": round(t, 4)} for i, ((n, ly, _, _), t) in enumerate(zip(table, acc))]
+        warp_i = next((i for i, (n, ly, _, _) in enumerate(table) if ly == "refine_flow.last" and n.endswith("+glue")), None)
+        blend_i = next((i for i, (n, ly, _, _) in enumerate(table) if ly == "Mask.last" and n.endswith("+glue")), None)
+        glue_launches = {}
+        for nm, i in (("refine_flow.last + residue add + both warps + Mask head pack", warp_i), ("Mask.last + sigmoid + blend + final head pack", blend_i)):
+            if i is not None:
+                glue_launches[nm] = {"ms": round(acc[i], 4), "gbs": round(table[i][3] / (acc[i] * 1e-3) / 1e9, 1),
+                                     "frac_of_hbm_peak": round(table[i][3] / (acc[i] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3)}
         roofline = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": ach / peak_tf, "traffic": traffic, "traffic_of": traffic_of,
                     "peak_source": peaks["source"] + ", bf16 sustained (kernel timed inside a long step)",
                     "launches_per_step": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
-                    "share_of_step": dom["ms"] / step_ms,
+                    "share_of_step": dom["ms"] / sum_ms,
                     "all_convs": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12, "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / peak_tf,
-                                  "share_of_step": conv_ms / step_ms},
+                                  "share_of_step": conv_ms / sum_ms},
+                    "whole_step": {"achieved": value * flop_per_step_job / frames_per_step_job / world / 1e12, "unit": "TFLOP/s per GPU",
+                                   "frac_of_burst_peak": value * flop_per_step_job / frames_per_step_job / world / 1e12 / peaks["tf_burst"],
+                                   "frac_of_sustained_peak": value * flop_per_step_job / frames_per_step_job / world / 1e12 / peaks["tf_sustained"],
+                                   "layerwise_roofline_ms": roof_ms, "frac_of_layerwise_roofline": roof_ms / sum_ms,
+                                   "note": "layer-wise roofline = sum over launches of max(FLOP / sustained bf16 peak, algorithmic bytes / HBM copy peak)"},
                     "warp_blend_glue": {"bound": "hbm", "kernels": sorted(n for n in classes if is_glue(n)),
                                         "achieved": glue_by / (glue_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                                         "unit": "GB/s", "frac": glue_by / (glue_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                        "share_of_step": glue_ms / step_ms},
+                                        "share_of_step": glue_ms / sum_ms, "launches": glue_launches},
                     "classes": {n: {"ms": round(c["ms"], 4), "launches": c["launches"],
                                     "tflops": round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 1) if c["flops"] else 0,
                                     "gbs": round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)} for n, c in classes.items()}}
-        # CPU baseline: oracle port on a bounded strip of the same workload, this box's host cores
-        # (the only place the GPU arm touches oracle/)
-        from oracle import rrin_oracle as O
-        threads = os.cpu_count() or 1
-        sdc, a, b, strip_h = cpu_reference_throughput(15.0, threads)
-        t0 = time.perf_counter(); O.forward(sdc, a, b, 0.5); dt = time.perf_counter() - t0
-        cpu = {"value": (strip_h / H) / dt, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"one {strip_h}x{W} strip of the 1080p pair (= {strip_h / H:.4f} frame), fp32, t=0.5, {dt:.1f} s"}
-        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"1080p (1920x1088) 2x interpolation of a synthetic clip, one batch of {B} consecutive frame pair(s) "
-                                       "per step, t=0.5, random-init weights (torch.manual_seed(0))",
-                           "batch": B, "arithmetic": "bf16 operands on tcgen05 tensor cores, fp32 accumulation; flows / mask logits / blend in fp32",
+        if args.per_launch:
+            roofline["per_launch"] = per_launch
+        # the warp under the flows a trained model produces: Flow.last scaled x200 (|flow| of several pixels, out-of-bounds
+        # taps) on the same smooth frames -- same launch, same bytes, scattered gathers
+        if args.config in ("1080p", "4k") and warp_i is not None:
+            sd2 = {k: v.clone() for k, v in sd.items()}
+            sd2["Flow.last.weight"] *= 200.0
+            sd2["Flow.last.bias"] *= 200.0
+            net2 = Net()
+            net2.load_state_dict(sd2, strict=True)
+            net2 = net2.cuda().eval()
+            net2.precision = args.precision
+            for _ in range(2):
+                net2(pa, pbt, t=0.5)
+            eng2 = net2._engines[next(iter(net2._engines))]
+            w2 = net2._weights(dev)
+            s2 = []
+            for r in range(3):
+                net2(pa, pbt, t=0.5)
+                s2.append(eng2.profile(w2, pa, pbt, 0.5)[warp_i])
+            fl = eng2.tap(0)
+            t2 = statistics.median(s2)
+            roofline["warp_blend_glue"]["warp_under_stress_flow"] = {
+                "weights": "Flow.last x200", "flow_abs_max_px": float(fl.abs().max().item()), "flow_abs_mean_px": float(fl.abs().mean().item()),
+                "ms": round(t2, 4), "gbs": round(table[warp_i][3] / (t2 * 1e-3) / 1e9, 1),
+                "frac_of_hbm_peak": round(table[warp_i][3] / (t2 * 1e-3) / 1e9 / peaks["hbm_gbs"], 3),
+                "same_launch_at_random_init_ms": round(acc[warp_i], 4)}
+            del net2, eng2, w2
+        gs = eng.graph_stats()
+        step_ms = ms_max / K
+        n_fwd = len(batches) if clip_mode else 1
+        line = {"metric": metric, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if clip_mode else "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": cfg["what"].format(B=B) + ", random-init weights (torch.manual_seed(0))", "name": args.config,
+                           "batch": B, "arithmetic": f"{args.precision} operands on tcgen05 tensor cores, fp32 accumulation; flows / mask logits / blend in fp32",
                            "sharding": f"{world} rank(s), contiguous shards of the {CLIP_FRAMES}-frame clip, no collective",
-                           "l2": f"per-step working set (~{0.75 * B:.1f} GB of activations) exceeds the 126 MB L2; no explicit flush",
-                           "tflop_per_frame": FLOP_PER_PX * H * W / 1e12,
-                           "tensor_frac_of_burst_peak": value / world * FLOP_PER_PX * H * W / 1e12 / peaks["tf_burst"],
-                           "tensor_frac_of_sustained_peak": value / world * FLOP_PER_PX * H * W / 1e12 / peaks["tf_sustained"]},
-                "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "steps": ke,
-                        "api": "rrin_b200.ClipInterpolator.run(pinned host clip) -> pinned host frames: each source frame uploaded once, "
-                               "H2D / forward / D2H of successive batches on three streams, one host sync at the end",
-                        "uint8_frames": {"value": e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": u8_h2d, "d2h_bytes_per_step": u8_d2h,
-                                         "api": "ClipInterpolator(uint8=True): 1920x1080x3 uint8 HWC frames in and out, pad/ToTensor/to_pil/crop on the device"},
-                        "per_call_sync_frames_per_sec": e2e_sync_call * world,
-                        "per_call_sync_api": "Net.forward(img1.cuda(), img2.cuda(), t) then .cpu() and a sync per step (convert.py:130-133)"},
-                "gpu_launches": eng.num_launches * K,
-                "roofline": roofline, "cpu_baseline": cpu}
+                           "l2": "per-step working set (>= 0.7 GB of activations per frame pair) exceeds the 126 MB L2; no explicit flush",
+                           "tflop_per_frame": flop_per_step_job / frames_per_step_job / 1e12,
+                           "tensor_frac_of_burst_peak": value / world * flop_per_step_job / frames_per_step_job / 1e12 / peaks["tf_burst"],
+                           "tensor_frac_of_sustained_peak": value / world * flop_per_step_job / frames_per_step_job / 1e12 / peaks["tf_sustained"]},
+                "clocks": clk, "e2e": e2e, "gpu_launches": eng.num_launches * K * n_fwd,
+                "launch_gap": {"step_ms": step_ms, "sum_kernel_ms": sum_ms * n_fwd if not clip_mode else None,
+                               "gap_frac": (step_ms - sum_ms) / step_ms if not clip_mode else None,
+                               "cuda_graph": {"replayed": gs[0], "direct": gs[1], "graphs": gs[2]},
+                               "note": "sum_kernel_ms: per-launch CUDA-event times (events between launches switch the programmatic-dependent-launch "
+                                       "overlap off, so this is an upper bound); the step replays one CUDA graph per forward"},
+                "roofline": roofline}
+        if batch1 is not None:
+            line["batch1"] = batch1
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
+        if world == 1 and not args.no_cpu:
+            # CPU baseline: oracle port on a bounded strip of the same workload, this box's host cores, N=1 only
+            # (the only place the GPU arm touches oracle/; after the process group is gone, so no GPU waits for it)
+            from oracle import rrin_oracle as O
+            threads = os.cpu_count() or 1
+            sdc, a, b, strip_h = cpu_reference_throughput(15.0, threads, H, W)
+            t0 = time.perf_counter(); O.forward(sdc, a, b, 0.5); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": (strip_h / H) / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"one {strip_h}x{W} strip of the {H}x{W} pair (= {strip_h / H:.4f} frame), fp32, t=0.5, {dt:.1f} s"}
         emit(line)
 
 
@@ -433,7 +571,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=4, help="frame pairs per step (per GPU)")
+    ap.add_argument("--batch", type=int, default=0, help="frame pairs per step (per GPU); 0 = the configuration's own")
+    ap.add_argument("--config", default="1080p", choices=sorted(CONFIGS), help="named BASELINE.json configuration (default: the headline one)")
+    ap.add_argument("--precision", default="bf16", help="operand format of the tensor-core path (Net.precision)")
+    ap.add_argument("--per-launch", action="store_true", help="add the per-launch time table to the JSON line")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--impl", default="rrin_b200", choices=["rrin_b200", "reference", "library"])
     args = ap.parse_args()
     if args.impl == "library":

@@ -9,7 +9,10 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
  *   - `stream` is a cudaStream_t passed as void* (the caller's current stream);
  *   - functions return 0 on success, non-zero otherwise (rrin_last_error() gives the text);
- *     they never throw, never allocate device memory, never synchronise the device;
+ *     they never throw, never allocate device memory, never synchronise the device (rrin_engine_forward_profiled, a
+ *     profiling aid, synchronises; rrin_engine_forward_graph instantiates a CUDA graph on its second call per pointer set);
+ *   - an engine and its workspace serve ONE forward at a time: calls on different streams must be ordered by the caller
+ *     (rrin_b200.engine.Engine.run does it with an event);
  *   - frames / results: fp32 NCHW [N,3,H,W] in [0,1]   (dataloader.py:116-118, convert.py:133)
  *   - U-Net activations: bf16 NHWC (level 0: space-to-depth, see K1); U-Net outputs: fp32 [N,H/2,W/2,4,4];
  *   - H and W must be multiples of 16 (four 2x2 pools in the Flow U-Net, unet.py:46).
@@ -68,6 +71,15 @@ RRIN_API int rrin_engine_num_launches(const rrin_engine* e);         /* kernels 
  * in0,in1: fp32 NCHW [n_pairs,3,H,W]; out: fp32 NCHW [n_samples,3,H,W]. */
 RRIN_API int rrin_engine_forward(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
                         const float* coef, float* out, void* stream);
+/* The same forward replayed from a CUDA graph (one cudaGraphLaunch instead of ~90 kernel launches; replaces the ~250-300
+ * eager op launches per Net.forward of the reference, model.py:59-65).  Graphs are cached per pointer set (blob, workspace,
+ * in0, in1, coef, out): the first call with a new set launches directly, the second captures + instantiates (the only
+ * allocation the library makes after rrin_engine_create: host/driver memory of the graph), later calls replay; at most 16
+ * sets are kept.  Results are bit-identical to rrin_engine_forward.  rrin_engine_graph_stats reports how many forwards of
+ * this engine were replayed / launched directly and how many graphs are alive. */
+RRIN_API int rrin_engine_forward_graph(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
+                              const float* coef, float* out, void* stream);
+RRIN_API int rrin_engine_graph_stats(const rrin_engine* e, int* graph_launches, int* direct_launches, int* graphs_alive);
 /* Profiling aids (bench.py): description of launch i of one forward (kernel class, reference layer,
  * algorithmic FLOPs and HBM bytes), and a forward that records a CUDA event after every launch and
  * returns per-launch device milliseconds in the HOST array ms_host[num_launches] (synchronises). */

@@ -27,6 +27,8 @@ _SIGNATURES = {
     "rrin_engine_workspace_bytes": (cs, [vp]),
     "rrin_engine_num_launches": (ci, [vp]),
     "rrin_engine_forward": (ci, [vp] * 8),
+    "rrin_engine_forward_graph": (ci, [vp] * 8),
+    "rrin_engine_graph_stats": (ci, [vp] + [C.POINTER(ci)] * 3),
     "rrin_engine_tap": (ci, [vp, vp, ci, vp, vp]),
     "rrin_engine_launch_info": (ci, [vp, ci, C.c_char_p, ci, C.c_char_p, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rrin_engine_forward_profiled": (ci, [vp] * 8 + [C.POINTER(C.c_float)]),

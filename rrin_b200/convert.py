@@ -1,0 +1,131 @@
+"""Folder-of-images -> folder-of-images interpolation: the reference's ``convert --image_folder`` path
+(convert.py:44-148 + dataloader.py:91-118 + utils.py:26-71) composed on the streaming pipeline.
+
+    convert_folder(src_dir, dst_dir, sf, model_name="MyModel")
+
+does what ``python . --model_name MyModel convert --sf SF --fps F --image_folder SRC`` does up to (and excluding) the
+ffmpeg encode: it finds the checkpoint the reference would pick (``models/<name>*``, convert.py:100-108), loads
+``state['model']`` with ``strict=True``, reads the frames, and writes into ``dst_dir`` the sequence
+
+    000000001<ext>  original frame 0 (file copy, convert.py:121-123)
+    000000002<ext>  .. interpolated t = 1/(sf+1) .. sf/(sf+1) (to_pil_image + crop + save, utils.py:51-58)
+    ...             original frame 1 (file copy, convert.py:136-139), and so on.
+
+The pixel path is ``ClipInterpolator(uint8=True)``: frames cross PCIe once, as the bytes PIL decoded; edge pad + ToTensor
+and mul(255).byte() + crop run on the device; for ``sf > 1`` the Flow U-Net runs once per pair.  Decoding, the file copies
+and PNG encoding stay on the host (PIL, a small thread pool like utils.py:36-37).  GPU video decode / encode
+ is out of scope: there is no ffmpeg / NVDEC / NVENC in the image.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import io as rio
+
+
+def _load_rgb(path: str):
+    """``Image.open`` + the channel rule of dataloader.py:116-118 (``ToTensor()(img)[:3]``: alpha dropped on the device)."""
+    from PIL import Image
+    with Image.open(path) as img:
+        if img.mode not in ("RGB", "RGBA"):
+            # ToTensor of an 'L' / 'P' image has one channel and the reference's Flow U-Net (6 input channels) fails on it
+            raise RuntimeError(f"{path}: image mode {img.mode!r}; the reference path handles RGB / RGBA frames only")
+        return np.asarray(img)
+
+
+def list_frames(src_dir: str, order: str = "sorted") -> List[str]:
+    """Frame file names of ``src_dir``.  The reference takes ``os.listdir`` order (dataloader.py:20), which is sorted on the
+    file systems it was written for (NTFS) and arbitrary elsewhere; ``order="sorted"`` (default) makes the intended
+    order explicit, ``order="listdir"`` mirrors the reference literally."""
+    names = os.listdir(src_dir)
+    if order == "sorted":
+        names = sorted(names)
+    elif order != "listdir":
+        raise ValueError("order must be 'sorted' or 'listdir'")
+    return names
+
+
+def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str] = None, models_dir: str = "models",
+                   net=None, batch: int = 2, resume: bool = False, order: str = "sorted", chunk_pairs: int = 64,
+                   io_workers: int = 4, device: Optional[torch.device] = None) -> List[str]:
+    """Interpolates ``sf`` frames between consecutive images of ``src_dir`` into ``dst_dir``; returns the written paths in
+    output order.  ``net``: a ready ``rrin_b200.Net`` (cuda, eval); otherwise the checkpoint ``models_dir/<model_name>*`` is
+    loaded like convert.py:98-111.  ``resume=True`` continues like convert.py:46-53 (the pair index is recomputed from the
+    number of files already in ``dst_dir``)."""
+    from .model import Net
+    from .pipeline import ClipInterpolator
+    if sf < 1:
+        raise ValueError("sf must be >= 1")
+    names = list_frames(src_dir, order)
+    if len(names) < 2:
+        raise RuntimeError(f"{src_dir}: need at least two frames, found {len(names)}")
+    os.makedirs(dst_dir, exist_ok=True)
+    existing = len(os.listdir(dst_dir))
+    if resume:
+        ridx = rio.resume_index(existing, sf)
+    else:
+        if existing:
+            raise RuntimeError("Folder is already in use! Did you intend to resume the progress? Use resume=True")   # convert.py:57-59
+        ridx = 1
+    first_pair = ridx - 1                                             # ConvertSampler(dataset, resume_index - 1), convert.py:95
+    img_count = rio.first_output_number(ridx, sf)                     # convert.py:118
+
+    if net is None:
+        if model_name is None:
+            raise ValueError("either `net` or `model_name` is required")
+        net = Net()
+        net.load_state_dict(rio.load_checkpoint(rio.find_checkpoint(models_dir, model_name)), strict=True)   # convert.py:100-104
+        net = net.cuda(device).eval()                                 # convert.py:110-111
+    dev = device or next(net.parameters()).device
+
+    paths = [os.path.join(src_dir, n) for n in names]
+    exts = [os.path.splitext(n)[1] for n in names]                    # dataloader.py:55: outputs keep the source file type
+    first = _load_rgb(paths[first_pair])
+    h0, w0, ch = first.shape
+    rio.padded_shape(h0, w0)                                          # raises like the reference when the padded size cannot run
+    pipe = ClipInterpolator(net, h0, w0, batch=batch, sf=sf, device=dev, uint8=True, channels=ch)
+    written: List[str] = []
+    pool = ThreadPoolExecutor(max_workers=max(1, io_workers))
+    jobs = []
+
+    def save_png(arr: np.ndarray, dest: str):
+        from PIL import Image
+        Image.fromarray(arr, "RGB").save(dest)                        # utils.py:58 (to_pil_image gives mode RGB)
+
+    def out_path(number: int, ext: str) -> str:
+        p = os.path.join(dst_dir, f"{number:09d}{ext}")               # convert.py:122,135,138
+        written.append(p)
+        return p
+
+    try:
+        n_pairs = len(names) - 1
+        p0 = first_pair
+        if img_count == 1:                                            # convert.py:121-123: the very first original
+            jobs.append(pool.submit(shutil.copy, paths[p0], out_path(1, exts[p0])))
+        carry = first
+        while p0 < n_pairs:
+            p1 = min(n_pairs, p0 + chunk_pairs)
+            frames = [carry] + [_load_rgb(paths[i]) for i in range(p0 + 1, p1 + 1)]
+            for i, f in enumerate(frames):
+                if f.shape != (h0, w0, ch):
+                    raise RuntimeError(f"{paths[p0 + i]}: frame is {f.shape}, expected {(h0, w0, ch)} like the first frame")
+            clip = torch.from_numpy(np.stack(frames)).pin_memory()
+            outs = pipe.run(clip).numpy()                             # [(p1-p0)*sf, h0, w0, 3] uint8, cropped like utils.py:56-57
+            for k, p in enumerate(range(p0, p1)):
+                for i in range(1, sf + 1):                            # convert.py:127-135
+                    jobs.append(pool.submit(save_png, outs[k * sf + i - 1].copy(), out_path(img_count + i, exts[p])))
+                jobs.append(pool.submit(shutil.copy, paths[p + 1], out_path(img_count + sf + 1, exts[p + 1])))   # convert.py:136-139
+                img_count += sf + 1
+            carry = frames[-1]
+            p0 = p1
+        for j in jobs:
+            j.result()
+    finally:
+        pool.shutdown(wait=True)
+    return written

@@ -395,6 +395,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const long want = (total + c.cg * c.msub - 1) / (c.cg * c.msub);
     const int workers = sms / c.cg;
     const int grid = c.cg * (int)(want < workers ? (want > 0 ? want : 1) : workers);
+#ifdef RRIN_DIAG
     // diagnostics only: RRIN_CONV_PROF=1 prints block 0's per-role wait cycles after every launch (synchronises)
     static const int dbg = getenv("RRIN_CONV_DBG") ? atoi(getenv("RRIN_CONV_DBG")) : 0;
     p.dbg = dbg;
@@ -405,12 +406,14 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
         RRIN_CUDA_CHECK(cudaMemsetAsync(prof_buf, 0, (16 + 4 * 160) * sizeof(unsigned long long), stream));
         p.prof = prof_buf;
     }
+#endif
     int rc = RRIN_ERR_BAD_ARG;
     switch (cfg) {
 #define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>(id, p, tm0, tm1, tmo, tmw, grid, stream); break;
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }
+#ifdef RRIN_DIAG
     if (prof_on && rc == RRIN_OK) {
         unsigned long long h[16 + 4 * 160];
         RRIN_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -426,6 +429,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
                         "mma total %llu wait_a %llu wait_b %llu wait_acc %llu issue %llu commit %llu | epi total %llu wait_full %llu\n",
                 cfg, d.N, d.H, d.W, p.n_stages, n_ent_of(d.sched), p.n_ntiles, h[7], h[2], h[1], h[0], h[6], h[3], h[4], h[5], h[10], h[11], h[9], h[8]);
     }
+#endif
     return rc;
 }
 

@@ -73,9 +73,11 @@ struct ConvParamsV2 {
     int units_per_nt;            // N * tiles_y * sx
     int total_units;             // n_ntiles * units_per_nt
     FuseParams fz;
-    int dbg;                     // diagnostics (RRIN_CONV_DBG, timing only, wrong results): 1 skip activation loads, 2 skip weight loads,
+#ifdef RRIN_DIAG                 // diagnostics build only (python -m rrin_b200.build --diag); the shipped library has neither
+    int dbg;                     // RRIN_CONV_DBG (timing only, wrong results): 1 skip activation loads, 2 skip weight loads,
                                  // 4 skip stores, 8 skip the whole epilogue, 16 issue one MMA per (stage, sub-tile)
-    unsigned long long* prof;    // diagnostics (RRIN_CONV_PROF=1): per-role wait/total cycle counters of block 0, else null
+    unsigned long long* prof;    // RRIN_CONV_PROF=1: per-role wait/total cycle counters of block 0, else null
+#endif
 };
 
 // EW epilogue groups of 4 warps + MMA, weights, activations (+ 4 transform warps when the A operand is computed: XF)
@@ -235,11 +237,19 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
     auto raw_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + C::RAW_SLOTS + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
 
+    // diagnostics (timing knobs that give wrong results, per-role cycle counters) exist only in -DRRIN_DIAG builds
+#ifdef RRIN_DIAG
+    const int dbg = p.dbg;
+    unsigned long long* const pprof = p.prof;
+#else
+    constexpr int dbg = 0;
+    constexpr unsigned long long* pprof = nullptr;
+#endif
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nst = p.n_stages;
     const int nblk = nst * N_ENT;
-    const long long t_begin = p.prof ? clock64() : 0;      // diagnostics: per-CTA timeline (prof[16 + 4*cta + k])
+    const long long t_begin = pprof ? clock64() : 0;      // diagnostics: per-CTA timeline (prof[16 + 4*cta + k])
 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
     // The rotation is a function of the tile's row band and n-tile only, so a pixel's K-sum order -- and with it the
     // bit pattern of the result -- does not depend on the batch size or the grid.
     auto rot_of = [&](const TileV2& tt) { return RES ? 0 : (int)((unsigned)(tt.ty + tt.nt) % (unsigned)nst) & (C::HALF ? ~1 : ~0); };
-    const bool prof = p.prof != nullptr && blockIdx.x == 0;
+    const bool prof = pprof != nullptr && blockIdx.x == 0;
     // CTA pairs: "full" barriers (activations, weights) and the accumulator "empty" barriers live in the leader
     auto leader_bar = [&](uint32_t bar) { return (CG == 2) ? mapa_shared(bar, 0) : bar; };
 
@@ -288,18 +298,18 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
-                    if (XF) {           // raw coarse tile of chunk st into the staging ring; the transform warps fill the A stage
+                    if constexpr (XF != 0) {   // raw coarse tile of chunk st into the staging ring; the transform warps fill the A stage
                         const int rs = it % C::RAW_SLOTS;
                         mbar_wait(raw_empty(rs), ((it / C::RAW_SLOTS) & 1) ^ 1);
                         mbar_arrive_expect_tx(raw_full(rs), C::RAW_BYTES);
                         tma_load_4d(s_base + C::OFF_RAW + rs * C::RAW_STRIDE, &tm0, st * 64, t.sx0 * 4 - 1, t.ty * (kTileH / 2) - 1, t.n, raw_full(rs));
                         continue;
-                    }
+                    } else {
                     const int stage = it % SA;
                     const long long c0 = prof ? clock64() : 0;
                     mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
                     if (prof) tw += clock64() - c0;
-                    if (p.dbg & 1) { mbar_arrive(a_full(stage)); continue; }
+                    if (dbg & 1) { mbar_arrive(a_full(stage)); continue; }
                     const bool first = st < p.c0_chunks;
                     if (CG == 2) {      // both CTAs' tiles complete the leader's barrier, armed by the leader for 2 boxes
                         if (cta_rank == 0) mbar_arrive_expect_tx(a_full(stage), 2 * C::BOX_BYTES);
@@ -309,9 +319,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         mbar_arrive_expect_tx(a_full(stage), C::BOX_BYTES);
                         tma_load_4d(s_a + stage * C::A_STAGE, first ? &tm0 : &tm1, (first ? st : st - p.c0_chunks) * C::BOX_CH, x0, y0, t.n, a_full(stage));
                     }
+                    }
                 }
             }
-            if (prof) { p.prof[0] = tw; p.prof[1] = clock64() - t00; p.prof[2] = it; }
+            if (prof) { pprof[0] = tw; pprof[1] = clock64() - t00; pprof[2] = it; }
         }
         __syncwarp();
     } else if (warp == W_B) {
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         uint32_t bytes = C::B_BLOCK;
                         if (C::HALF && ((st & 1) ? (e < 4) : (e >= 4))) bytes = C::B_BLOCK / 2;
                         mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
-                        if (p.dbg & 2) { mbar_arrive(b_full(slot)); continue; }
+                        if (dbg & 2) { mbar_arrive(b_full(slot)); continue; }
                         if (CG == 2) {
                             // this CTA's half (N/2 rows) of block b, as a 64-row x 128-byte box of the packed weights viewed
                             // as a 2-D tensor of 128-byte rows; both halves complete the leader's barrier
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         }
 #pragma unroll
                         for (int s = 0; s < KB / 16; ++s)
-                            if (!(p.dbg & 16) || (e | s) == 0)                 // diagnostics: one MMA per (stage, sub-tile) only
+                            if (!(dbg & 16) || (e | s) == 0)                 // diagnostics: one MMA per (stage, sub-tile) only
                                 mma(tmem_base + ts * NT + dcol, a_e + j * (C::ROWB / 2) + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
                                     (e | s) != 0 || !first_stage);
                     }
@@ -475,11 +486,12 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 slot0 = (slot0 + m) % C::SLOTS;
                 ++ntile;
             }
-            if (prof) { p.prof[3] = twa; p.prof[4] = twb; p.prof[5] = twc; p.prof[6] = clock64() - t00; p.prof[7] = ntile; p.prof[10] = tmma; p.prof[11] = tcom; }
-            if (p.prof) { p.prof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; p.prof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
+            if (prof) { pprof[3] = twa; pprof[4] = twb; pprof[5] = twc; pprof[6] = clock64() - t00; pprof[7] = ntile; pprof[10] = tmma; pprof[11] = tcom; }
+            if (pprof) { pprof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; pprof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
         }
         __syncwarp();
     } else if (XF && warp >= W_X) {
+      if constexpr (XF != 0) {
         // =========================================================== transform warps: exact bilinear x2 of the raw coarse tile
         // thread -> 16-byte channel chunk c8 of halo pixels q = px0, px0 + 16, ...; source taps / weights as ATen's
         // upsample_bilinear2d (align_corners=False): src = max((o + 0.5) / 2 - 0.5, 0), i1 = i0 + (i0 < size - 1)
@@ -532,6 +544,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 mbar_arrive(raw_empty(rs));
             }
         }
+      }
     } else if (warp < 4 * EW) {
         // =========================================================== epilogue: EW groups of 4 warps (quadrant = warp % 4)
         const int quad = warp & 3, grp = warp >> 2;
@@ -555,7 +568,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 const bool ok = (gy < p.H) && (gx < p.W);
                 const size_t pix = (size_t)(t.n * p.H + gy) * p.W + gx;
                 const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + ts * NT;
-                if (p.dbg & 8) { tc_fence_before(); if (CG == 2) mbar_arrive_cluster(leader_bar(acc_empty(ts))); else mbar_arrive(acc_empty(ts)); continue; }   // diagnostics
+                if (dbg & 8) { tc_fence_before(); if (CG == 2) mbar_arrive_cluster(leader_bar(acc_empty(ts))); else mbar_arrive(acc_empty(ts)); continue; }   // diagnostics
                 // Tiles that take more than half of the accumulator slots (no double buffering: the next tile starts on
                 // SLOTS - MSUB free slots): the slot goes back to the MMA thread as soon as its last column is in registers,
                 // before the bias / activation / staging / store of that data.  (Measured: -4 % on the level-0 cat conv;
@@ -608,7 +621,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                          "r"(o[4 * k]), "r"(o[4 * k + 1]), "r"(o[4 * k + 2]), "r"(o[4 * k + 3]) : "memory");
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && !(p.dbg & 4)) {
+                        if (lane == 0 && !(dbg & 4)) {
                             tma_store_4d(&tmo, stg, t.nt * NT + c, (t.sx0 + j) * 8, t.ty * kTileH + 4 * quad, t.n);
                             bulk_commit_group();
                         }
@@ -746,8 +759,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
             seq += t.m;
         }
         if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed
-        if (prof && threadIdx.x == 0) { p.prof[8] = twf; p.prof[9] = clock64() - t00; }
-        if (p.prof && warp == 4 * EW - 4 && lane == 0) p.prof[16 + 4 * blockIdx.x + 2] = clock64() - t_begin;                       // last epilogue group done
+        if (prof && threadIdx.x == 0) { pprof[8] = twf; pprof[9] = clock64() - t00; }
+        if (pprof && warp == 4 * EW - 4 && lane == 0) pprof[16 + 4 * blockIdx.x + 2] = clock64() - t_begin;                       // last epilogue group done
     }
 
     // ---------------- teardown
@@ -757,7 +770,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
     if (warp == W_MMA) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
-        if (p.prof && lane == 0) p.prof[16 + 4 * blockIdx.x + 3] = clock64() - t_begin;                                              // CTA end
+        if (pprof && lane == 0) pprof[16 + 4 * blockIdx.x + 3] = clock64() - t_begin;                                              // CTA end
     }
 }
 

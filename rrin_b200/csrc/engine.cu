@@ -197,6 +197,18 @@ struct rrin_engine {
     const void* tmap_ws = nullptr;              // workspace base the cached tensor maps were encoded for
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every launch
     int prof_n = 0;
+    // rrin_engine_forward_graph: instantiated CUDA graphs of the launch sequence, keyed by every pointer baked into it
+    struct GraphEntry {
+        const void* key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // blob, workspace, in0, in1, coef, out
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long last_use = 0;
+        int dev = -1;
+    };
+    std::vector<GraphEntry> graphs;
+    cudaStream_t cap_stream = nullptr;          // capture happens on a private stream (torch's default stream is the legacy stream,
+    int cap_dev = -1;                           // which cannot be captured); the instantiated graph launches into any stream
+    unsigned long long tick = 0;
+    int graph_launches = 0, direct_launches = 0;
 };
 
 static inline void mark(rrin_engine* e, cudaStream_t st) {
@@ -409,13 +421,27 @@ int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** o
     return RRIN_OK;
 }
 
-void rrin_engine_destroy(rrin_engine* e) { delete e; }
+void rrin_engine_destroy(rrin_engine* e) {
+    if (!e) return;
+    for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    delete e;
+}
 size_t rrin_engine_workspace_bytes(const rrin_engine* e) { return e ? e->ws_bytes : 0; }
 int rrin_engine_num_launches(const rrin_engine* e) { return e ? (int)e->launches.size() : 0; }
 
 int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, const float* in0, const float* in1,
                         const float* coef, float* out, void* stream) {
     if (!e || !blob_ || !workspace || !in0 || !in1 || !coef || !out) { set_error("rrin_engine_forward: null argument"); return RRIN_ERR_BAD_ARG; }
+    // frames are read with 8-byte loads and the result is written with 8-byte stores; the workspace and the weight blob
+    // hold TMA / 256-bit-store targets.  A misaligned pointer would fault on the device (sticky): refuse it here.
+    if ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(out)) & 15) {
+        set_error("rrin_engine_forward: in0, in1 and out must be 16-byte aligned"); return RRIN_ERR_BAD_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(blob_) | reinterpret_cast<uintptr_t>(workspace)) & 255) {
+        set_error("rrin_engine_forward: the weight blob and the workspace must be 256-byte aligned"); return RRIN_ERR_BAD_ARG;
+    }
+    if (reinterpret_cast<uintptr_t>(coef) & 3) { set_error("rrin_engine_forward: coef must be 4-byte aligned"); return RRIN_ERR_BAD_ARG; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint8_t* blob = static_cast<const uint8_t*>(blob_);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
@@ -471,6 +497,80 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
         if (r != RRIN_OK) return r;
         mark(e, st);
     }
+    return RRIN_OK;
+}
+
+// Net.forward replayed from a CUDA graph (model.py:59-65; same launches, same programmatic-dependent-launch edges as
+// rrin_engine_forward, one cudaGraphLaunch instead of ~90 kernel launches).  A graph bakes in every pointer, so graphs are
+// cached per (blob, workspace, in0, in1, coef, out): the FIRST call with a new pointer set launches directly and only
+// remembers the set; the second call captures and instantiates (this is the one place the library allocates -- host and
+// driver memory of the graph -- after engine creation); later calls replay.  A streaming caller that cycles through a few
+// staging buffers (rrin_b200.pipeline, convert.py's loop under torch's caching allocator) therefore replays every step,
+// while a caller with ever-new pointers never pays for a capture.  At most kMaxGraphs graphs are kept (least recently used
+// is dropped).
+static constexpr int kMaxGraphs = 16;
+
+int rrin_engine_forward_graph(rrin_engine* e, const void* blob, void* workspace, const float* in0, const float* in1,
+                              const float* coef, float* out, void* stream) {
+    if (!e) { set_error("rrin_engine_forward_graph: null engine"); return RRIN_ERR_BAD_ARG; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int dev = -1;
+    RRIN_CUDA_CHECK(cudaGetDevice(&dev));
+    const void* key[6] = {blob, workspace, in0, in1, coef, out};
+    rrin_engine::GraphEntry* hit = nullptr;
+    for (auto& g : e->graphs)
+        if (g.dev == dev && memcmp(g.key, key, sizeof key) == 0) { hit = &g; break; }
+    ++e->tick;
+    if (hit && hit->exec) {
+        hit->last_use = e->tick;
+        RRIN_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
+        ++e->graph_launches;
+        return RRIN_OK;
+    }
+    if (!hit) {                                   // first sighting: remember the pointer set, launch directly
+        if ((int)e->graphs.size() >= kMaxGraphs) {
+            size_t lru = 0;
+            for (size_t i = 1; i < e->graphs.size(); ++i) if (e->graphs[i].last_use < e->graphs[lru].last_use) lru = i;
+            if (e->graphs[lru].exec) cudaGraphExecDestroy(e->graphs[lru].exec);
+            e->graphs.erase(e->graphs.begin() + lru);
+        }
+        rrin_engine::GraphEntry g;
+        memcpy(g.key, key, sizeof key);
+        g.dev = dev; g.last_use = e->tick;
+        e->graphs.push_back(g);
+        ++e->direct_launches;
+        return rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
+    }
+    // second sighting: capture the launch sequence on the private stream and instantiate it
+    hit->last_use = e->tick;
+    if (e->cap_stream && e->cap_dev != dev) { cudaStreamDestroy(e->cap_stream); e->cap_stream = nullptr; }
+    if (!e->cap_stream) { RRIN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking)); e->cap_dev = dev; }
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal);
+    int r = RRIN_OK;
+    if (ce == cudaSuccess) {
+        r = rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, e->cap_stream);
+        ce = cudaStreamEndCapture(e->cap_stream, &graph);          // always ends the capture, also after a failed launch
+        if (r == RRIN_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+    }
+    if (r != RRIN_OK || ce != cudaSuccess || !hit->exec) {         // capture unavailable: stay on direct launches for this set
+        cudaGetLastError();
+        hit->exec = nullptr;
+        ++e->direct_launches;
+        return rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
+    }
+    RRIN_CUDA_CHECK(cudaGraphLaunch(hit->exec, st));
+    ++e->graph_launches;
+    return RRIN_OK;
+}
+
+// how many forwards of this engine were replayed from a graph / launched kernel by kernel (tests, bench.py)
+int rrin_engine_graph_stats(const rrin_engine* e, int* graph_launches, int* direct_launches, int* graphs_alive) {
+    if (!e) { set_error("rrin_engine_graph_stats: null engine"); return RRIN_ERR_BAD_ARG; }
+    if (graph_launches) *graph_launches = e->graph_launches;
+    if (direct_launches) *direct_launches = e->direct_launches;
+    if (graphs_alive) { int n = 0; for (auto& g : e->graphs) n += g.exec != nullptr; *graphs_alive = n; }
     return RRIN_OK;
 }
 

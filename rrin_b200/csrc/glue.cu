@@ -123,7 +123,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kGlueThreads) frame_from_u8_kernel(const uint8_t* __restrict__ src, int H0, int W0, int C, int top,
                                                                       int H, float* __restrict__ dst) {
     const long total = (long)H * W0;
-    if (VEC == 4) {
+    if constexpr (VEC == 4) {
         // 4 pixels per thread: 12 (RGB) or 16 (RGBA) source bytes as 32-bit words, one float4 per plane (W0 % 4 == 0, aligned bases)
         const long groups = total / 4;
         const int Wg = W0 / 4;
@@ -140,14 +140,14 @@ __global__ void __launch_bounds__(kGlueThreads) frame_from_u8_kernel(const uint8
                     make_float4(__fdiv_rn((float)b[c], 255.f), __fdiv_rn((float)b[C + c], 255.f), __fdiv_rn((float)b[2 * C + c], 255.f),
                                 __fdiv_rn((float)b[3 * C + c], 255.f));                          // ToTensor: byte -> float, div(255)
         }
-        return;
-    }
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
-        const int sy = min(max(y - top, 0), H0 - 1);
-        const uint8_t* p = src + ((long)sy * W0 + x) * C;
+    } else {
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+            const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
+            const int sy = min(max(y - top, 0), H0 - 1);
+            const uint8_t* p = src + ((long)sy * W0 + x) * C;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) dst[(long)c * total + i] = __fdiv_rn((float)p[c], 255.f);    // ToTensor: byte -> float, div(255)
+            for (int c = 0; c < 3; ++c) dst[(long)c * total + i] = __fdiv_rn((float)p[c], 255.f);    // ToTensor: byte -> float, div(255)
+        }
     }
 }
 // K9 = to_pil_image (pic.mul(255).byte(): truncation) + crop((0, H - H0, W0, H)) (utils.py:51-58): fp32 NCHW [3,H,W] ->
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kGlueThreads) frame_to_u8_kernel(const float* 
                                                                     uint8_t* __restrict__ dst) {
     const long total = (long)H0 * W0, plane = (long)H * W;
     const int crop = H - H0;
-    if (VEC == 4) {
+    if constexpr (VEC == 4) {
         // 4 pixels per thread: one float4 per plane in, 12 bytes out as three 32-bit words (W, W0 % 4 == 0, aligned bases)
         const long groups = total / 4;
         const int Wg = W0 / 4;
@@ -176,15 +176,15 @@ __global__ void __launch_bounds__(kGlueThreads) frame_to_u8_kernel(const float* 
             uint32_t* d = reinterpret_cast<uint32_t*>(dst + ((long)y * W0 + x) * 3);
             d[0] = w[0]; d[1] = w[1]; d[2] = w[2];
         }
-        return;
-    }
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
-        const float* p = src + (long)(y + crop) * W + x;
+    } else {
+        for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+            const int y = (int)(i / W0), x = (int)(i - (long)y * W0);
+            const float* p = src + (long)(y + crop) * W + x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float v = __fmul_rn(p[c * plane], 255.f);
-            dst[i * 3 + c] = (uint8_t)(int)v;                      // float -> integer truncation, then the low byte (torch .byte())
+            for (int c = 0; c < 3; ++c) {
+                const float v = __fmul_rn(p[c * plane], 255.f);
+                dst[i * 3 + c] = (uint8_t)(int)v;                  // float -> integer truncation, then the low byte (torch .byte())
+            }
         }
     }
 }

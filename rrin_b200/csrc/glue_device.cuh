@@ -58,7 +58,10 @@ __device__ __forceinline__ float warp_coord(int g, float d, float size) {
 __device__ __forceinline__ void bilinear_gather3(const float* __restrict__ img, long HW, int H, int W, float ix, float iy, float (&o)[3]) {
     const float xw = floorf(ix), yn = floorf(iy);
     const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
-    const int x0 = (int)xw, y0 = (int)yn;
+    // float -> int saturates here (NaN -> 0, +-inf -> INT_MAX / INT_MIN); the clamp keeps x0 + 1 / the base offset from
+    // overflowing.  A NaN coordinate (NaN flow) yields NaN weights, so every in-range tap contributes NaN: the sample is NaN
+    // like grid_sample's; an infinite coordinate has all four taps out of range and samples 0, also like grid_sample.
+    const int x0 = min(max((int)xw, -2), W), y0 = min(max((int)yn, -2), H);
     const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
     const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
     const float wnw = s * e, wne = s * w, wsw = nn * e, wse = nn * w;
@@ -143,14 +146,17 @@ __device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const fl
     stg256(out4 + 2, ob[2], ob[3]);
 }
 
+// torch.clamp(x, 0, 1) (model.py:63) propagates NaN; fminf / fmaxf alone would return the non-NaN operand
+__device__ __forceinline__ float clamp01(float x) { return x != x ? x : fminf(fmaxf(x, 0.f), 1.f); }
+
 // ---- K5: final residue + clamp (model.py:62-63) -> the block pixel's 2x2 pixels of the fp32 NCHW result
 __device__ __forceinline__ void glue_clamp_block(const float4 (&r)[4], const float4 (&o)[4], long HW, int W, int by, int bx, float* __restrict__ y) {
     float v[3][4];
 #pragma unroll
     for (int ph = 0; ph < 4; ++ph) {
-        v[0][ph] = fminf(fmaxf(r[ph].x + o[ph].x, 0.f), 1.f);
-        v[1][ph] = fminf(fmaxf(r[ph].y + o[ph].y, 0.f), 1.f);
-        v[2][ph] = fminf(fmaxf(r[ph].z + o[ph].z, 0.f), 1.f);
+        v[0][ph] = clamp01(r[ph].x + o[ph].x);
+        v[1][ph] = clamp01(r[ph].y + o[ph].y);
+        v[2][ph] = clamp01(r[ph].z + o[ph].z);
     }
     float* d = y + (long)(2 * by) * W + 2 * bx;
 #pragma unroll

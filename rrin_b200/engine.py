@@ -6,11 +6,19 @@ and the current CUDA stream.  All arithmetic happens inside ``librrin_b200.so``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Sequence, Union
 
 import torch
 
 from ._lib import check, lib
+
+
+# operand formats of the tensor-core path -> code passed through the C-ABI
+PRECISIONS = {"bf16": 0}
+
+# RRIN_GRAPH=0: launch kernel by kernel instead of replaying CUDA graphs (A/B timing; results are bit-identical)
+USE_GRAPH = os.environ.get("RRIN_GRAPH", "1") != "0"
 
 
 def conv_table():
@@ -36,9 +44,11 @@ def _stream() -> int:
 class PackedWeights:
     """bf16 UMMA-ordered copy of all 81 conv weights + fp32 biases in one device blob (K7)."""
 
-    def __init__(self, net: torch.nn.Module, device: torch.device, fingerprint=None):
+    def __init__(self, net: torch.nn.Module, device: torch.device, fingerprint=None, precision: str = "bf16"):
         l = lib()
-        self.device, self.fingerprint = device, fingerprint
+        self.device, self.fingerprint, self.precision = device, fingerprint, precision
+        if precision not in PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r}")
         sd = net.state_dict()
         with torch.cuda.device(device):
             self.blob = torch.zeros(l.rrin_packed_weights_bytes(), dtype=torch.uint8, device=device)
@@ -76,16 +86,21 @@ def time_coefficients(t: Union[float, torch.Tensor, Sequence[float]], n: int, de
 class Engine:
     """One problem shape (n_pairs, n_samples, H, W) on one device."""
 
-    def __init__(self, device: torch.device, n: int, h: int, w: int, n_pairs: int | None = None):
+    def __init__(self, device: torch.device, n: int, h: int, w: int, n_pairs: int | None = None, precision: str = "bf16"):
         l = lib()
-        self.device, self.n, self.h, self.w = device, n, h, w
+        self.device, self.n, self.h, self.w, self.precision = device, n, h, w, precision
+        if precision not in PRECISIONS:
+            raise ValueError(f"unknown precision {precision!r}")
         self.n_pairs = n if n_pairs is None else n_pairs
         hnd = C.c_void_p()
         check(l.rrin_engine_create(self.n_pairs, n, h, w, C.byref(hnd)), "rrin_engine_create")
         self._h = hnd
         with torch.cuda.device(device):
             self.workspace = torch.empty(l.rrin_engine_workspace_bytes(hnd), dtype=torch.uint8, device=device)
+            self._done = torch.cuda.Event()           # end of the last forward that used this engine's workspace
+        self._last_stream = None
         self.num_launches = l.rrin_engine_num_launches(hnd)
+        self.workspace_bytes = self.workspace.numel()
         self._coef_cache = {}
 
     def __del__(self):
@@ -96,18 +111,36 @@ class Engine:
         except Exception:
             pass
 
-    def invalidate_graph(self):
-        pass
+    def graph_stats(self):
+        """(forwards replayed from a CUDA graph, forwards launched kernel by kernel, graphs alive)."""
+        v = [C.c_int() for _ in range(3)]
+        check(lib().rrin_engine_graph_stats(self._h, *[C.byref(x) for x in v]), "rrin_engine_graph_stats")
+        return tuple(x.value for x in v)
+
+    @staticmethod
+    def _frames(x: torch.Tensor) -> torch.Tensor:
+        """fp32, contiguous, 16-byte aligned (the kernels read frames with 8-byte loads): a misaligned view -- e.g. a slice of
+        a flat buffer at an odd element offset -- is copied rather than faulted on."""
+        x = x.detach().to(torch.float32).contiguous()
+        return x if x.data_ptr() % 16 == 0 else x.clone()
 
     def run(self, weights: "PackedWeights", in0: torch.Tensor, in1: torch.Tensor, coef: torch.Tensor,
             out: torch.Tensor | None = None) -> torch.Tensor:
-        in0 = in0.detach().to(torch.float32).contiguous()
-        in1 = in1.detach().to(torch.float32).contiguous()
+        in0, in1 = self._frames(in0), self._frames(in1)
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((self.n, 3, self.h, self.w), dtype=torch.float32, device=self.device)
-            check(lib().rrin_engine_forward(self._h, _ptr(weights.blob), _ptr(self.workspace), _ptr(in0), _ptr(in1),
-                                            _ptr(coef), _ptr(out), _stream()), "rrin_engine_forward")
+            elif out.data_ptr() % 16:
+                raise RuntimeError("`out` must be 16-byte aligned (the kernels write it with vector stores)")
+            cur = torch.cuda.current_stream()
+            # One workspace per engine: a forward issued on another stream than the previous one is ordered after it.
+            if self._last_stream is not None and self._last_stream != cur.cuda_stream:
+                cur.wait_event(self._done)
+            fwd = lib().rrin_engine_forward_graph if USE_GRAPH else lib().rrin_engine_forward
+            check(fwd(self._h, _ptr(weights.blob), _ptr(self.workspace), _ptr(in0), _ptr(in1),
+                      _ptr(coef), _ptr(out), cur.cuda_stream), "rrin_engine_forward")
+            self._done.record(cur)
+            self._last_stream = cur.cuda_stream
         return out
 
     def _coef(self, t):
@@ -142,8 +175,7 @@ class Engine:
     def profile(self, weights, in0, in1, t) -> List[float]:
         """Per-launch device milliseconds of one forward (CUDA events on the launching stream)."""
         coef = time_coefficients(t, self.n, self.device)
-        in0 = in0.detach().float().contiguous()
-        in1 = in1.detach().float().contiguous()
+        in0, in1 = self._frames(in0), self._frames(in1)
         ms = (C.c_float * self.num_launches)()
         with torch.cuda.device(self.device):
             out = torch.empty((self.n, 3, self.h, self.w), dtype=torch.float32, device=self.device)

@@ -50,8 +50,22 @@ def output_names(n_frames: int, sf: int, ext: str = ".png") -> List[Tuple[str, O
 
 
 def resume_index(n_existing_outputs: int, sf: int) -> int:
-    """First pair to process when resuming (convert.py:50-56): ``(len(listdir(dest)) - 1) // (sf + 1)``."""
-    return max(n_existing_outputs - 1, 0) // (sf + 1)
+    """The reference's 1-BASED ``resume_index`` (convert.py:46-53): 1 unless more than 5 outputs exist, else
+    ``(len(listdir(dest)) - 1) // (sf + 1)``.  The reference then starts its sampler at pair ``resume_index - 1``
+    (convert.py:95) -- see ``resume_first_pair`` -- and numbers that pair's first frame ``first_output_number``."""
+    return (n_existing_outputs - 1) // (sf + 1) if n_existing_outputs > 5 else 1
+
+
+def resume_first_pair(n_existing_outputs: int, sf: int) -> int:
+    """Zero-based index of the first frame pair a resumed conversion processes (``ConvertSampler(dataset,
+    resume_index - 1)``, convert.py:95, utils.py:22-23)."""
+    return resume_index(n_existing_outputs, sf) - 1
+
+
+def first_output_number(resume_idx: int, sf: int) -> int:
+    """Running number (1-based, the 9-digit file name) of the first ORIGINAL frame of the pair a conversion starts with:
+    ``img_count = resume_index + resume_index * sf - sf`` (convert.py:118) == (resume_index - 1) * (sf + 1) + 1."""
+    return resume_idx + resume_idx * sf - sf
 
 
 def find_checkpoint(models_dir: str, model_name: str) -> str:

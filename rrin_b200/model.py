@@ -11,6 +11,12 @@ Boundary:
   * ``forward`` returns a new ``[N,3,H,W]`` fp32 CUDA tensor in [0,1], enqueued on torch's
     current stream (the caller does ``.cpu()`` right after, convert.py:132-135).
     Inputs are not modified (the reference's dataloader reuses img2, dataloader.py:153-166).
+  * Inference only (convert.py:117 wraps the call in ``torch.no_grad()``): with grad enabled in ``train()`` mode, or with
+    inputs that require grad, ``forward`` raises instead of returning a tensor without ``grad_fn``.
+  * One forward at a time per ``Net``: an engine (one per problem shape) owns one workspace; calls from different CUDA
+    streams are ordered by an event, calls from different host threads must be serialised by the caller.
+  * NaN / Inf follow the reference: ``clamp`` propagates NaN (model.py:63), a NaN flow gives a NaN sample, an infinite
+    one samples the zero padding (model.py:20).
 
 All arithmetic runs in the hand-written sm_100a kernels of ``rrin_b200/csrc`` through
 the C-ABI library (``include/rrin_b200.h``).  There is no CPU / torch fallback: a
@@ -18,6 +24,7 @@ non-CUDA input or a missing library raises.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Optional, Sequence, Union
 
 import torch
@@ -34,40 +41,91 @@ class Net(nn.Module):
         self.Flow = UNet(6, 4, 5)
         self.refine_flow = UNet(10, 4, 4)
         self.final = UNet(9, 3, 4)
-        self._engines = {}        # (device, n_pairs, N, H, W) -> engine.Engine
-        self._packed = None       # engine.PackedWeights, rebuilt when parameters change
-        self.precision = "bf16"   # operand format of the tensor-core path (fp32 accumulate)
+        self._engines = OrderedDict()   # (device, n_pairs, N, H, W, precision) -> engine.Engine, least recently used first
+        self._packed = {}               # precision -> engine.PackedWeights, rebuilt when parameters change
+        self._plist = None              # cached list(self.parameters())
+        self._precision = "bf16"
+
+    # Engines own multi-GB workspaces (1080p batch 4: ~3 GB; 4K: ~3.3 GB): the cache is bounded by BYTES, least recently
+    # used evicted first, so a caller alternating between a handful of small shapes never re-allocates while a caller
+    # walking through large shapes cannot pile workspaces up.
+    ENGINE_CACHE_BYTES = 24 << 30
+    ENGINE_CACHE_MAX = 32
+
+    # ------------------------------------------------------------------ precision
+    @property
+    def precision(self) -> str:
+        """Operand format of the tensor-core path (accumulation is always fp32; flows, mask logits and the blend are fp32):
+        ``"bf16"`` (default: bf16 range == fp32 range, PSNR >= 50 dB bar) or ``"fp16"`` (11-bit significand: the
+        <= 1e-3 max-abs bar also under multi-pixel flows; activations above 65504 would overflow)."""
+        return self._precision
+
+    @precision.setter
+    def precision(self, value: str):
+        from .engine import PRECISIONS
+        if value not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {value!r}")
+        self._precision = value
 
     # ------------------------------------------------------------------ weights
+    def _params(self):
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return self._plist
+
     def _param_fingerprint(self):
-        return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
+        # in-place updates (optimizer steps, load_state_dict's copy_) bump Tensor._version; re-allocation (.cuda(), .to())
+        # goes through _apply, which drops the cache.  Writes through `.data` bypass both: call invalidate_weights().
+        ps = self._params()
+        return (sum(p._version for p in ps), ps[0].data_ptr(), ps[-1].data_ptr())
+
+    def invalidate_weights(self):
+        """Forget the packed (tensor-core layout) copy of the weights; the next forward re-packs them.  Needed only after
+        parameter updates that PyTorch's version counters do not see (``p.data.copy_(...)``, ``p.data.mul_(...)``)."""
+        self._packed = {}
+        self._plist = None
+
+    def _apply(self, fn, *args, **kwargs):          # .cuda() / .to() / .float(): parameters are re-created
+        self.invalidate_weights()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_weights()
+        return super().load_state_dict(*args, **kwargs)
 
     def _weights(self, device):
         from . import engine
         fp = self._param_fingerprint()
-        if self._packed is None or self._packed.fingerprint != fp or self._packed.device != device:
-            self._packed = engine.PackedWeights(self, device, fp)
-            for e in self._engines.values():
-                e.invalidate_graph()
-        return self._packed
+        pk = self._packed.get(self._precision)
+        if pk is None or pk.fingerprint != fp or pk.device != device:
+            pk = self._packed[self._precision] = engine.PackedWeights(self, device, fp, self._precision)
+        return pk
 
     def _engine(self, device, n, h, w, n_pairs=None):
         from . import engine
         n_pairs = n if n_pairs is None else n_pairs
-        key = (device, n_pairs, n, h, w)
+        key = (device, n_pairs, n, h, w, self._precision)
         e = self._engines.get(key)
-        if e is None:
-            if len(self._engines) >= 4:           # bound workspace memory: keep few shapes alive
-                self._engines.pop(next(iter(self._engines)))
-            e = self._engines[key] = engine.Engine(device, n, h, w, n_pairs)
+        if e is not None:
+            self._engines.move_to_end(key)
+            return e
+        e = engine.Engine(device, n, h, w, n_pairs, self._precision)
+        self._engines[key] = e
+        total = sum(x.workspace_bytes for x in self._engines.values())
+        while len(self._engines) > 1 and (total > self.ENGINE_CACHE_BYTES or len(self._engines) > self.ENGINE_CACHE_MAX):
+            _, old = self._engines.popitem(last=False)
+            total -= old.workspace_bytes
         return e
 
     # ------------------------------------------------------------------ forward
-    @staticmethod
-    def _check(input0: torch.Tensor, input1: torch.Tensor):
+    def _check(self, input0: torch.Tensor, input1: torch.Tensor):
         if not (input0.is_cuda and input1.is_cuda):
             raise RuntimeError("rrin_b200.Net runs on CUDA (sm_100a) only; there is no CPU fallback "
                                "(the reference too hard-codes .cuda(), model.py:11-12)")
+        if torch.is_grad_enabled() and (input0.requires_grad or input1.requires_grad or (self.training and self._params()[0].requires_grad)):
+            # train.py:98 calls model(f0, f1) with grad enabled in train() mode and then loss.backward(): that cannot work here
+            raise RuntimeError("rrin_b200.Net is inference only (no backward pass): call it under torch.no_grad() / in eval() mode "
+                               "like convert.py:111,117, or use the reference model for training")
         if input0.shape != input1.shape or input0.dim() != 4 or input0.shape[1] != 3:
             raise RuntimeError(f"Sizes of tensors must match: expected two [N,3,H,W] frames, got "
                                f"{tuple(input0.shape)} and {tuple(input1.shape)}")
