@@ -310,10 +310,10 @@ def run_gpu(args):
         frames_per_step_job = world * frames_per_step_rank
 
     # ---------------- device-resident throughput (`value`)
+    clocks = ClockSampler(local)                 # started before the warm-up: nvidia-smi needs a moment before its first sample
     for i in range(Wm):
         step(i)
     barrier()
-    clocks = ClockSampler(local)
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

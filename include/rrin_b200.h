@@ -39,6 +39,13 @@ extern "C" {
 #define RRIN_ERR_CUDA 3
 #define RRIN_ERR_BAD_ARG 4
 
+/* 16-bit operand / activation format of the tensor-core path (accumulation is always fp32; flows, mask logits, the blend
+ * and the final residue stay fp32).  BF16: fp32 range, 8-bit significand -- the default, PSNR >= 50 dB path.  FP16: 11-bit
+ * significand at the same speed and size -- the "fp32-accumulate path within 1e-3" precision mode; activations above 65504
+ * would overflow.  The reference computes these convs in fp32 (unet.py:29,38,59,62,78). */
+#define RRIN_PRECISION_BF16 0
+#define RRIN_PRECISION_FP16 1
+
 /* library version (major*10000 + minor*100 + patch) and last error text of this thread */
 RRIN_API int rrin_version(void);
 RRIN_API const char* rrin_last_error(void);
@@ -56,14 +63,16 @@ RRIN_API int rrin_conv_info(int idx, char* key, int key_cap, int* cin, int* cout
  * convert.py:100-104).  w: fp32 OIHW [cout,cin,3,3], b: fp32 [cout] -> this conv's slice of the
  * packed blob (bf16, per-tap K-major UMMA core-matrix order).  blob must be 256-byte aligned. */
 RRIN_API size_t rrin_packed_weights_bytes(void);
-RRIN_API int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* stream);
+RRIN_API int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* stream);               /* bf16 */
+RRIN_API int rrin_pack_conv_ex(int idx, const float* w, const float* b, void* blob, int precision, void* stream);
 
 /* ---- the engine: Net.forward (model.py:59-65) for a fixed problem shape -------------------
  * n_pairs frame pairs and n_samples interpolated frames: either n_samples == n_pairs (sample i
  * uses pair i: a batch, model.py:59) or n_pairs == 1 (all samples interpolate the same pair at
  * different t; the t-independent Flow U-Net, model.py:33-35, then runs once). */
 typedef struct rrin_engine rrin_engine;
-RRIN_API int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** out);
+RRIN_API int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** out);                    /* bf16 */
+RRIN_API int rrin_engine_create_ex(int n_pairs, int n_samples, int H, int W, int precision, rrin_engine** out);  /* blob packed with the same precision */
 RRIN_API void rrin_engine_destroy(rrin_engine* e);
 RRIN_API size_t rrin_engine_workspace_bytes(const rrin_engine* e);   /* caller-provided scratch, 256-B aligned */
 RRIN_API int rrin_engine_num_launches(const rrin_engine* e);         /* kernels enqueued by one forward */
@@ -118,6 +127,12 @@ RRIN_API int rrin_pack_conv_raw(int kind, const float* w, const float* b, int co
 RRIN_API int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                  int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
                  int act, int ring_only, int cfg, void* pool_out, void* stream);
+/* the same two with the 16-bit format given (RRIN_PRECISION_*); the plain names are the bf16 ones */
+RRIN_API int rrin_pack_conv_raw_ex(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
+                          void* wpack, float* bias_pack, int precision, void* stream);
+RRIN_API int rrin_conv3x3_ex(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
+                    int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
+                    int act, int ring_only, int cfg, void* pool_out, int precision, void* stream);
 
 /* Glue kernels.  Frames are fp32 NCHW; tensors exchanged with the U-Nets are space-to-depth on the half-res
  * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8].

@@ -22,7 +22,9 @@ _SIGNATURES = {
     "rrin_conv_info": (ci, [ci, C.c_char_p, ci] + [C.POINTER(ci)] * 5),
     "rrin_packed_weights_bytes": (cs, []),
     "rrin_pack_conv": (ci, [ci, vp, vp, vp, vp]),
+    "rrin_pack_conv_ex": (ci, [ci, vp, vp, vp, ci, vp]),
     "rrin_engine_create": (ci, [ci, ci, ci, ci, C.POINTER(vp)]),
+    "rrin_engine_create_ex": (ci, [ci, ci, ci, ci, ci, C.POINTER(vp)]),
     "rrin_engine_destroy": (None, [vp]),
     "rrin_engine_workspace_bytes": (cs, [vp]),
     "rrin_engine_num_launches": (ci, [vp]),
@@ -37,6 +39,8 @@ _SIGNATURES = {
     "rrin_conv_packed_bias_count": (ci, [ci, ci]),
     "rrin_pack_conv_raw": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
     "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
+    "rrin_pack_conv_raw_ex": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, ci, vp]),
+    "rrin_conv3x3_ex": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, ci, vp]),
     "rrin_pack_pair": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "rrin_flow_tscale_pack": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_warp_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),

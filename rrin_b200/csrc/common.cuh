@@ -3,6 +3,7 @@
 // status plumbing of the C-ABI.  No CUTLASS/CuTe: everything is spelled out in PTX.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -306,6 +307,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Same with the operand format chosen at run time (precision mode): f16 = 0 -> bf16 operands, 1 -> fp16 operands
+// (kind::f16 covers both at the same rate; D stays f32).
+__host__ __device__ constexpr uint32_t make_idesc_ab(int M, int N, int f16) {
+    return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------- bf16 packing
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -313,6 +320,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+}
+
+// ---------------------------------------------------------------- 16-bit operand format as a template parameter
+// F16 = 0: bf16 (fp32 range, 8-bit significand; the default path) | 1: fp16 (11-bit significand, max 65504; the
+// "fp32-accumulate within 1e-3" precision mode).  Storage size, TMA boxes, swizzles and MMA rate are identical.
+template <int F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (F16 != 0) {
+        __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&v);
+    } else {
+        return pack_bf16x2(lo, hi);
+    }
+}
+template <int F16>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+    if constexpr (F16 != 0) return __half22float2(*reinterpret_cast<__half2*>(&v));
+    else return unpack_bf16x2(v);
+}
+// run-time variant (the transform kernel conv3x3.cuh and the weight repack take the format as a launch parameter)
+__device__ __forceinline__ uint32_t pack2_rt(int f16, float lo, float hi) { return f16 ? pack2<1>(lo, hi) : pack2<0>(lo, hi); }
+__device__ __forceinline__ float2 unpack2_rt(int f16, uint32_t v) { return f16 ? unpack2<1>(v) : unpack2<0>(v); }
+__device__ __forceinline__ uint16_t to16_rt(int f16, float v) {
+    if (f16) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&b);
 }
 
 }  // namespace rrin

@@ -1,7 +1,8 @@
 // Host side of K1: configuration table, weight repack (K7: plain / space-to-depth / folded
 // upsample) and launcher for the tcgen05 implicit-GEMM 3x3 convolution (conv3x3.cuh).
 #include "conv3x3.cuh"
-#include "conv3x3_v2.cuh"
+#define RRIN_CONV2_INSTANTIATE
+#include "conv3x3_launch.cuh"
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,40 +34,6 @@ namespace rrin {
     X(6, 128, 32, 128, 1, 2, 16, 0) \
     X(7, 64, 64, 64, 1, 3, 6, 1)   \
     X(8, 64, 16, 128, 1, 3, 12, 1)
-
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>  (XF = 0 unless noted)
-// 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
-// 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
-// 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
-// 13 : < 64, 32,  16, 2, 2, 16, S2D8 , 1, 0, 2, 1>  level-0 `last` 32->{2,3,4}, fp32 output + fused glue (two epilogue groups: the warps gather)
-// 14 : < 64, 64,  64, 2, 3,  9, TAPS9, 1, 1, 1, 1>  level-1 64->64, weights resident
-// 15 : < 64, 64,  64, 4, 2,  6, TAPS9, 0, 1, 1, 1>  level-1 cat(64+64)->64
-// 16 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  levels >= 2 plain / cat (3 of the 4 accumulator slots per tile, two epilogue groups:
-//                                                    the next tile's MMAs start as soon as the first slots are drained)
-// 17 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 0, 2, 1>  per-thread stores: folded upsample conv scattering into level 1
-// 18 : < 64, 64, 128, 3, 2,  4, TAPS9, 0, 1, 2, 1>  folded upsample conv writing level 0 (K = 64 x 9 only: epilogue-heavy)
-// 19 : < 64, 64, 128, 3, 2,  6, TAPS9, 0, 1, 2, 2>  levels >= 2 plain / cat on CTA PAIRS (cta_group::2, M = 256): half of every
-//                                                    weight block per CTA
-// 20 : < 64, 64, 128, 2, 2,  4, TAPS9, 0, 1, 2, 1, XF>  exact bilinear x2 source (up.1 convs of levels >= 2): TMA-staged raw coarse
-//                                                    tile + four transform warps
-// 21 : < 32, 32,  64, 4, 3,  9, TAPS9, 1, 1, 1, 1>     level-1 block.0 on the pooled 32-channel level-0 tensor: 64-byte pixel rows
-//                                                    (TMA SWIZZLE_64B boxes, 64-byte-swizzle A descriptors), weights resident
-// 22 : < 64, 64,  64, 4, 2,  8, TAPS9, 0, 1, 2, 2>     level 1 on CTA pairs (experimental, RRIN_L1_PAIR=1): M = 256, each CTA holds 32 of the 64
-//                                                    weight rows, so an MMA reads 4 KB (A) + 1 KB (B) per SM instead of 4 + 2
-#define RRIN_CONV2_CONFIGS(X)                   \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
-    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
-    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1, 0)  \
-    X(13, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1, 0)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1, 0)   \
-    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
-    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1, 0)  \
-    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0)  \
-    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0) \
-    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1) \
-    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0) \
-    X(22, 64, 64, 64, 4, 2, 8, 0, 0, 1, 2, 2, 0)
 
 constexpr int kV2Base = 10;
 struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf; };
@@ -119,8 +86,8 @@ __host__ __device__ inline void s2d8_entry(int r, int e, int& u, int& v, int& c)
 // ------------------------------------------------------------------ K7: weight repack
 // -> bf16 [n_ntiles][n_stages][n_ent][KB/8][NT][8] (+ fp32 bias [n_ntiles*NT]); once per load_state_dict.
 __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const float* __restrict__ b, int cout, int cin,
-                                    int kcs, int kb, int nt, int n_ntiles, int n_stages, int n_ent,
-                                    __nv_bfloat16* __restrict__ wp, float* __restrict__ bp) {
+                                    int kcs, int kb, int nt, int n_ntiles, int n_stages, int n_ent, int f16,
+                                    uint16_t* __restrict__ wp, float* __restrict__ bp) {
     // bilinear x2 (align_corners=False) coefficient of coarse sample (i+u) in hi-res sample 2i+a+d:  al[a][d+1][u+1]
     const float al[2][3][3] = {{{.75f, .25f, 0.f}, {.25f, .75f, 0.f}, {0.f, .75f, .25f}},
                                {{.25f, .75f, 0.f}, {0.f, .75f, .25f}, {0.f, .25f, .75f}}};
@@ -142,10 +109,10 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
                 // CTA pairs: each block is stored as two halves [n / (nt/2)][KB/8][nt/2][8] -- one per CTA of the pair
                 const int hn = nt / 2, half = n / hn, nn = n - half * hn;
                 const long blk = i - (((long)k8 * nt + n) * 8 + e8);
-                wp[blk + (long)half * (kb * hn) + ((long)k8 * hn + nn) * 8 + e8] = __float2bfloat16_rn(v);
+                wp[blk + (long)half * (kb * hn) + ((long)k8 * hn + nn) * 8 + e8] = to16_rt(f16, v);
                 continue;
             }
-        } else if (kind == PACK_S2D || kind == PACK_S2D8) {
+        } else if (kind == PACK_S2D || kind == PACK_S2D8 || kind == PACK_S2D8_CG2) {
             const int cpp = nt / 4, ph = n / cpp, co = n - ph * cpp;
             int u, rr, vv, cc, ci;
             if (kind == PACK_S2D) { s2d_entry(ent, u, rr, vv, cc); ci = st * kb + k; }
@@ -153,15 +120,22 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
             const int dy = 2 * u + rr - (ph >> 1), dx = 2 * vv + cc - (ph & 1);
             if (dy >= -1 && dy <= 1 && dx >= -1 && dx <= 1 && co < cout && ci < cin)
                 v = w[((long)co * cin + ci) * 9 + (dy + 1) * 3 + (dx + 1)];
-            if (kind == PACK_S2D8 && nt == 128) {
+            if (kind != PACK_S2D && nt == 128) {
                 // half entries (conv3x3_v2.cuh): a +-1 row block shift feeds one output phase row only -> the block is
                 // stored compactly as [KB/8][64][8] (first half of its slot) for an N = 64 MMA
                 const int hf = (rr == 0) ? ((ent >> 2) == 1 ? 2 : 0) : ((ent >> 2) == 0 ? 1 : 0);
+                const int lo = (hf == 2) ? 64 : 0, ncb = hf ? 64 : 128;      // first column and column count of this block
+                if (hf && (n < lo || n >= lo + 64)) continue;
+                const int nn = n - lo;
+                const long blk = i - (((long)k8 * nt + n) * 8 + e8);
+                if (kind == PACK_S2D8_CG2) {
+                    // CTA pairs: two halves [h][KB/8][ncb/2][8], one per CTA (each holds N/2 weight rows of every block)
+                    const int hn = ncb / 2, half = nn / hn, n2 = nn - half * hn;
+                    wp[blk + (long)half * (kb * hn) + ((long)k8 * hn + n2) * 8 + e8] = to16_rt(f16, v);
+                    continue;
+                }
                 if (hf) {
-                    const int lo = (hf == 2) ? 64 : 0;
-                    if (n < lo || n >= lo + 64) continue;
-                    const long blk = i - (((long)k8 * nt + n) * 8 + e8);
-                    wp[blk + ((long)k8 * 64 + (n - lo)) * 8 + e8] = __float2bfloat16_rn(v);
+                    wp[blk + ((long)k8 * 64 + nn) * 8 + e8] = to16_rt(f16, v);
                     continue;
                 }
             }
@@ -174,12 +148,12 @@ __global__ void pack_weights_kernel(int kind, const float* __restrict__ w, const
                     for (int dx = 0; dx < 3; ++dx) v += al[a][dy][u] * al[bb][dx][vv] * wk[dy * 3 + dx];
             }
         }
-        wp[i] = __float2bfloat16_rn(v);
+        wp[i] = to16_rt(f16, v);
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ntiles * nt; i += gridDim.x * blockDim.x) {
         float v = 0.f;
         if (kind == PACK_NORMAL || kind == PACK_NORMAL_CG2) { if (i < cout) v = b[i]; }
-        else if (kind == PACK_S2D || kind == PACK_S2D8) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
+        else if (kind == PACK_S2D || kind == PACK_S2D8 || kind == PACK_S2D8_CG2) { const int co = i % (nt / 4); if (co < cout) v = b[co]; }
         else { if (i < 4 * cout) v = b[i % cout]; }
         bp[i] = v;
     }
@@ -198,7 +172,7 @@ int conv_packed_bias_count(int cfg, int n_cols) {
 }
 
 int conv_pack_weights(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
-                      void* wpack, float* bias_pack, cudaStream_t stream) {
+                      void* wpack, float* bias_pack, cudaStream_t stream, int f16) {
     if (!cfg_valid(cfg)) { set_error("conv_pack_weights: bad config %d", cfg); return RRIN_ERR_BAD_ARG; }
     const CfgInfo& c = cfg_info(cfg);
     int n_cols, n_ent, kspan;
@@ -208,17 +182,19 @@ int conv_pack_weights(int kind, const float* w, const float* b, int cout, int ci
         if ((kind == PACK_NORMAL_CG2) != (c.cg == 2)) { set_error("pack: kind %d does not match config %d (CTA-pair layout)", kind, cfg); return RRIN_ERR_BAD_ARG; }
     }
     else if (kind == PACK_S2D) { n_cols = c.nt; n_ent = 16; kspan = c.kb; if (cout > c.nt / 4) { set_error("pack(s2d): cout %d > %d", cout, c.nt / 4); return RRIN_ERR_BAD_SHAPE; } }
-    else if (kind == PACK_S2D8) {
+    else if (kind == PACK_S2D8 || kind == PACK_S2D8_CG2) {
         n_cols = c.nt; n_ent = 8; kspan = c.kb;
+        if ((kind == PACK_S2D8_CG2) != (c.cg == 2)) { set_error("pack(s2d8): kind %d does not match config %d (CTA-pair layout)", kind, cfg); return RRIN_ERR_BAD_ARG; }
+        if (kind == PACK_S2D8_CG2 && c.nt != 128) { set_error("pack(s2d8, pairs): NT must be 128"); return RRIN_ERR_BAD_ARG; }
         if (cout > c.nt / 4 || c.kcs != 2 * c.kb || (n_stages & 1)) { set_error("pack(s2d8): bad shape (cout %d, config %d, %d stages)", cout, cfg, n_stages); return RRIN_ERR_BAD_SHAPE; }
         if (cin > (n_stages / 2) * kspan) { set_error("pack(s2d8): cin %d does not fit %d stage pair(s) of %d", cin, n_stages / 2, kspan); return RRIN_ERR_BAD_SHAPE; }
     }
     else if (kind == PACK_FOLD) { n_cols = 4 * cout; n_ent = 9; kspan = c.kcs; if (c.kb != c.kcs || (4 * cout) % c.nt) { set_error("pack(fold): bad shape"); return RRIN_ERR_BAD_SHAPE; } }
     else { set_error("conv_pack_weights: bad kind %d", kind); return RRIN_ERR_BAD_ARG; }
-    if (n_stages < 1 || (kind != PACK_S2D8 && cin > n_stages * kspan)) { set_error("pack: cin %d does not fit %d stage(s) of %d", cin, n_stages, kspan); return RRIN_ERR_BAD_SHAPE; }
+    if (n_stages < 1 || (kind != PACK_S2D8 && kind != PACK_S2D8_CG2 && cin > n_stages * kspan)) { set_error("pack: cin %d does not fit %d stage(s) of %d", cin, n_stages, kspan); return RRIN_ERR_BAD_SHAPE; }
     const int n_ntiles = (n_cols + c.nt - 1) / c.nt;
-    pack_weights_kernel<<<256, 256, 0, stream>>>(kind, w, b, cout, cin, c.kcs, c.kb, c.nt, n_ntiles, n_stages, n_ent,
-                                                 reinterpret_cast<__nv_bfloat16*>(wpack), bias_pack);
+    pack_weights_kernel<<<256, 256, 0, stream>>>(kind, w, b, cout, cin, c.kcs, c.kb, c.nt, n_ntiles, n_stages, n_ent, f16 ? 1 : 0,
+                                                 reinterpret_cast<uint16_t*>(wpack), bias_pack);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
@@ -254,19 +230,9 @@ static int launch_cfg(int id, const ConvParams& p, int grid, cudaStream_t stream
     return RRIN_OK;
 }
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF>
-static int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
-                       const CUtensorMap& tmw, int grid, cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
-    const int dev = current_device();
-    if (dev < 0) { set_error("conv3x3: no current CUDA device"); return RRIN_ERR_CUDA; }
-    if (!g_attr_set[dev][id]) {
-        RRIN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        g_attr_set[dev][id] = true;
-    }
-    RRIN_CUDA_CHECK(launch_pdl(kern, grid, C::THREADS, C::SMEM_BYTES, stream, CG, p, tm0, tm1, tmo, tmw));
-    return RRIN_OK;
+int launch_v2_bf16(int cfg, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
+                   const CUtensorMap& tmw, int grid, cudaStream_t stream) {
+    return launch_v2_impl<0>(cfg, p, tm0, tm1, tmo, tmw, grid, stream);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -407,12 +373,7 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
         p.prof = prof_buf;
     }
 #endif
-    int rc = RRIN_ERR_BAD_ARG;
-    switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF) case id: rc = launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>(id, p, tm0, tm1, tmo, tmw, grid, stream); break;
-        RRIN_CONV2_CONFIGS(X)
-#undef X
-    }
+    const int rc = d.f16 ? launch_v2_f16(cfg, p, tm0, tm1, tmo, tmw, grid, stream) : launch_v2_bf16(cfg, p, tm0, tm1, tmo, tmw, grid, stream);
 #ifdef RRIN_DIAG
     if (prof_on && rc == RRIN_OK) {
         unsigned long long h[16 + 4 * 160];
@@ -500,6 +461,7 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream) {
     const long work = (long)p.n_ntiles * d.N * p.tiles_per_img;
     if (work > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
     p.total_work = (int)work;
+    p.f16 = d.f16 ? 1 : 0;
     p.b_resident = (!c.strip && p.n_ntiles == 1 && p.n_stages * p.n_ent <= c.sb) ? 1 : 0;   // strips permute weight blocks per item
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }

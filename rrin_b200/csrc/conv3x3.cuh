@@ -66,6 +66,7 @@ struct ConvParams {
     int tiles_per_img;           // tiles_x*tiles_y, or the ring count
     int total_work;              // n_ntiles * N * tiles_per_img
     int b_resident;              // all n_stages*n_ent weight blocks stay in SMEM (requires n_ntiles == 1)
+    int f16;                     // 16-bit format of activations / weights: 0 bf16, 1 fp16 (precision mode)
 };
 
 constexpr int kEpiWarps = 4;
@@ -111,31 +112,35 @@ __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
 }
 
 // mean of four 8-channel bf16 vectors: ((a+b)+c)+d then *0.25 (ATen avg_pool2d sums h-major, then divides)
-__device__ __forceinline__ uint4 avg4_bf16x8(uint4 a, uint4 b, uint4 c, uint4 d) {
+__device__ __forceinline__ uint4 avg4_bf16x8(uint4 a, uint4 b, uint4 c, uint4 d, int f16 = 0) {
     uint4 o;
     const uint32_t* pa = &a.x; const uint32_t* pb = &b.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
     uint32_t* po = &o.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 fa = unpack_bf16x2(pa[i]), fb = unpack_bf16x2(pb[i]), fc = unpack_bf16x2(pc[i]), fd = unpack_bf16x2(pd[i]);
-        po[i] = pack_bf16x2((((fa.x + fb.x) + fc.x) + fd.x) * 0.25f, (((fa.y + fb.y) + fc.y) + fd.y) * 0.25f);
+        float2 fa = unpack2_rt(f16, pa[i]), fb = unpack2_rt(f16, pb[i]), fc = unpack2_rt(f16, pc[i]), fd = unpack2_rt(f16, pd[i]);
+        po[i] = pack2_rt(f16, (((fa.x + fb.x) + fc.x) + fd.x) * 0.25f, (((fa.y + fb.y) + fc.y) + fd.y) * 0.25f);
     }
     return o;
 }
 // bilinear: wy0*(wx0*v00 + wx1*v01) + wy1*(wx0*v10 + wx1*v11)   (ATen upsample_bilinear2d order)
-__device__ __forceinline__ uint4 bilerp_bf16x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11, float wx1, float wy1) {
+template <int F16 = 0>
+__device__ __forceinline__ uint4 bilerp_x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11, float wx1, float wy1) {
     const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
     uint4 o;
     const uint32_t* p00 = &v00.x; const uint32_t* p01 = &v01.x; const uint32_t* p10 = &v10.x; const uint32_t* p11 = &v11.x;
     uint32_t* po = &o.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 a = unpack_bf16x2(p00[i]), b = unpack_bf16x2(p01[i]), c = unpack_bf16x2(p10[i]), d = unpack_bf16x2(p11[i]);
+        float2 a = unpack2<F16>(p00[i]), b = unpack2<F16>(p01[i]), c = unpack2<F16>(p10[i]), d = unpack2<F16>(p11[i]);
         float rx = wy0 * (wx0 * a.x + wx1 * b.x) + wy1 * (wx0 * c.x + wx1 * d.x);
         float ry = wy0 * (wx0 * a.y + wx1 * b.y) + wy1 * (wx0 * c.y + wx1 * d.y);
-        po[i] = pack_bf16x2(rx, ry);
+        po[i] = pack2<F16>(rx, ry);
     }
     return o;
+}
+__device__ __forceinline__ uint4 bilerp_bf16x8(uint4 v00, uint4 v01, uint4 v10, uint4 v11, float wx1, float wy1, int f16 = 0) {
+    return f16 ? bilerp_x8<1>(v00, v01, v10, v11, wx1, wy1) : bilerp_x8<0>(v00, v01, v10, v11, wx1, wy1);
 }
 // source index / weight of nn.Upsample(bilinear, x2, align_corners=False) for output index o
 // (ATen/native/UpSample.h:289-314,443-476): src = max((o+0.5)/2-0.5, 0); i1 = i0 + (i0 < size-1)
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                         for (int u = 0; u < U; ++u) {
                             const int q = px + u * PXSTEP;
                             if (q < C::HALO_PX) {
-                                uint4 o = okk[u] ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3]) : make_uint4(0, 0, 0, 0);
+                                uint4 o = okk[u] ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], p.f16) : make_uint4(0, 0, 0, 0);
                                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + q * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                             }
                         }
@@ -356,8 +361,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                             const int q = px + u * PXSTEP;
                             if (q < C::HALO_PX) {
                                 uint4 o = make_uint4(0, 0, 0, 0);
-                                if (okk[u]) o = pool ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3])
-                                                     : bilerp_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], wx[u], wy[u]);
+                                if (okk[u]) o = pool ? avg4_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], p.f16)
+                                                     : bilerp_bf16x8(v[u][0], v[u][1], v[u][2], v[u][3], wx[u], wy[u], p.f16);
                                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + q * 16), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                             }
                         }
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
         if (elect_one()) {
             constexpr bool S2D = (KB != KCS);
             constexpr int N_ENT = S2D ? 16 : 9;
-            constexpr uint32_t idesc = make_idesc_bf16(128, NT);
+            const uint32_t idesc = make_idesc_ab(128, NT, p.f16);
             const uint64_t a_desc0 = make_smem_desc(0, C::PS, STRIP ? 128 : C::PW * 16);   // strip: 8-row groups are 8 positions apart
             const uint64_t b_desc0 = make_smem_desc(0, NT * 16, 128);
             const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                             float v0 = __uint_as_float(ra[2 * i]) + bsrc[c + 2 * i];
                             float v1 = __uint_as_float(ra[2 * i + 1]) + bsrc[c + 2 * i + 1];
                             if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                            o[i] = pack_bf16x2(v0, v1);
+                            o[i] = pack2_rt(p.f16, v0, v1);
                         }
                         if (NT >= 32) {
 #pragma unroll
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3x3_umma_kernel(const __g
                                 float v0 = __uint_as_float(rb[2 * i]) + bsrc[c + 16 + 2 * i];
                                 float v1 = __uint_as_float(rb[2 * i + 1]) + bsrc[c + 16 + 2 * i + 1];
                                 if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                                o[8 + i] = pack_bf16x2(v0, v1);
+                                o[8 + i] = pack2_rt(p.f16, v0, v1);
                             }
                         }
                         if (ok) {

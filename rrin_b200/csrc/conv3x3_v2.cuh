@@ -97,8 +97,10 @@ constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32
 // CG   : 1 = one CTA per tile.  2 = CTA pair (cluster of 2, tcgen05 cta_group::2): the leader's MMA thread issues M = 256
 //        MMAs over both CTAs' sub-tiles; each CTA stages its own activation halo but only HALF of every weight block
 //        (N/2 rows), so the per-SM shared-memory operand traffic of an MMA drops from 8 KB to 6 KB per 64 cycles and the
-//        weight stream per SM halves (N = 64: 6 KB -> 5 KB per 48 cycles).  Streamed 9-tap schedule only; pair tiles
-//        are even-sized (TileWalkV2).
+//        weight stream per SM halves (N = 64: 6 KB -> 5 KB per 48 cycles).  Streamed 9-tap schedule, or the resident
+//        half-phase schedule of level 0: a pair keeps the layer's weights resident with half of the bytes per SM
+//        (32->32: 48 KB instead of 96 KB, which buys larger halo tiles; cat(32+32)->32: 96 KB per SM instead of
+//        re-streaming 192 KB per tile).  Pair tiles are even-sized (TileWalkV2).
 // XF   : 1 = the A operand is the exact bilinear x2 upsample (nn.Upsample, align_corners=False, unet.py:77) of a coarser
 //        NHWC tensor: TMA stages the raw coarse tile [10 rows][4*MSUB+2 px][64 ch] in shared memory, four transform
 //        warps interpolate it into the swizzled halo tile (shared-memory reads instead of global-load latency).
@@ -113,7 +115,8 @@ struct ConvCfgV2 {
     static constexpr int A_STAGE = BOXES * BOX_STRIDE;
     static constexpr int B_BLOCK = NT * KB * 2 / CG;   // bytes of a weight block held by ONE CTA
     static constexpr bool HALF = (SCHED == 2 && NT == 128);
-    static_assert(CG == 1 || (CG == 2 && SCHED == 0 && !RES && (NT == 128 || NT == 64)), "CTA pairs: streamed 9-tap schedule, N = 128 or 64");
+    static_assert(CG == 1 || (CG == 2 && SCHED == 0 && !RES && (NT == 128 || NT == 64)) || (CG == 2 && SCHED == 2 && RES && NT == 128),
+                  "CTA pairs: streamed 9-tap schedule (N = 128 or 64), or the resident half-phase schedule (level 0: each CTA keeps half of every weight block)");
     static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
     static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;
     static constexpr int THREADS = v2_threads(EW, XF);
@@ -132,7 +135,7 @@ struct ConvCfgV2 {
     static constexpr int OFF_RAW = OFF_EPI + EPI_STAGE;                 // 1024-byte aligned
     static constexpr int OFF_BIAS = OFF_RAW + RAW_SLOTS * RAW_STRIDE;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
-    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS;
+    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS + 1;   // + "resident weights of both CTAs have landed" (pairs)
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
     static_assert(KCS == 64 || (KCS == 32 && SCHED == 0 && CG == 1 && !XF), "one 64-channel TMA box per stage (32: a 32-channel NHWC source)");
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
@@ -209,7 +212,8 @@ struct TileWalkV2 {
     }
 };
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF>
+// F16 : 16-bit format of activations and weights: 0 bf16 (default) | 1 fp16 (precision mode); same kernel otherwise
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16>
 __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
     auto acc_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + C::SLOTS + i); };
     auto raw_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + i); };
     auto raw_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + C::RAW_SLOTS + i); };
+    const uint32_t w_ready = s_bar + 8u * (C::NBAR - 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
 
     // diagnostics (timing knobs that give wrong results, per-role cycle counters) exist only in -DRRIN_DIAG builds
@@ -257,6 +262,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
         for (int i = 0; i < C::RAW_SLOTS; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), CG * kEpiWarps * 32); }   // both CTAs' epilogues
+        mbar_init(w_ready, CG);
         mbar_fence_init();
     }
     if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); if (CG == 2) tma_prefetch_desc(&tmw); }
@@ -337,8 +343,14 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         const bool odd = (SCHED == 2) && (st & 1);
                         const uint32_t bytes = (odd ? C::half_of(1, e) : C::half_of(0, e)) ? C::B_BLOCK / 2 : C::B_BLOCK;
                         mbar_arrive_expect_tx(b_full(b), bytes);
-                        bulk_g2s(s_b + st * C::B_STAGE + (odd ? C::res_off(1, e) : C::res_off(0, e)), p.wpack + (size_t)b * (NT * KB), bytes, b_full(b));
+                        // pairs: the block is stored as two halves (N/2 weight rows each), one per CTA of the pair
+                        bulk_g2s(s_b + st * C::B_STAGE + (odd ? C::res_off(1, e) : C::res_off(0, e)),
+                                 p.wpack + (size_t)b * (NT * KB) + (CG == 2 ? cta_rank * (bytes / 2) : 0u), bytes, b_full(b));
                     }
+                }
+                if (CG == 2) {      // the leader's MMAs read both CTAs' halves: tell it when this CTA's have landed
+                    for (int b = 0; b < nblk; ++b) mbar_wait(b_full(b), 0);
+                    mbar_arrive_cluster(mapa_shared(w_ready, 0));
                 }
             } else {
                 // The layer's weights are cold in L2 at launch and every CTA walks the same block sequence, so each
@@ -385,10 +397,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
         // (no per-entry warp re-convergence; entries, K steps and their descriptor offsets are compile-time)
         // CTA pairs: only the leader issues (M = 256 over both CTAs); its commits arrive on both CTAs' barriers.
         if (cta_rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128 * CG, NT), idesc_h = make_idesc_bf16(128, 64);
+            constexpr uint32_t idesc = make_idesc_ab(128 * CG, NT, F16), idesc_h = make_idesc_ab(128 * CG, 64, F16);
             constexpr int NB = NT / CG;                 // weight-block rows (N) held per CTA
             const uint64_t a_desc0 = (KCS == 32) ? make_smem_desc_sw64(0, C::PW * 64) : make_smem_desc_sw128(0, C::PW * 128);
-            const uint64_t b_desc0 = make_smem_desc(0, NB * 16, 128), b_desc0h = make_smem_desc(0, 64 * 16, 128);
+            const uint64_t b_desc0 = make_smem_desc(0, NB * 16, 128), b_desc0h = make_smem_desc(0, (64 / CG) * 16, 128);
             auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t id, uint32_t acc) {
                 if (CG == 2) umma_bf16_lh_cg2(d, alo, ahi, blo, bhi, id, acc); else umma_bf16_lh(d, alo, ahi, blo, bhi, id, acc);
             };
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
                     }
                     const uint32_t a_e = a_st + C::ent_off(PAR, e);
-                    const uint32_t b_ks = hf ? 2 * 64 : 2 * (NT / CG);        // descriptor step per K=16: two core-matrix planes
+                    const uint32_t b_ks = hf ? 2 * (64 / CG) : 2 * (NT / CG);  // descriptor step per K=16: two core-matrix planes
                     const uint32_t id = hf ? idesc_h : idesc;
                     const uint32_t dcol = (hf == 2) ? 64 : 0;
                     const long long cm0 = prof ? clock64() : 0;
@@ -460,6 +472,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 if constexpr (MSUB >= 3) { if (m == 3) run_stage(par_c, std::integral_constant<int, 3>{}, st, first_stage, stage); }
                 if constexpr (MSUB >= 4) { if (m == 4) run_stage(par_c, std::integral_constant<int, 4>{}, st, first_stage, stage); }
             };
+            if (CG == 2 && RES) mbar_wait(w_ready, 0);      // pairs with resident weights: both CTAs' halves are in place
             while (walk.next<MSUB, CG>(p, t)) {
                 const int m = t.m;
                 const int st_rot = rot_of(t);
@@ -534,7 +547,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                             int i0, i1; float wy, wx;
                             up2_taps(gy, sh, i0, i1, wy);
                             up2_taps(gx, sw, i0, i1, wx);
-                            o = bilerp_bf16x8(v00, v01, v10, v11, wx, wy);
+                            o = bilerp_x8<F16>(v00, v01, v10, v11, wx, wy);
                         }
                         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + q * 128 + ((c8 ^ (q & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
                     }
@@ -607,10 +620,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
 #pragma unroll
                                     for (int q = 0; q < 8; ++q) v[q] = v[q] >= 0.f ? v[q] : 0.1f * v[q];
                                 }
-                                o[16 * h + 2 * i] = pack_bf16x2(v[0], v[1]);
-                                o[16 * h + 2 * i + 1] = pack_bf16x2(v[2], v[3]);
-                                o[16 * h + 8 + 2 * i] = pack_bf16x2(v[4], v[5]);
-                                o[16 * h + 8 + 2 * i + 1] = pack_bf16x2(v[6], v[7]);
+                                o[16 * h + 2 * i] = pack2<F16>(v[0], v[1]);
+                                o[16 * h + 2 * i + 1] = pack2<F16>(v[2], v[3]);
+                                o[16 * h + 8 + 2 * i] = pack2<F16>(v[4], v[5]);
+                                o[16 * h + 8 + 2 * i + 1] = pack2<F16>(v[6], v[7]);
                             }
                         }
                         if (lane == 0) bulk_wait_group_read<0>();       // the previous store has finished reading the buffer
@@ -631,14 +644,14 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                 // ATen's avg_pool2d: ((p0 + p1) + p2) + p3.  This chunk holds phases c/32 and c/32 + 1.
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
-                                    const float2 a = unpack_bf16x2(o[i]), b = unpack_bf16x2(o[16 + i]);
+                                    const float2 a = unpack2<F16>(o[i]), b = unpack2<F16>(o[16 + i]);
                                     if (c == 0) { pacc[2 * i] = a.x + b.x; pacc[2 * i + 1] = a.y + b.y; }
                                     else { pacc[2 * i] = (pacc[2 * i] + a.x) + b.x; pacc[2 * i + 1] = (pacc[2 * i + 1] + a.y) + b.y; }
                                 }
                                 if (c == NT - 64 && ok) {
                                     __nv_bfloat16* d = p.pool_out + pix * (size_t)(NT / 4);        // 64 bytes per pooled pixel
-                                    stg256_bf16x16(d, pacc, 0.25f);
-                                    stg256_bf16x16(d + 16, pacc + 16, 0.25f);
+                                    stg256_x16<F16>(d, pacc, 0.25f);
+                                    stg256_x16<F16>(d + 16, pacc + 16, 0.25f);
                                 }
                             } else {
                                 // 2x2 mean over this warp's 4 x 8 pixels from the staged bf16 tile: lane -> pooled pixel
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                         const uint32_t vv[4] = {v0, v1, v2, v3};
 #pragma unroll
                                         for (int i = 0; i < 4; ++i) {
-                                            const float2 f = unpack_bf16x2(vv[i]);
+                                            const float2 f = unpack2<F16>(vv[i]);
                                             if (dd == 0) { acc[8 * kk + 2 * i] = f.x; acc[8 * kk + 2 * i + 1] = f.y; }
                                             else { acc[8 * kk + 2 * i] += f.x; acc[8 * kk + 2 * i + 1] += f.y; }
                                         }
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                                 }
                                 const int py = (t.ty * kTileH + 4 * quad) / 2 + pyl, px = (t.sx0 + j) * 4 + pxl;
                                 if (py < (p.H >> 1) && px < (p.W >> 1)) {
-                                    stg256_bf16x16(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride + t.nt * NT + c + 16 * q,
+                                    stg256_x16<F16>(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride + t.nt * NT + c + 16 * q,
                                                    acc, 0.25f);
                                 }
                             }
@@ -692,18 +705,18 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         if (fz.mode == 1) {              // t.n = pair; every sample of that pair gets its refine_flow head input
                             const int s0 = fz.pair_mul ? t.n : 0, s1 = fz.pair_mul ? t.n + 1 : fz.Nt;
                             for (int sn = s0; sn < s1; ++sn)
-                                glue_tscale_block(v, fz.in0 + (long)t.n * 3 * HW, fz.in1 + (long)t.n * 3 * HW, fz.coef + sn * 6, HW, fz.W, gy, gx,
+                                glue_tscale_block<F16>(v, fz.in0 + (long)t.n * 3 * HW, fz.in1 + (long)t.n * 3 * HW, fz.coef + sn * 6, HW, fz.W, gy, gx,
                                                   fz.h16 + ((long)sn * nb + q) * 64);
                         } else if (fz.mode == 2) {       // t.n = sample
                             const long pn = (long)t.n * fz.pair_mul;
                             float4 f[4];
 #pragma unroll
                             for (int ph = 0; ph < 4; ++ph) f[ph] = fz.aux[(pn * nb + q) * 4 + ph];
-                            glue_warp_block(f, v, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
+                            glue_warp_block<F16>(f, v, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
                                             fz.h16 + ((long)t.n * nb + q) * 64, reinterpret_cast<float4*>(fz.dst) + ((long)t.n * nb + q) * 8);
                         } else if (fz.mode == 3) {
                             const long pn = (long)t.n * fz.pair_mul, i = (long)t.n * nb + q;
-                            glue_blend_block(v, fz.aux + i * 8, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef[t.n * 6 + 4], fz.coef[t.n * 6 + 5],
+                            glue_blend_block<F16>(v, fz.aux + i * 8, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef[t.n * 6 + 4], fz.coef[t.n * 6 + 5],
                                              HW, fz.W, gy, gx, reinterpret_cast<float4*>(fz.dst) + i * 4, fz.h16 + i * 64);
                         } else if (fz.mode == 4) {
                             const long i = (long)t.n * nb + q;
@@ -727,14 +740,14 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                             float v0 = __uint_as_float(ra[2 * i]) + bsrc[c + 2 * i];
                             float v1 = __uint_as_float(ra[2 * i + 1]) + bsrc[c + 2 * i + 1];
                             if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                            o[i] = pack_bf16x2(v0, v1);
+                            o[i] = pack2<F16>(v0, v1);
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float v0 = __uint_as_float(rb[2 * i]) + bsrc[c + 16 + 2 * i];
                             float v1 = __uint_as_float(rb[2 * i + 1]) + bsrc[c + 16 + 2 * i + 1];
                             if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                            o[8 + i] = pack_bf16x2(v0, v1);
+                            o[8 + i] = pack2<F16>(v0, v1);
                         }
                         if (ok) {
                             __nv_bfloat16* op;

@@ -89,6 +89,23 @@ static bool l1_pair() {
     return on;
 }
 
+// level-0 32->32 and cat(32+32)->32 convs on CTA pairs with resident half-blocks (configs 23 / 24): RRIN_L0_PAIR=0 selects the
+// single-CTA configs 11 / 12; RRIN_L0_PAIR=<a>,<b> picks explicit config ids for the two layer kinds (A/B runs: 23|26 and 24|25)
+static void l0_pair_cfgs(int& c32, int& ccat) {
+    static int a = -1, b = -1;
+    if (a < 0) {
+        a = 23; b = 24;
+        const char* e = getenv("RRIN_L0_PAIR");
+        if (e) {
+            int x = 0, y = 0;
+            const int n = sscanf(e, "%d,%d", &x, &y);
+            if (n == 1 && x == 0) { a = 11; b = 12; }
+            else if (n == 2) { a = (x == 23 || x == 26 || x == 11) ? x : 23; b = (y == 24 || y == 25 || y == 12) ? y : 24; }
+        }
+    }
+    c32 = a; ccat = b;
+}
+
 static Schedule build_schedule() {
     Schedule s;
     size_t off = 0;
@@ -109,7 +126,12 @@ static Schedule build_schedule() {
             m.n_cols = is_last ? 16 : 128;
             if (src == K_HEAD) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 10; m.n_stages = 1; }
             else if (src == K_UP) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 1; m.n_stages = cin / 32; }   // exact bilinear (ring / small frames)
-            else { m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? 13 : (cin == 32 ? 11 : 12); m.n_stages = 2 * (cin / 32); }
+            else {
+                int c32, ccat;
+                l0_pair_cfgs(c32, ccat);
+                m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? 13 : (cin == 32 ? c32 : ccat); m.n_stages = 2 * (cin / 32);
+                if (m.cfg >= 23) m.kind = PACK_S2D8_CG2;
+            }
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
             // K_POOL sources are read from the pooled copy the previous level's block.2 epilogue wrote: plain convs
@@ -191,6 +213,7 @@ using namespace rrin;
 // ------------------------------------------------------------------ engine object
 struct rrin_engine {
     int Np, Nt, H, W, pair_mul;
+    int f16 = 0;                                // operand / activation format (RRIN_PRECISION_*)
     size_t ws_bytes;
     size_t off_tmp[3], off_skip[4], off_pool[4], off_h16, off_flow4, off_u4, off_out4, off_xt8;
     std::vector<Launch> launches;
@@ -208,7 +231,7 @@ struct rrin_engine {
     cudaStream_t cap_stream = nullptr;          // capture happens on a private stream (torch's default stream is the legacy stream,
     int cap_dev = -1;                           // which cannot be captured); the instantiated graph launches into any stream
     unsigned long long tick = 0;
-    int graph_launches = 0, direct_launches = 0;
+    int graph_launches = 0, direct_launches = 0, captures = 0;
 };
 
 static inline void mark(rrin_engine* e, cudaStream_t st) {
@@ -361,30 +384,46 @@ int rrin_conv_info(int idx, char* key, int key_cap, int* cin, int* cout, int* le
 size_t rrin_packed_weights_bytes(void) { return schedule().blob_bytes; }
 
 int rrin_pack_conv(int idx, const float* w, const float* b, void* blob, void* stream) {
+    return rrin_pack_conv_ex(idx, w, b, blob, RRIN_PRECISION_BF16, stream);
+}
+
+static int check_precision(const char* who, int precision) {
+    if (precision != RRIN_PRECISION_BF16 && precision != RRIN_PRECISION_FP16) { set_error("%s: unknown precision %d", who, precision); return RRIN_ERR_BAD_ARG; }
+    return RRIN_OK;
+}
+
+int rrin_pack_conv_ex(int idx, const float* w, const float* b, void* blob, int precision, void* stream) {
+    if (int r = check_precision("rrin_pack_conv_ex", precision)) return r;
+    const int f16 = precision == RRIN_PRECISION_FP16;
     const Schedule& s = schedule();
     if (idx < 0 || idx >= (int)s.layers.size() || !w || !b || !blob) { set_error("rrin_pack_conv: bad argument"); return RRIN_ERR_BAD_ARG; }
     const Layer& L = s.layers[idx];
     uint8_t* base = static_cast<uint8_t*>(blob);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int r = conv_pack_weights(L.main.kind, w, b, L.cout, L.cin, L.main.n_stages, L.main.cfg, base + L.main.w_off,
-                              reinterpret_cast<float*>(base + L.main.b_off), st);
+                              reinterpret_cast<float*>(base + L.main.b_off), st, f16);
     if (r == RRIN_OK && L.fold.kind >= 0)
         r = conv_pack_weights(L.fold.kind, w, b, L.cout, L.cin, L.fold.n_stages, L.fold.cfg, base + L.fold.w_off,
-                              reinterpret_cast<float*>(base + L.fold.b_off), st);
+                              reinterpret_cast<float*>(base + L.fold.b_off), st, f16);
     if (r == RRIN_OK && L.strip.kind >= 0)
         r = conv_pack_weights(L.strip.kind, w, b, L.cout, L.cin, L.strip.n_stages, L.strip.cfg, base + L.strip.w_off,
-                              reinterpret_cast<float*>(base + L.strip.b_off), st);
+                              reinterpret_cast<float*>(base + L.strip.b_off), st, f16);
     return r;
 }
 
 int rrin_engine_create(int n_pairs, int n_samples, int H, int W, rrin_engine** out) {
+    return rrin_engine_create_ex(n_pairs, n_samples, H, W, RRIN_PRECISION_BF16, out);
+}
+
+int rrin_engine_create_ex(int n_pairs, int n_samples, int H, int W, int precision, rrin_engine** out) {
+    if (int r = check_precision("rrin_engine_create_ex", precision)) return r;
     if (!out) { set_error("rrin_engine_create: null out"); return RRIN_ERR_BAD_ARG; }
     *out = nullptr;
     if (n_pairs <= 0 || n_samples <= 0 || H <= 0 || W <= 0) { set_error("rrin_engine_create: empty shape"); return RRIN_ERR_BAD_SHAPE; }
     if (H % 16 || W % 16) { set_error("H and W must be multiples of 16 (got %dx%d)", H, W); return RRIN_ERR_BAD_SHAPE; }
     if (n_pairs != n_samples && n_pairs != 1) { set_error("n_pairs must equal n_samples or be 1 (got %d, %d)", n_pairs, n_samples); return RRIN_ERR_BAD_SHAPE; }
     rrin_engine* e = new rrin_engine();
-    e->Np = n_pairs; e->Nt = n_samples; e->H = H; e->W = W;
+    e->Np = n_pairs; e->Nt = n_samples; e->H = H; e->W = W; e->f16 = precision == RRIN_PRECISION_FP16;
     e->pair_mul = (n_pairs == n_samples) ? 1 : 0;
     const int B = n_pairs > n_samples ? n_pairs : n_samples;
     const size_t px = (size_t)H * W;
@@ -470,10 +509,10 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
         int r = RRIN_OK;
         if (ln.glue >= 0) {
             switch (ln.glue) {
-                case 0: r = pack_pair(in0, in1, Np, H, W, h16, st); break;
-                case 1: r = flow_tscale_pack(flow4, in0, in1, coef, Nt, pm, H, W, h16, st); break;
-                case 2: r = warp_pack(flow4, u4, in0, in1, coef, Nt, pm, H, W, h16, xt8, st); break;
-                case 3: r = blend_pack(u4, xt8, in0, in1, coef, Nt, pm, H, W, out4, h16, st); break;
+                case 0: r = pack_pair(in0, in1, Np, H, W, h16, st, e->f16); break;
+                case 1: r = flow_tscale_pack(flow4, in0, in1, coef, Nt, pm, H, W, h16, st, e->f16); break;
+                case 2: r = warp_pack(flow4, u4, in0, in1, coef, Nt, pm, H, W, h16, xt8, st, e->f16); break;
+                case 3: r = blend_pack(u4, xt8, in0, in1, coef, Nt, pm, H, W, out4, h16, st, e->f16); break;
                 case 4: r = residue_clamp(u4, out4, Nt, H, W, out, st); break;
             }
         } else {
@@ -482,6 +521,7 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
             ConvDesc cd = ln.cd;
             cd.src0 = dec(cd.src0); cd.src1 = dec(cd.src1); cd.out = dec(cd.out); cd.pool_out = dec(cd.pool_out);
             cd.wpack = blob + pk.w_off;
+            cd.f16 = e->f16;
             cd.bias = reinterpret_cast<const float*>(blob + pk.b_off);
             if (cd.cfg >= 10) { cd.tmap0 = ln.tmap[0]; cd.tmap1 = ln.tmap[1]; cd.tmap_out = ln.tmap[2]; }
             if (ln.fuse_mode) {
@@ -541,8 +581,14 @@ int rrin_engine_forward_graph(rrin_engine* e, const void* blob, void* workspace,
         ++e->direct_launches;
         return rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
     }
-    // second sighting: capture the launch sequence on the private stream and instantiate it
+    // second sighting: capture the launch sequence on the private stream and instantiate it -- unless this caller keeps
+    // producing new pointer sets (captures that are hardly ever replayed): then stay on direct launches
     hit->last_use = e->tick;
+    if (e->captures >= 32 && e->graph_launches < 4 * e->captures) {
+        ++e->direct_launches;
+        return rrin_engine_forward(e, blob, workspace, in0, in1, coef, out, stream);
+    }
+    ++e->captures;
     if (e->cap_stream && e->cap_dev != dev) { cudaStreamDestroy(e->cap_stream); e->cap_stream = nullptr; }
     if (!e->cap_stream) { RRIN_CUDA_CHECK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking)); e->cap_dev = dev; }
     cudaGraph_t graph = nullptr;
@@ -635,10 +681,23 @@ int rrin_pack_conv_raw(int kind, const float* w, const float* b, int cout, int c
                        float* bias_pack, void* stream) {
     return conv_pack_weights(kind, w, b, cout, cin, n_stages, cfg, wpack, bias_pack, static_cast<cudaStream_t>(stream));
 }
+int rrin_pack_conv_raw_ex(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg, void* wpack,
+                          float* bias_pack, int precision, void* stream) {
+    if (int r = check_precision("rrin_pack_conv_raw_ex", precision)) return r;
+    return conv_pack_weights(kind, w, b, cout, cin, n_stages, cfg, wpack, bias_pack, static_cast<cudaStream_t>(stream), precision == RRIN_PRECISION_FP16);
+}
 int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                  int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
                  int act, int ring_only, int cfg, void* pool_out, void* stream) {
+    return rrin_conv3x3_ex(src0, src1, c0, c1, src_mode, pad_clamp, N, H, W, sched, n_cols, wpack, bias_pack, out, epi, cout_stride, act,
+                           ring_only, cfg, pool_out, RRIN_PRECISION_BF16, stream);
+}
+int rrin_conv3x3_ex(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
+                    int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
+                    int act, int ring_only, int cfg, void* pool_out, int precision, void* stream) {
+    if (int r = check_precision("rrin_conv3x3_ex", precision)) return r;
     ConvDesc cd;
+    cd.f16 = precision == RRIN_PRECISION_FP16;
     cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = src_mode; cd.pad_clamp = pad_clamp;
     cd.N = N; cd.H = H; cd.W = W; cd.sched = sched; cd.n_cols = n_cols; cd.wpack = wpack; cd.bias = bias_pack;
     cd.out = out; cd.epi = epi; cd.cout_stride = cout_stride; cd.act = act; cd.ring_only = ring_only; cd.cfg = cfg; cd.pool_out = pool_out;

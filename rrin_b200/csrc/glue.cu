@@ -31,6 +31,7 @@ static inline int glue_grid(long items) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (total_blocks); i += (long)gridDim.x * blockDim.x)
 
 // ------------------------------------------------------------------ K6: cat(x0, x1) -> Flow head input
+template <int F16>
 __global__ void __launch_bounds__(kGlueThreads) pack_pair_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
                                                                   int N, int H, int W, __nv_bfloat16* __restrict__ x16) {
     const int Hb = H >> 1, Wb = W >> 1;
@@ -44,12 +45,13 @@ __global__ void __launch_bounds__(kGlueThreads) pack_pair_kernel(const float* __
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) {
             float v[16] = {a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            store_bf16x16(x16 + (i * 4 + ph) * 16, v);
+            store_x16<F16>(x16 + (i * 4 + ph) * 16, v);
         }
     }
 }
 
 // ------------------------------------------------------------------ K2: cat(F_t0, F_t1, x) -> refine_flow head input
+template <int F16>
 __global__ void __launch_bounds__(kGlueThreads) flow_tscale_pack_kernel(const float4* __restrict__ flow4, const float* __restrict__ in0,
                                                                         const float* __restrict__ in1, const float* __restrict__ coef,
                                                                         int Nt, int pair_mul, int H, int W, __nv_bfloat16* __restrict__ r16) {
@@ -61,11 +63,12 @@ __global__ void __launch_bounds__(kGlueThreads) flow_tscale_pack_kernel(const fl
         float4 f[4];
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) f[ph] = flow4[(pn * nb + q) * 4 + ph];
-        glue_tscale_block(f, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef + n * 6, HW, W, by, bx, r16 + i * 64);
+        glue_tscale_block<F16>(f, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef + n * 6, HW, W, by, bx, r16 + i * 64);
     }
 }
 
 // ------------------------------------------------------------------ K3: residue add + two backward warps
+template <int F16>
 __global__ void __launch_bounds__(kGlueThreads) warp_pack_kernel(const float4* __restrict__ flow4, const float4* __restrict__ res4,
                                                                  const float* __restrict__ in0, const float* __restrict__ in1,
                                                                  const float* __restrict__ coef, int Nt, int pair_mul, int H, int W,
@@ -78,11 +81,12 @@ __global__ void __launch_bounds__(kGlueThreads) warp_pack_kernel(const float4* _
         float4 f[4], r[4];
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) { f[ph] = flow4[(pn * nb + q) * 4 + ph]; r[ph] = res4[i * 4 + ph]; }
-        glue_warp_block(f, r, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef + n * 6, HW, H, W, by, bx, m16 + i * 64, xt8 + i * 8);
+        glue_warp_block<F16>(f, r, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef + n * 6, HW, H, W, by, bx, m16 + i * 64, xt8 + i * 8);
     }
 }
 
 // ------------------------------------------------------------------ K4: sigmoid + occlusion-weighted blend
+template <int F16>
 __global__ void __launch_bounds__(kGlueThreads) blend_pack_kernel(const float4* __restrict__ mask4, const float4* __restrict__ xt8,
                                                                   const float* __restrict__ in0, const float* __restrict__ in1,
                                                                   const float* __restrict__ coef, int Nt, int pair_mul, int H, int W,
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(kGlueThreads) blend_pack_kernel(const float4* 
         float4 mk[4];
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) mk[ph] = mask4[i * 4 + ph];
-        glue_blend_block(mk, xt8 + i * 8, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef[n * 6 + 4], coef[n * 6 + 5], HW, W, by, bx,
+        glue_blend_block<F16>(mk, xt8 + i * 8, in0 + pn * 3 * HW, in1 + pn * 3 * HW, coef[n * 6 + 4], coef[n * 6 + 5], HW, W, by, bx,
                          out4 + i * 4, f16 + i * 64);
     }
 }
@@ -202,37 +206,37 @@ static int check_align32(const char* who, std::initializer_list<const void*> ptr
     return RRIN_OK;
 }
 
-int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s) {
+int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s, int f16) {
     if (int e = check_dims("pack_pair", N, H, W)) return e;
     if (int e = check_align32("pack_pair", {x16})) return e;
-    RRIN_CUDA_CHECK(launch_pdl(pack_pair_kernel, glue_grid(nblocks(N, H, W)), kGlueThreads, 0, s, 1, in0, in1, N, H, W, reinterpret_cast<__nv_bfloat16*>(x16)));
+    RRIN_CUDA_CHECK(launch_pdl(f16 ? pack_pair_kernel<1> : pack_pair_kernel<0>, glue_grid(nblocks(N, H, W)), kGlueThreads, 0, s, 1, in0, in1, N, H, W, reinterpret_cast<__nv_bfloat16*>(x16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
 int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, const float* coef, int Nt, int pair_mul,
-                     int H, int W, void* r16, cudaStream_t s) {
+                     int H, int W, void* r16, cudaStream_t s, int f16) {
     if (int e = check_dims("flow_tscale_pack", Nt, H, W)) return e;
     if (int e = check_align32("flow_tscale_pack", {r16, flow4})) return e;
-    RRIN_CUDA_CHECK(launch_pdl(flow_tscale_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(flow4), in0, in1, coef, Nt,
+    RRIN_CUDA_CHECK(launch_pdl(f16 ? flow_tscale_pack_kernel<1> : flow_tscale_pack_kernel<0>, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(flow4), in0, in1, coef, Nt,
                                                                                  pair_mul, H, W, reinterpret_cast<__nv_bfloat16*>(r16)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
 int warp_pack(const float* flow4, const float* res4, const float* in0, const float* in1, const float* coef, int Nt,
-              int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s) {
+              int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s, int f16) {
     if (int e = check_dims("warp_pack", Nt, H, W)) return e;
     if (int e = check_align32("warp_pack", {m16, xt8, flow4, res4})) return e;
-    RRIN_CUDA_CHECK(launch_pdl(warp_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1,
+    RRIN_CUDA_CHECK(launch_pdl(f16 ? warp_pack_kernel<1> : warp_pack_kernel<0>, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1,
         reinterpret_cast<const float4*>(flow4), reinterpret_cast<const float4*>(res4), in0, in1, coef, Nt, pair_mul, H, W,
         reinterpret_cast<__nv_bfloat16*>(m16), reinterpret_cast<float4*>(xt8)));
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }
 int blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef, int Nt,
-               int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s) {
+               int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s, int use_f16) {
     if (int e = check_dims("blend_pack", Nt, H, W)) return e;
     if (int e = check_align32("blend_pack", {f16, out4, mask4, xt8})) return e;
-    RRIN_CUDA_CHECK(launch_pdl(blend_pack_kernel, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
+    RRIN_CUDA_CHECK(launch_pdl(use_f16 ? blend_pack_kernel<1> : blend_pack_kernel<0>, glue_grid(nblocks(Nt, H, W)), kGlueThreads, 0, s, 1, reinterpret_cast<const float4*>(mask4), reinterpret_cast<const float4*>(xt8),
                                                                            in0, in1, coef, Nt, pair_mul, H, W, reinterpret_cast<float4*>(out4),
                                                                            reinterpret_cast<__nv_bfloat16*>(f16)));
     RRIN_CUDA_CHECK(cudaGetLastError());

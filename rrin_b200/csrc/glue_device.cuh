@@ -15,14 +15,16 @@ __device__ __forceinline__ void stg256(void* dst, const float4& a, const float4&
     stg256(dst, __float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w),
            __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
 }
-__device__ __forceinline__ void stg256_bf16x16(void* dst, const float* v, float scale) {       // 16 floats * scale -> 16 bf16
-    stg256(dst, pack_bf16x2(v[0] * scale, v[1] * scale), pack_bf16x2(v[2] * scale, v[3] * scale), pack_bf16x2(v[4] * scale, v[5] * scale),
-           pack_bf16x2(v[6] * scale, v[7] * scale), pack_bf16x2(v[8] * scale, v[9] * scale), pack_bf16x2(v[10] * scale, v[11] * scale),
-           pack_bf16x2(v[12] * scale, v[13] * scale), pack_bf16x2(v[14] * scale, v[15] * scale));
+template <int F16>
+__device__ __forceinline__ void stg256_x16(void* dst, const float* v, float scale) {       // 16 floats * scale -> 16 bf16 / fp16
+    stg256(dst, pack2<F16>(v[0] * scale, v[1] * scale), pack2<F16>(v[2] * scale, v[3] * scale), pack2<F16>(v[4] * scale, v[5] * scale),
+           pack2<F16>(v[6] * scale, v[7] * scale), pack2<F16>(v[8] * scale, v[9] * scale), pack2<F16>(v[10] * scale, v[11] * scale),
+           pack2<F16>(v[12] * scale, v[13] * scale), pack2<F16>(v[14] * scale, v[15] * scale));
 }
-__device__ __forceinline__ void store_bf16x16(void* dst, const float (&v)[16]) {
-    stg256(dst, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]),
-           pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+template <int F16>
+__device__ __forceinline__ void store_x16(void* dst, const float (&v)[16]) {
+    stg256(dst, pack2<F16>(v[0], v[1]), pack2<F16>(v[2], v[3]), pack2<F16>(v[4], v[5]), pack2<F16>(v[6], v[7]),
+           pack2<F16>(v[8], v[9]), pack2<F16>(v[10], v[11]), pack2<F16>(v[12], v[13]), pack2<F16>(v[14], v[15]));
 }
 
 // 2x2 block of a 3-channel fp32 NCHW frame: f[c][phase]
@@ -80,6 +82,7 @@ __device__ __forceinline__ void bilinear_gather3(const float* __restrict__ img, 
 
 // ---- K2: cat(F_t0, F_t1, x) (model.py:37-41) for one block pixel.  flow[ph]: Flow U-Net output of the pair;
 // i0/i1: the pair's frames; cf: the sample's coefficients; r16: the sample's packed head input at this block pixel.
+template <int F16>
 __device__ __forceinline__ void glue_tscale_block(const float4 (&flow)[4], const float* __restrict__ i0, const float* __restrict__ i1,
                                                   const float* __restrict__ cf, long HW, int W, int by, int bx, __nv_bfloat16* __restrict__ r16) {
     float a[3][4], b[3][4];
@@ -90,11 +93,12 @@ __device__ __forceinline__ void glue_tscale_block(const float4 (&flow)[4], const
         float a0, a1, b0, b1;
         tscale(flow[ph], cf, a0, a1, b0, b1);
         float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], 0, 0, 0, 0, 0, 0};
-        store_bf16x16(r16 + ph * 16, v);
+        store_x16<F16>(r16 + ph * 16, v);
     }
 }
 
 // ---- K3: residue add (model.py:44-45) + two backward warps (model.py:47-48) + cat (model.py:50) for one block pixel
+template <int F16>
 __device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const float4 (&res)[4], const float* __restrict__ i0,
                                                 const float* __restrict__ i1, const float* __restrict__ cf, long HW, int H, int W, int by,
                                                 int bx, __nv_bfloat16* __restrict__ m16, float4* __restrict__ xt8) {
@@ -115,13 +119,14 @@ __device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const f
         bilinear_gather3(i1, HW, H, W, warp_coord(gx, b0, fW), warp_coord(gy, b1, fH), xt2);   // model.py:48
         float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph],
                        xt1[0], xt1[1], xt1[2], xt2[0], xt2[1], xt2[2]};                          // model.py:50
-        store_bf16x16(m16 + ph * 16, v);
+        store_x16<F16>(m16 + ph * 16, v);
         stg256(xt8 + ph * 2, __float_as_uint(xt1[0]), __float_as_uint(xt1[1]), __float_as_uint(xt1[2]), __float_as_uint(xt2[0]),
                __float_as_uint(xt2[1]), __float_as_uint(xt2[2]), 0u, 0u);
     }
 }
 
 // ---- K4: sigmoid + occlusion-weighted blend (model.py:52-55) + cat (model.py:61) for one block pixel
+template <int F16>
 __device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const float4* __restrict__ xt8, const float* __restrict__ i0,
                                                  const float* __restrict__ i1, float omt, float t, long HW, int W, int by, int bx,
                                                  float4* __restrict__ out4, __nv_bfloat16* __restrict__ f16) {
@@ -140,7 +145,7 @@ __device__ __forceinline__ void glue_blend_block(const float4 (&mk)[4], const fl
         const float o2 = (w1 * ta.z + w2 * tb.y) / den;
         ob[ph] = make_float4(o0, o1, o2, 0.f);
         float v[16] = {a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph], o0, o1, o2, 0, 0, 0, 0, 0, 0, 0};   // model.py:61
-        store_bf16x16(f16 + ph * 16, v);
+        store_x16<F16>(f16 + ph * 16, v);
     }
     stg256(out4, ob[0], ob[1]);
     stg256(out4 + 2, ob[2], ob[3]);

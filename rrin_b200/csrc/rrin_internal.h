@@ -23,7 +23,7 @@ enum ConvEpilogue : int {
     EPI_SCATTER = 2,   // folded upsample: column (a,b,co) -> bf16 NHWC [N,2H,2W,cout_stride] at (2y+a,2x+b)
 };
 enum ConvSched : int { SCHED_TAPS9 = 0, SCHED_S2D16 = 1, SCHED_S2D8 = 2 };   // S2D8: half-phase stages of the TMA kernel
-enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3, PACK_NORMAL_CG2 = 4 };   // CG2: per-CTA halves of every block
+enum PackKind : int { PACK_NORMAL = 0, PACK_S2D = 1, PACK_FOLD = 2, PACK_S2D8 = 3, PACK_NORMAL_CG2 = 4, PACK_S2D8_CG2 = 5 };   // CG2: per-CTA halves of every block
 
 // Glue fused into the fp32 epilogue of a `last` conv (conv3x3_v2.cuh FuseParams); mode 0 = none.
 struct ConvFuse {
@@ -54,6 +54,7 @@ struct ConvDesc {
     int act = 0;
     int ring_only = 0;
     int cfg = -1;
+    int f16 = 0;                  // operand / activation format: 0 bf16, 1 fp16 (precision mode)
     const void* tmap0 = nullptr;  // TMA configs: pre-encoded CUtensorMap (128 bytes, host memory) of src0 / src1, or null
     const void* tmap1 = nullptr;
     const void* tmap_out = nullptr; // TMA-epilogue configs: pre-encoded map of `out`, or null
@@ -100,7 +101,7 @@ int conv_packed_bias_count(int cfg, int n_cols);
 //  PACK_S2D   : columns = (phase, co) with NT/4 columns per phase; stage s covers input channels [s*KB, +KB)
 //  PACK_FOLD  : bilinear x2 folded into the weights; columns = (phase, co), 4*cout in total; stages as NORMAL
 int conv_pack_weights(int kind, const float* w, const float* b, int cout, int cin, int n_stages, int cfg,
-                      void* wpack, float* bias_pack, cudaStream_t stream);
+                      void* wpack, float* bias_pack, cudaStream_t stream, int f16 = 0);
 int conv_launch(const ConvDesc& d, cudaStream_t stream);
 
 // Fused elementwise / gather kernels (glue.cu).  Frames are fp32 NCHW; everything these kernels
@@ -108,13 +109,14 @@ int conv_launch(const ConvDesc& d, cudaStream_t stream);
 //   head inputs bf16 [N,H/2,W/2,4,16], U-Net outputs fp32 [N,H/2,W/2,4,4].
 //   coef: [Nt][6] = {c00, c01, c10, c11, 1-t, t} per sample (model.py:38-39,54)
 //   pair_mul: 1 when sample n uses frame pair n, 0 when all samples share pair 0 (multi-t)
-int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s);
+//   f16: 16-bit format of the packed head tensors (0 bf16, 1 fp16: the precision mode)
+int pack_pair(const float* in0, const float* in1, int N, int H, int W, void* x16, cudaStream_t s, int f16 = 0);
 int flow_tscale_pack(const float* flow4, const float* in0, const float* in1, const float* coef,
-                     int Nt, int pair_mul, int H, int W, void* r16, cudaStream_t s);
+                     int Nt, int pair_mul, int H, int W, void* r16, cudaStream_t s, int f16 = 0);
 int warp_pack(const float* flow4, const float* res4, const float* in0, const float* in1, const float* coef,
-              int Nt, int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s);
+              int Nt, int pair_mul, int H, int W, void* m16, float* xt8, cudaStream_t s, int f16 = 0);
 int blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef,
-               int Nt, int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s);
+               int Nt, int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s, int use_f16 = 0);
 int residue_clamp(const float* res4, const float* out4, int Nt, int H, int W, float* out_nchw, cudaStream_t s);
 // uint8 frame I/O of the streaming pipeline: Pad(edge) + ToTensor (dataloader.py:93-118) and to_pil_image + crop (utils.py:51-58)
 int frame_from_u8(const uint8_t* src, int H0, int W0, int C, int top, int bottom, float* dst, cudaStream_t s);

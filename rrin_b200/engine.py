@@ -15,7 +15,7 @@ from ._lib import check, lib
 
 
 # operand formats of the tensor-core path -> code passed through the C-ABI
-PRECISIONS = {"bf16": 0}
+PRECISIONS = {"bf16": 0, "fp16": 1}
 
 # RRIN_GRAPH=0: launch kernel by kernel instead of replaying CUDA graphs (A/B timing; results are bit-identical)
 USE_GRAPH = os.environ.get("RRIN_GRAPH", "1") != "0"
@@ -59,7 +59,7 @@ class PackedWeights:
                 if tuple(w.shape) != (cout, cin, 3, 3) or tuple(b.shape) != (cout,):
                     raise RuntimeError(f"size mismatch for {key}: {tuple(w.shape)} vs {(cout, cin, 3, 3)}")
                 keep += [w, b]
-                check(l.rrin_pack_conv(i, _ptr(w), _ptr(b), _ptr(self.blob), _stream()), f"rrin_pack_conv({key})")
+                check(l.rrin_pack_conv_ex(i, _ptr(w), _ptr(b), _ptr(self.blob), PRECISIONS[precision], _stream()), f"rrin_pack_conv({key})")
             torch.cuda.current_stream().synchronize()   # w/b temporaries may be freed after this
 
 
@@ -93,7 +93,7 @@ class Engine:
             raise ValueError(f"unknown precision {precision!r}")
         self.n_pairs = n if n_pairs is None else n_pairs
         hnd = C.c_void_p()
-        check(l.rrin_engine_create(self.n_pairs, n, h, w, C.byref(hnd)), "rrin_engine_create")
+        check(l.rrin_engine_create_ex(self.n_pairs, n, h, w, PRECISIONS[precision], C.byref(hnd)), "rrin_engine_create")
         self._h = hnd
         with torch.cuda.device(device):
             self.workspace = torch.empty(l.rrin_engine_workspace_bytes(hnd), dtype=torch.uint8, device=device)
@@ -127,6 +127,10 @@ class Engine:
     def run(self, weights: "PackedWeights", in0: torch.Tensor, in1: torch.Tensor, coef: torch.Tensor,
             out: torch.Tensor | None = None) -> torch.Tensor:
         in0, in1 = self._frames(in0), self._frames(in1)
+        # CUDA-graph replay needs stable pointers (a graph bakes them in): callers that own their output buffer
+        # (forward_into / the streaming pipeline) cycle through a few buffers and replay; `forward`, which allocates a new
+        # result tensor per call like the reference, launches kernel by kernel.
+        graph = USE_GRAPH and out is not None
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty((self.n, 3, self.h, self.w), dtype=torch.float32, device=self.device)
@@ -136,7 +140,7 @@ class Engine:
             # One workspace per engine: a forward issued on another stream than the previous one is ordered after it.
             if self._last_stream is not None and self._last_stream != cur.cuda_stream:
                 cur.wait_event(self._done)
-            fwd = lib().rrin_engine_forward_graph if USE_GRAPH else lib().rrin_engine_forward
+            fwd = lib().rrin_engine_forward_graph if graph else lib().rrin_engine_forward
             check(fwd(self._h, _ptr(weights.blob), _ptr(self.workspace), _ptr(in0), _ptr(in1),
                       _ptr(coef), _ptr(out), cur.cuda_stream), "rrin_engine_forward")
             self._done.record(cur)

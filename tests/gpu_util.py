@@ -11,20 +11,44 @@ from rrin_b200._lib import check, lib
 SRC_PLAIN, SRC_CAT, SRC_POOL, SRC_UP, SRC_POOL_S2D, SRC_UP_S2D = range(6)
 EPI_BF16, EPI_F32X16, EPI_SCATTER = range(3)
 SCHED_TAPS9, SCHED_S2D16, SCHED_S2D8 = 0, 1, 2
-PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8, PACK_NORMAL_CG2 = 0, 1, 2, 3, 4
+PACK_NORMAL, PACK_S2D, PACK_FOLD, PACK_S2D8, PACK_NORMAL_CG2, PACK_S2D8_CG2 = 0, 1, 2, 3, 4, 5
 # transform kernel (conv3x3.cuh)
 CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
 T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP, T_POOL32, T_L1_PAIR = range(10, 23)
+T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3 = 23, 24, 25, 26     # level 0 on CTA pairs, resident half-blocks
 
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# 16-bit operand format under test: 0 = bf16 (RRIN_PRECISION_BF16), 1 = fp16 (RRIN_PRECISION_FP16, the precision mode).
+# The helpers below read it at call time; `with precision(1): ...` runs a block of kernel tests in fp16.
+PREC = 0
+
+
+class precision:
+    def __init__(self, p):
+        self.p = p
+
+    def __enter__(self):
+        global PREC
+        self.old, PREC = PREC, self.p
+
+    def __exit__(self, *a):
+        global PREC
+        PREC = self.old
+
+
+def dt():
+    return torch.float16 if PREC else torch.bfloat16
+
+
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32)
+    """Round to the 16-bit operand format under test (bf16 by default)."""
+    return x.to(dt()).to(torch.float32)
 
 
 def cfg_info(cfg):
@@ -33,12 +57,14 @@ def cfg_info(cfg):
     return tuple(x.value for x in v)      # kcs, kb, nt, msub
 
 
-def nhwc(x_nchw, dtype=torch.bfloat16):
+def nhwc(x_nchw, dtype=None):
+    dtype = dtype or dt()
     return x_nchw.permute(0, 2, 3, 1).contiguous().to(dtype)
 
 
-def to_s2d(x_nchw, dtype=torch.bfloat16):
+def to_s2d(x_nchw, dtype=None):
     """[N,C,H,W] -> space-to-depth [N,H/2,W/2,4,C] (phase = 2*a+b for pixel (2y+a, 2x+b))."""
+    dtype = dtype or dt()
     n, c, h, w = x_nchw.shape
     return x_nchw.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, h // 2, w // 2, 4, c).contiguous().to(dtype)
 
@@ -53,21 +79,21 @@ def pack(kind, cfg, weight, bias, n_stages, sched):
     l = lib()
     cout, cin = weight.shape[:2]
     _, _, nt, _ = cfg_info(cfg)
-    n_cols = {PACK_NORMAL: cout, PACK_NORMAL_CG2: cout, PACK_S2D: nt, PACK_S2D8: nt, PACK_FOLD: 4 * cout}[kind]
+    n_cols = {PACK_NORMAL: cout, PACK_NORMAL_CG2: cout, PACK_S2D: nt, PACK_S2D8: nt, PACK_S2D8_CG2: nt, PACK_FOLD: 4 * cout}[kind]
     n_cols = (n_cols + nt - 1) // nt * nt
     wp = torch.zeros(l.rrin_conv_packed_weight_bytes(cfg, n_cols, n_stages, sched), dtype=torch.uint8, device="cuda")
     bp = torch.zeros(l.rrin_conv_packed_bias_count(cfg, n_cols), dtype=torch.float32, device="cuda")
     wc, bc = weight.contiguous().float(), bias.contiguous().float()
-    check(l.rrin_pack_conv_raw(kind, wc.data_ptr(), bc.data_ptr(), cout, cin, n_stages, cfg, wp.data_ptr(), bp.data_ptr(), stream()),
+    check(l.rrin_pack_conv_raw_ex(kind, wc.data_ptr(), bc.data_ptr(), cout, cin, n_stages, cfg, wp.data_ptr(), bp.data_ptr(), PREC, stream()),
           "rrin_pack_conv_raw")
     torch.cuda.synchronize()
     return wp, bp, n_cols
 
 
 def launch(src0, src1, c0, c1, mode, pad_clamp, n, gh, gw, sched, n_cols, wp, bp, out, epi, cout_stride, act, ring_only, cfg, pool_out=None):
-    check(lib().rrin_conv3x3(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, pad_clamp, n, gh, gw,
+    check(lib().rrin_conv3x3_ex(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, pad_clamp, n, gh, gw,
                              sched, n_cols, wp.data_ptr(), bp.data_ptr(), out.data_ptr(), epi, cout_stride, int(act), int(ring_only),
-                             cfg, pool_out.data_ptr() if pool_out is not None else None, stream()), "rrin_conv3x3")
+                             cfg, pool_out.data_ptr() if pool_out is not None else None, PREC, stream()), "rrin_conv3x3")
     torch.cuda.synchronize()
 
 
@@ -79,7 +105,7 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
     c1 = src1.shape[-1] if src1 is not None else 0
     wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg in (T_BIG_PAIR, T_L1_PAIR) else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if out is None:
-        out = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        out = torch.full((n, h, w, cout), float("nan"), dtype=dt(), device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg, pool_out)
     return out.float().permute(0, 3, 1, 2), out
 
@@ -92,15 +118,16 @@ def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring
     cout = weight.shape[0]
     c0 = src0.shape[-1] * (src0.shape[-2] if src0.dim() == 5 else 1)
     c1 = (src1.shape[-1] * src1.shape[-2]) if src1 is not None else 0
-    half = cfg in (T_L0, T_L0CAT, T_LAST)
-    kind, sched = (PACK_S2D8, SCHED_S2D8) if half else (PACK_S2D, SCHED_S2D16)
+    pair = cfg in (T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3)
+    half = cfg in (T_L0, T_L0CAT, T_LAST) or pair
+    kind, sched = ((PACK_S2D8_CG2 if pair else PACK_S2D8), SCHED_S2D8) if half else (PACK_S2D, SCHED_S2D16)
     if half:
         n_stages *= 2
     wp, bp, n_cols = pack(kind, cfg, weight, bias, n_stages, sched)
     f32 = (nt == 16)
     cpp = nt // 4
     if out is None:
-        out = torch.full((n, hb, wb, 4, cpp), float("nan"), dtype=torch.float32 if f32 else torch.bfloat16, device="cuda")
+        out = torch.full((n, hb, wb, 4, cpp), float("nan"), dtype=torch.float32 if f32 else dt(), device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, hb, wb, sched, n_cols, wp, bp, out, EPI_F32X16 if f32 else EPI_BF16,
            16 if f32 else nt, act, ring_only, cfg, pool_out)
     return from_s2d(out)[:, :cout], out
@@ -116,11 +143,11 @@ def conv_fold(src, n, hc, wc, weight, bias, level0, out=None):
     wp, bp, n_cols = pack(PACK_FOLD, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if level0:
         if out is None:
-            out = torch.full((n, hc, wc, 4, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            out = torch.full((n, hc, wc, 4, cout), float("nan"), dtype=dt(), device="cuda")
         launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, 4 * cout, False, False, T_FOLD0)
         return from_s2d(out), out
     if out is None:
-        out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        out = torch.full((n, 2 * hc, 2 * wc, cout), float("nan"), dtype=dt(), device="cuda")
     launch(src, None, cin, 0, SRC_PLAIN, 0, n, hc, wc, SCHED_TAPS9, n_cols, wp, bp, out, EPI_SCATTER, cout, False, False, T_BIG_SCATTER)
     return out.float().permute(0, 3, 1, 2), out
 

@@ -347,12 +347,13 @@ def test_misaligned_views_and_weight_invalidation():
     with pytest.raises(RuntimeError, match="aligned"):
         net.forward_into(a.cuda(), b.cuda(), 0.5, flat[1:1 + 3 * 64 * 64].view(1, 3, 64, 64))
     # parameter updates PyTorch's version counters see (in-place ops) re-pack automatically ...
+    orig = net.final.last.bias.detach().clone()
     with torch.no_grad():
         net.final.last.bias.add_(0.25)
     y2 = net(a.cuda(), b.cuda(), t=0.5)
     assert (y2 - y).abs().max().item() > 0.1
     # ... writes through .data do not: invalidate_weights() forces the re-pack
-    net.final.last.bias.data.sub_(0.25)
+    net.final.last.bias.data.copy_(orig)
     assert torch.equal(net(a.cuda(), b.cuda(), t=0.5), y2)
     net.invalidate_weights()
     assert torch.equal(net(a.cuda(), b.cuda(), t=0.5), y)
@@ -384,3 +385,49 @@ def test_training_mode_call_raises_instead_of_dropping_grad():
     net(x, x)
     with pytest.raises(RuntimeError, match="inference only"):
         net(x.requires_grad_(), x)
+
+
+# ------------------------------------------------------------------ precision mode: fp16 operands, fp32 accumulation
+FP16_GOLD = ["rand64_t050", "rand_32x48_t030", "stress64_t050", "stress_smooth_48x80_n2_t0875"]
+
+
+@pytest.mark.parametrize("name", FP16_GOLD)
+def test_fp16_precision_mode_meets_1e3_on_reference_fixtures(golden_dir, name):
+    """north_star: "the fp32-accumulate path must be within 1e-3 max-abs" -- also under the stress weights (|flow| up to
+    11 / 17 px, clamp active) where the bf16-operand path only holds the PSNR >= 50 dB bar.  Fixtures come from the
+    unmodified reference (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sd = O.seeded_state_dict(float(g["stress_flow"]), float(g["stress_final"]))
+    net = make_net(sd)
+    net.precision = "fp16"
+    a, b = torch.from_numpy(g["in0"]).cuda(), torch.from_numpy(g["in1"]).cuda()
+    y = net(a, b, t=float(g["t"])).cpu()
+    ref = torch.from_numpy(g["out"])
+    err = (y - ref).abs().max().item()
+    net.precision = "bf16"
+    err_bf16 = (net(a, b, t=float(g["t"])).cpu() - ref).abs().max().item()
+    print(f"{name}: fp16 max-abs {err:.3e} (bf16 {err_bf16:.3e}) psnr {psnr(y, ref):.1f} dB")
+    assert err <= 1e-3, f"{name}: fp16 max-abs {err}"
+    assert psnr(y, ref) >= 70
+
+
+def test_fp16_precision_mode_shapes_and_multi_t():
+    sd = O.seeded_state_dict(stress_flow=100.0)
+    net = make_net(sd)
+    net.precision = "fp16"
+    with pytest.raises(ValueError):
+        net.precision = "fp8"
+    for n, h, w in [(1, 16, 16), (2, 128, 144), (1, 80, 272)]:
+        a, b = O.seeded_frames(n, h, w, seed=30 + h, smooth=True)
+        y = net(a.cuda(), b.cuda(), t=0.4).cpu()
+        assert (y - O.forward(sd, a, b, 0.4)).abs().max().item() <= 1e-3, (n, h, w)
+    a, b = O.seeded_frames(1, 48, 64, seed=4, smooth=True)
+    ts = [0.25, 0.5, 0.75]
+    singles = torch.cat([net(a.cuda(), b.cuda(), t=t) for t in ts])
+    assert torch.equal(singles, net.forward_multi(a.cuda(), b.cuda(), ts))
+    # both precisions live side by side in one Net (separate packed weights and engines)
+    net.precision = "bf16"
+    yb = net(a.cuda(), b.cuda(), t=0.5)
+    net.precision = "fp16"
+    yh = net(a.cuda(), b.cuda(), t=0.5)
+    assert torch.equal(yh, singles[1:2]) and not torch.equal(yb, yh)

@@ -86,6 +86,19 @@ def test_1080p_stress_flow_matches_oracle():
     assert p >= 50
 
 
+def test_1080p_stress_flow_fp16_precision_mode():
+    """The precision mode (fp16 operands, fp32 accumulation) at 1080p with multi-pixel flows: the 1e-3 bar that the bf16
+    path only meets with random-init weights."""
+    sd = O.seeded_state_dict(stress_flow=100.0)
+    net = make_net(sd, precision="fp16")
+    a, b = O.seeded_frames(1, 1088, 1920, seed=2, smooth=True)
+    y = net(a.cuda(), b.cuda(), t=0.5).cpu()
+    ref = O.forward(sd, a, b, 0.5)
+    err = (y - ref).abs().max().item()
+    print(f"1080p stress fp16: max-abs {err:.3e} psnr {psnr(y, ref):.1f} dB")
+    assert err <= 1e-3 and psnr(y, ref) >= 70
+
+
 def test_720p_batch8_sample_matches_oracle():
     """BASELINE configs[1]: 736x1280, batch of 8 pairs; two samples of the batch against the oracle."""
     sd = O.seeded_state_dict()
@@ -157,6 +170,7 @@ torch.save(y, sys.argv[1])
 """
 
 SWITCHES = [("RRIN_FUSE", "0", 0.0), ("RRIN_PDL", "0", 0.0), ("RRIN_GRAPH", "0", 0.0), ("RRIN_BIG_CFG", "19", 2e-3),
+            ("RRIN_L0_PAIR", "0", 2e-3), ("RRIN_L0_PAIR", "26,25", 2e-3),
             ("RRIN_L1_PAIR", "1", 2e-3), ("RRIN_UP_CFG", "5", 2e-3), ("RRIN_POOL1_CFG", "3", 2e-3)]
 
 

@@ -30,7 +30,7 @@ def _check(name, y, ref, f32=False, rel=1.0 / 128):
     assert torch.isfinite(y).all(), f"{name}: non-finite output (unwritten pixels?)"
     err = (y - ref).abs().max().item()
     scale = max(ref.abs().max().item(), 1.0)
-    tol = (3e-5 if f32 else rel) * scale + 1e-5
+    tol = (3e-5 if f32 else (rel / 8 if G.PREC else rel)) * scale + 1e-5        # fp16 stores 3 more significand bits than bf16
     assert err <= tol, f"{name}: max err {err:.4g} (scale {scale:.3g}, tol {tol:.3g})"
 
 
@@ -147,6 +147,18 @@ S2D_CASES = [
     ("tma_many_tiles_l0cat", 12, "cat", 64, 32, 32, True, 1, 368, 368),
     ("tma_many_tiles_head", 10, "plain", 10, 16, 32, True, 1, 368, 368),
     ("tma_many_tiles_last", 13, "plain", 32, 32, 4, False, 1, 368, 368),
+    # CTA pairs with resident half-blocks (configs 23 / 26: 32->32, 24 / 25: cat)
+    ("pair_l0_32_32", 23, "plain", 32, 32, 32, True, 1, 64, 128),
+    ("pair_l0_32_32_partial", 23, "plain", 32, 32, 32, True, 2, 48, 80),
+    ("pair_l0_many_tiles", 23, "plain", 32, 32, 32, True, 1, 368, 368),
+    ("pair_l0_odd_groups", 23, "plain", 32, 32, 32, False, 1, 176, 208),      # 13 column groups per band: odd runs, partial pair tiles
+    ("pair3_l0_32_32_partial", 26, "plain", 32, 32, 32, True, 2, 48, 80),
+    ("pair3_l0_many_tiles", 26, "plain", 32, 32, 32, True, 1, 368, 368),
+    ("pair_l0_cat", 24, "cat", 64, 32, 32, True, 1, 64, 96),
+    ("pair_l0_cat_many_tiles", 24, "cat", 64, 32, 32, True, 1, 368, 368),
+    ("pair_l0_cat_odd_groups", 24, "cat", 64, 32, 32, False, 2, 80, 208),
+    ("pair1_l0_cat", 25, "cat", 64, 32, 32, True, 1, 64, 96),
+    ("pair1_l0_cat_many_tiles", 25, "cat", 64, 32, 32, True, 1, 368, 368),
 ]
 
 
@@ -181,26 +193,27 @@ def test_conv_level0_s2d(case):
 def test_conv_with_pooled_output(cfg, cin, cout, n, h, w):
     x = _rand(n, cin, h, w, 1)
     wgt, b = _rand_wb(cout, cin, 3)
-    pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    pool = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=G.dt(), device="cuda")
     y, raw = G.conv_normal(G.nhwc(x), None, G.SRC_PLAIN, n, h, w, wgt, b, True, cfg, pool_out=pool)
     _check("conv", y, G.reference(x, wgt, b, True))
     want = G.bf16_round(torch.nn.functional.avg_pool2d(raw.float().permute(0, 3, 1, 2), 2))       # pool of the STORED bf16 tensor
     got = pool.float().permute(0, 3, 1, 2)
     assert torch.isfinite(got).all()
-    assert (got - want).abs().max().item() <= 2 ** -8 * max(1.0, want.abs().max().item())
+    assert (got - want).abs().max().item() <= (2 ** -11 if G.PREC else 2 ** -8) * max(1.0, want.abs().max().item())
 
 
+@pytest.mark.parametrize("cfg", [11, 23, 26], ids=["single", "pair", "pair3"])
 @pytest.mark.parametrize("n,h,w", [(1, 64, 128), (2, 48, 80), (1, 368, 368)], ids=["small", "partial_n2", "many"])
-def test_conv_level0_with_pooled_output(n, h, w):
+def test_conv_level0_with_pooled_output(n, h, w, cfg):
     x = _rand(n, 32, h, w, 1)
     wgt, b = _rand_wb(32, 32, 3)
-    pool = torch.full((n, h // 2, w // 2, 32), float("nan"), dtype=torch.bfloat16, device="cuda")
-    y, raw = G.conv_s2d(G.to_s2d(x), None, G.SRC_PLAIN, n, h // 2, w // 2, wgt, b, True, G.T_L0, 1, pool_out=pool)
+    pool = torch.full((n, h // 2, w // 2, 32), float("nan"), dtype=G.dt(), device="cuda")
+    y, raw = G.conv_s2d(G.to_s2d(x), None, G.SRC_PLAIN, n, h // 2, w // 2, wgt, b, True, cfg, 1, pool_out=pool)
     _check("conv", y, G.reference(x, wgt, b, True))
     want = G.bf16_round(torch.nn.functional.avg_pool2d(G.from_s2d(raw), 2))
     got = pool.float().permute(0, 3, 1, 2)
     assert torch.isfinite(got).all()
-    assert (got - want).abs().max().item() <= 2 ** -8 * max(1.0, want.abs().max().item())
+    assert (got - want).abs().max().item() <= (2 ** -11 if G.PREC else 2 ** -8) * max(1.0, want.abs().max().item())
 
 
 # ------------------------------------------------------------------ folded upsample + exact ring
@@ -328,3 +341,34 @@ def test_glue_multi_t_shares_pair():
         ft0 = -(1 - t) * t * flow[0, :2] + t * t * flow[0, 2:]
         assert (got[i, :2] - ft0).abs().max() <= 2 ** -8 * ft0.abs().max() + 1e-6
         assert torch.equal(got[i, 4:7], G.bf16_round(a[0]))
+
+
+# ------------------------------------------------------------------ fp16 operands (the precision mode, RRIN_PRECISION_FP16)
+FP16_NORMAL = ["tma_l1_64_64", "tma_l1_cat", "tma_l2_cat", "tma_l4_512_512", "tma_many_tiles_l3_ntiles", "tma_direct_l2_cat",
+               "tma_msub3_many_tiles", "tma_pool32_many_tiles", "tma_up_many_tiles", "tma_up_odd_sizes", "pair_many_tiles_l2",
+               "pair64_many_tiles", "l1_up", "l2_up", "l1_pool_s2d"]
+FP16_S2D = ["pair_l0_many_tiles", "pair_l0_cat_many_tiles", "tma_head16_partial", "tma_l0_32_32_partial", "tma_l0_cat", "tma_last3", "tma_many_tiles_l0", "tma_many_tiles_l0cat",
+            "tma_many_tiles_head", "tma_many_tiles_last", "l0_up_exact"]
+
+
+@pytest.mark.parametrize("name", FP16_NORMAL)
+def test_fp16_conv_levels_ge1(name):
+    """Same kernels with fp16 operands: compared with the fp64 conv of the fp16-rounded operands, 8x tighter output bar."""
+    with G.precision(1):
+        test_conv_levels_ge1(next(c for c in NORMAL_CASES if c[0] == name))
+
+
+@pytest.mark.parametrize("name", FP16_S2D)
+def test_fp16_conv_level0(name):
+    with G.precision(1):
+        test_conv_level0_s2d(next(c for c in S2D_CASES if c[0] == name))
+
+
+def test_fp16_pooled_outputs_and_fold_ring():
+    with G.precision(1):
+        test_conv_with_pooled_output(14, 64, 64, 2, 184, 72)
+        test_conv_with_pooled_output(16, 256, 256, 1, 100, 72)
+        test_conv_level0_with_pooled_output(2, 48, 80, 11)
+        test_conv_level0_with_pooled_output(1, 368, 368, 23)
+        test_conv_folded_upsample_with_ring(True, 64, 32, 1, 136, 200, "strips")
+        test_conv_folded_upsample_with_ring(False, 128, 64, 1, 72, 136, "strips")
