@@ -27,6 +27,11 @@
 // 24 : < 64, 32, 128, 2, 2, 32, S2D8 , 1, 1, 2, 2>     level-0 cat(32+32)->32 on CTA pairs, the 192 KB of weights resident as two 96 KB halves
 // 25 : < 64, 32, 128, 1, 4, 32, S2D8 , 1, 1, 2, 2>     same with 16 x 8 tiles and four stages
 // 26 : < 64, 32, 128, 3, 2, 16, S2D8 , 1, 1, 2, 2>     level-0 32->32 on pairs with 16 x 24 tiles, two stages
+// 27 : < 64, 32, 128, 1, 6, 16, S2D8 , 1, 1, 2, 2>     level-0 32->32 on pairs with 16 x 8 tiles and six stages
+// 28 : < 64, 64,  64, 2, 4,  9, TAPS9, 1, 1, 1, 2>     level-1 64->64 on pairs, weights resident as two 36 KB halves, four stages
+// 29 : < 64, 64,  64, 2, 3, 18, TAPS9, 1, 1, 1, 2>     level-1 cat(64+64)->64 on pairs, 144 KB of weights resident as two 72 KB halves
+// 30 / 31 : the same two with 16 x 8 tiles (MSUB = 1), six / four stages, two epilogue groups
+// 32 / 33 / 34 : level-0 `last` (config 13) with 16 x 8 tiles and four / eight stages, or 16 x 16 tiles and four stages
 #define RRIN_CONV2_CONFIGS(X)                   \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0) \
     X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0) \
@@ -44,7 +49,15 @@
     X(23, 64, 32, 128, 2, 3, 16, 2, 1, 1, 2, 2, 0) \
     X(24, 64, 32, 128, 2, 2, 32, 2, 1, 1, 2, 2, 0) \
     X(25, 64, 32, 128, 1, 4, 32, 2, 1, 1, 2, 2, 0) \
-    X(26, 64, 32, 128, 3, 2, 16, 2, 1, 1, 2, 2, 0)
+    X(26, 64, 32, 128, 3, 2, 16, 2, 1, 1, 2, 2, 0) \
+    X(27, 64, 32, 128, 1, 6, 16, 2, 1, 1, 2, 2, 0) \
+    X(28, 64, 64, 64, 2, 4, 9, 0, 1, 1, 1, 2, 0) \
+    X(29, 64, 64, 64, 2, 3, 18, 0, 1, 1, 1, 2, 0) \
+    X(30, 64, 64, 64, 1, 6, 9, 0, 1, 1, 2, 2, 0) \
+    X(31, 64, 64, 64, 1, 4, 18, 0, 1, 1, 2, 2, 0) \
+    X(32, 64, 32, 16, 1, 4, 16, 2, 1, 0, 2, 1, 0) \
+    X(33, 64, 32, 16, 1, 8, 16, 2, 1, 0, 2, 1, 0) \
+    X(34, 64, 32, 16, 2, 4, 16, 2, 1, 0, 2, 1, 0)
 
 
 namespace rrin {

@@ -115,7 +115,7 @@ struct ConvCfgV2 {
     static constexpr int A_STAGE = BOXES * BOX_STRIDE;
     static constexpr int B_BLOCK = NT * KB * 2 / CG;   // bytes of a weight block held by ONE CTA
     static constexpr bool HALF = (SCHED == 2 && NT == 128);
-    static_assert(CG == 1 || (CG == 2 && SCHED == 0 && !RES && (NT == 128 || NT == 64)) || (CG == 2 && SCHED == 2 && RES && NT == 128),
+    static_assert(CG == 1 || (CG == 2 && SCHED == 0 && (NT == 128 || NT == 64)) || (CG == 2 && SCHED == 2 && RES && NT == 128),
                   "CTA pairs: streamed 9-tap schedule (N = 128 or 64), or the resident half-phase schedule (level 0: each CTA keeps half of every weight block)");
     static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
     static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;

@@ -88,19 +88,36 @@ static bool l1_pair() {
     static const bool on = getenv("RRIN_L1_PAIR") && atoi(getenv("RRIN_L1_PAIR")) != 0;
     return on;
 }
+// level-1 64->64 / cat(64+64)->64 config ids: RRIN_L1_CFG=<a>,<b> with a in {14, 28, 30}, b in {15, 29, 31} (28-31: CTA pairs
+// with resident half-blocks)
+static void l1_cfgs(int& c64, int& ccat) {
+    static int a = -1, b = -1;
+    if (a < 0) {
+        a = 14; b = 15;
+        const char* e = getenv("RRIN_L1_CFG");
+        int x = 0, y = 0;
+        if (e && sscanf(e, "%d,%d", &x, &y) == 2) {
+            if (x == 14 || x == 28 || x == 30) a = x;
+            if (y == 15 || y == 29 || y == 31) b = y;
+        }
+    }
+    c64 = a; ccat = b;
+}
 
-// level-0 32->32 and cat(32+32)->32 convs on CTA pairs with resident half-blocks (configs 23 / 24): RRIN_L0_PAIR=0 selects the
-// single-CTA configs 11 / 12; RRIN_L0_PAIR=<a>,<b> picks explicit config ids for the two layer kinds (A/B runs: 23|26 and 24|25)
+// Level-0 cat(32+32)->32 conv: CTA pairs that keep the layer's 192 KB of space-to-depth weights resident as two 96 KB halves
+// (config 25; measured 0.44 -> 0.33 ms per 4-pair launch against the single-CTA config 12, which re-streams them per tile).
+// The 32->32 conv stays on the single-CTA config 11 (its 96 KB fit one SM; the pair variants 23 / 26 / 27 measured slower).
+// RRIN_L0_PAIR=0 selects 11 / 12; RRIN_L0_PAIR=<a>,<b> picks explicit ids (A/B runs: a in {11,23,26,27}, b in {12,24,25}).
 static void l0_pair_cfgs(int& c32, int& ccat) {
     static int a = -1, b = -1;
     if (a < 0) {
-        a = 23; b = 24;
+        a = 11; b = 25;
         const char* e = getenv("RRIN_L0_PAIR");
         if (e) {
             int x = 0, y = 0;
             const int n = sscanf(e, "%d,%d", &x, &y);
             if (n == 1 && x == 0) { a = 11; b = 12; }
-            else if (n == 2) { a = (x == 23 || x == 26 || x == 11) ? x : 23; b = (y == 24 || y == 25 || y == 12) ? y : 24; }
+            else if (n == 2) { a = (x == 23 || x == 26 || x == 27 || x == 11) ? x : 23; b = (y == 24 || y == 25 || y == 12) ? y : 24; }
         }
     }
     c32 = a; ccat = b;
@@ -129,8 +146,9 @@ static Schedule build_schedule() {
             else {
                 int c32, ccat;
                 l0_pair_cfgs(c32, ccat);
-                m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? 13 : (cin == 32 ? c32 : ccat); m.n_stages = 2 * (cin / 32);
-                if (m.cfg >= 23) m.kind = PACK_S2D8_CG2;
+                static const int last_cfg = [] { const char* e = getenv("RRIN_LAST_CFG"); const int v = e ? atoi(e) : 13; return (v >= 32 && v <= 34) ? v : 13; }();
+                m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? last_cfg : (cin == 32 ? c32 : ccat); m.n_stages = 2 * (cin / 32);
+                if (m.cfg >= 23 && m.cfg <= 27) m.kind = PACK_S2D8_CG2;
             }
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;
@@ -138,8 +156,11 @@ static Schedule build_schedule() {
             if (level == 1) {
                 if (src == K_POOL) { m.cfg = pool1_cfg(); m.n_stages = 1; }      // 32 stored channels: 64-byte TMA rows (config 21)
                 else {
-                    m.cfg = (src == K_UP) ? 4 : (cin == 64 ? 14 : 15); m.n_stages = cin / 64;
-                    if (src != K_UP && l1_pair()) { m.cfg = 22; m.kind = PACK_NORMAL_CG2; }
+                    int c64, ccat;
+                    l1_cfgs(c64, ccat);
+                    m.cfg = (src == K_UP) ? 4 : (cin == 64 ? c64 : ccat); m.n_stages = cin / 64;
+                    if (src != K_UP && l1_pair()) m.cfg = 22;
+                    if (m.cfg == 22 || m.cfg >= 28) m.kind = PACK_NORMAL_CG2;
                 }
             } else {
                 m.cfg = (src == K_UP) ? up_cfg() : big_cfg(); m.n_stages = cin / 64;

@@ -17,7 +17,8 @@ CFG_HEAD, CFG_L0, CFG_LAST, CFG_L1POOL, CFG_L1, CFG_BIG = range(6)
 CFG_L1_STRIP, CFG_L0_STRIP = 7, 8            # 128-pixel border strips (ring_only launches)
 # TMA-fed kernel (conv3x3_v2.cuh)
 T_HEAD, T_L0, T_L0CAT, T_LAST, T_L1, T_L1CAT, T_BIG, T_BIG_SCATTER, T_FOLD0, T_BIG_PAIR, T_UP, T_POOL32, T_L1_PAIR = range(10, 23)
-T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3 = 23, 24, 25, 26     # level 0 on CTA pairs, resident half-blocks
+T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3, T_L0_PAIR1 = 23, 24, 25, 26, 27
+T_L1_PAIR_RES = (28, 29, 30, 31)      # level 1 on CTA pairs, resident half-blocks     # level 0 on CTA pairs, resident half-blocks
 
 
 def stream():
@@ -103,7 +104,7 @@ def conv_normal(src0, src1, mode, n, h, w, weight, bias, act, cfg, ring_only=Fal
     cout, cin = weight.shape[:2]
     c0 = src0.shape[-1] * (src0.shape[-2] if mode == SRC_POOL_S2D else 1)
     c1 = src1.shape[-1] if src1 is not None else 0
-    wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg in (T_BIG_PAIR, T_L1_PAIR) else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
+    wp, bp, n_cols = pack(PACK_NORMAL_CG2 if cfg in (T_BIG_PAIR, T_L1_PAIR) + T_L1_PAIR_RES else PACK_NORMAL, cfg, weight, bias, cin // kcs, SCHED_TAPS9)
     if out is None:
         out = torch.full((n, h, w, cout), float("nan"), dtype=dt(), device="cuda")
     launch(src0, src1, c0, c1, mode, 0, n, h, w, SCHED_TAPS9, n_cols, wp, bp, out, EPI_BF16, cout, act, ring_only, cfg, pool_out)
@@ -118,7 +119,7 @@ def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring
     cout = weight.shape[0]
     c0 = src0.shape[-1] * (src0.shape[-2] if src0.dim() == 5 else 1)
     c1 = (src1.shape[-1] * src1.shape[-2]) if src1 is not None else 0
-    pair = cfg in (T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3)
+    pair = cfg in (T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3, T_L0_PAIR1)
     half = cfg in (T_L0, T_L0CAT, T_LAST) or pair
     kind, sched = ((PACK_S2D8_CG2 if pair else PACK_S2D8), SCHED_S2D8) if half else (PACK_S2D, SCHED_S2D16)
     if half:

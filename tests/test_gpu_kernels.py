@@ -87,6 +87,13 @@ NORMAL_CASES = [
     ("pair64_l1_plain", 22, "plain", 64, 64, True, 2, 24, 40),
     ("pair64_l1_cat", 22, "cat", 64, 64, True, 1, 36, 52),
     ("pair64_many_tiles", 22, "cat", 64, 64, False, 1, 200, 136),
+    # level-1 CTA pairs with resident half-blocks
+    ("pairres_l1_plain", 28, "plain", 64, 64, True, 2, 24, 40),
+    ("pairres_l1_many_tiles", 28, "plain", 64, 64, True, 1, 184, 184),
+    ("pairres_l1_cat", 29, "cat", 64, 64, True, 1, 36, 52),
+    ("pairres_l1_cat_many_tiles", 29, "cat", 64, 64, False, 1, 200, 136),
+    ("pairres1_l1_many_tiles", 30, "plain", 64, 64, True, 1, 184, 184),
+    ("pairres1_l1_cat_many_tiles", 31, "cat", 64, 64, False, 1, 200, 136),
 ]
 
 
@@ -159,6 +166,8 @@ S2D_CASES = [
     ("pair_l0_cat_odd_groups", 24, "cat", 64, 32, 32, False, 2, 80, 208),
     ("pair1_l0_cat", 25, "cat", 64, 32, 32, True, 1, 64, 96),
     ("pair1_l0_cat_many_tiles", 25, "cat", 64, 32, 32, True, 1, 368, 368),
+    ("pair6_l0_partial", 27, "plain", 32, 32, 32, True, 2, 48, 80),
+    ("pair6_l0_many_tiles", 27, "plain", 32, 32, 32, True, 1, 368, 368),
 ]
 
 
@@ -187,9 +196,9 @@ def test_conv_level0_s2d(case):
 
 
 # ------------------------------------------------------------------ pooled second output of the TMA epilogue (unet.py:46)
-@pytest.mark.parametrize("cfg,cin,cout,n,h,w", [(14, 64, 64, 1, 24, 40), (14, 64, 64, 2, 184, 72), (16, 128, 128, 1, 12, 20),
+@pytest.mark.parametrize("cfg,cin,cout,n,h,w", [(14, 64, 64, 1, 24, 40), (14, 64, 64, 2, 184, 72), (28, 64, 64, 2, 184, 72), (30, 64, 64, 2, 184, 72), (16, 128, 128, 1, 12, 20),
                                                 (16, 256, 256, 1, 100, 72), (16, 128, 128, 2, 208, 104)],
-                         ids=["l1", "l1_many", "l2", "l3_ntiles", "l2_many"])
+                         ids=["l1", "l1_many", "l1_pair_many", "l1_pair1_many", "l2", "l3_ntiles", "l2_many"])
 def test_conv_with_pooled_output(cfg, cin, cout, n, h, w):
     x = _rand(n, cin, h, w, 1)
     wgt, b = _rand_wb(cout, cin, 3)
@@ -202,7 +211,7 @@ def test_conv_with_pooled_output(cfg, cin, cout, n, h, w):
     assert (got - want).abs().max().item() <= (2 ** -11 if G.PREC else 2 ** -8) * max(1.0, want.abs().max().item())
 
 
-@pytest.mark.parametrize("cfg", [11, 23, 26], ids=["single", "pair", "pair3"])
+@pytest.mark.parametrize("cfg", [11, 23, 26, 27], ids=["single", "pair", "pair3", "pair6"])
 @pytest.mark.parametrize("n,h,w", [(1, 64, 128), (2, 48, 80), (1, 368, 368)], ids=["small", "partial_n2", "many"])
 def test_conv_level0_with_pooled_output(n, h, w, cfg):
     x = _rand(n, 32, h, w, 1)
