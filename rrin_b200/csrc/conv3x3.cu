@@ -44,8 +44,8 @@ static const CfgInfo kCfg1[] = {
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>::PW, SCHED, RES, ETMA, 0, CG, XF},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>::PW, SCHED, RES, ETMA, 0, CG, XF},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };

@@ -81,7 +81,7 @@ struct ConvParamsV2 {
 };
 
 // EW epilogue groups of 4 warps + MMA, weights, activations (+ 4 transform warps when the A operand is computed: XF)
-constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32; }
+constexpr int v2_threads(int ew, int xf = 0, int ns = 1) { return (4 * ew + 3 + 4 * xf + (ns - 1)) * 32; }
 
 // KCS  : stored channels per K stage = channels per TMA box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte rows,
 //        SWIZZLE_64B: the pooled level-0 tensor)
@@ -104,7 +104,12 @@ constexpr int v2_threads(int ew, int xf = 0) { return (4 * ew + 3 + 4 * xf) * 32
 // XF   : 1 = the A operand is the exact bilinear x2 upsample (nn.Upsample, align_corners=False, unet.py:77) of a coarser
 //        NHWC tensor: TMA stages the raw coarse tile [10 rows][4*MSUB+2 px][64 ch] in shared memory, four transform
 //        warps interpolate it into the swizzled halo tile (shared-memory reads instead of global-load latency).
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0>
+// NS   : tile streams per CTA.  1 = one MMA-issuing thread walks all tiles.  2 = the CTA's tiles alternate between two streams, each
+//        with its own MMA-issuing warp, half of the activation stages, half of the accumulator slots and its own epilogue
+//        group(s); the TMA producers and resident weights are shared.  A single thread issues one tcgen05.mma per ~39 cycles
+//        (tools/umma_queue_probe.cu) next to its barrier traffic, which is as long as an N = 64 MMA runs (48 cycles) and not
+//        far from the half-phase mix of level 0: two issuers keep the tensor pipe fed where one cannot.
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0, int NS = 1>
 struct ConvCfgV2 {
     static constexpr int BOXES = 1;                    // TMA boxes per stage
     static constexpr int BOX_CH = KCS;                 // channels per box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte, SWIZZLE_64B)
@@ -119,7 +124,7 @@ struct ConvCfgV2 {
                   "CTA pairs: streamed 9-tap schedule (N = 128 or 64), or the resident half-phase schedule (level 0: each CTA keeps half of every weight block)");
     static constexpr int B_STAGE = HALF ? 6 * B_BLOCK : (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8)) * B_BLOCK;   // resident bytes per stage
     static constexpr int B_BYTES = RES ? (SB / (SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8))) * B_STAGE : SB * B_BLOCK;
-    static constexpr int THREADS = v2_threads(EW, XF);
+    static constexpr int THREADS = v2_threads(EW, XF, NS);
     static constexpr int RAW_W = 4 * MSUB + 2, RAW_H = kTileH / 2 + 2;            // raw coarse tile (XF)
     static constexpr int RAW_BYTES = RAW_H * RAW_W * 128;
     static constexpr int RAW_STRIDE = (RAW_BYTES + 1023) / 1024 * 1024;
@@ -127,6 +132,9 @@ struct ConvCfgV2 {
     static_assert(!XF || (CG == 1 && SCHED == 0), "transform stage: single CTA, 9-tap schedule");
     static_assert(!XF || ((8 * MSUB + 2) % 2 == 0 && (kTileH + 2) % 2 == 0), "transform stage works on 2x2 cells of the halo tile");
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
+    static constexpr int SAQ = SA / NS, SLQ = SLOTS / NS, SBQ = SB / NS, EWQ = EW / NS;   // per tile stream
+    static_assert(NS == 1 || (NS == 2 && CG == 1 && !XF && SA % 2 == 0 && SLOTS % 2 == 0 && EW % 2 == 0 && (RES || SB % 2 == 0)),
+                  "two tile streams: single CTA, no transform stage, even stage / slot / epilogue-group counts");
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;
@@ -141,7 +149,7 @@ struct ConvCfgV2 {
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
     static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert((SCHED == 0 && KB == KCS) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
-    static_assert(MSUB >= 1 && MSUB <= SLOTS && SLOTS <= 32 && SLOTS % EW == 0, "accumulator slots");
+    static_assert(MSUB >= 1 && MSUB <= SLOTS / NS && SLOTS <= 32 && SLOTS % EW == 0, "accumulator slots");
     static_assert(!RES || SB % N_ENT == 0, "resident weights: SB counts whole stages of blocks");
     // half entry? (parity, e) -> 0 full | 1 lower columns [0,64) (a = 0) | 2 upper columns [64,128) (a = 1)
     __host__ __device__ static constexpr int half_of(int parity, int e) {
@@ -172,9 +180,11 @@ struct TileWalkV2 {
     int u, u_end;
     int nt, n, ty, sx0;          // decomposition of u
     int rank;                    // CTA pairs: rank in the pair (0 otherwise)
+    int k;                       // running number of the tile returned last by next() (tile streams: stream = k % NS)
     __device__ __forceinline__ void init(const ConvParamsV2& p, int cg = 1, int cta_rank = 0) {
         const unsigned wid = blockIdx.x / cg, nw = gridDim.x / cg;     // work-sharing entity: CTA or CTA pair
         rank = cta_rank;
+        k = -1;
         u = (int)((long long)p.total_units * wid / nw);
         u_end = (int)((long long)p.total_units * (wid + 1) / nw);
         if (cg == 2) {                           // pairs: even range boundaries (see next())
@@ -193,6 +203,7 @@ struct TileWalkV2 {
     template <int MSUB, int CG = 1>
     __device__ __forceinline__ bool next(const ConvParamsV2& p, TileV2& t) {
         if (u >= u_end) return false;
+        ++k;
         t.nt = nt; t.n = n; t.ty = ty;
         // equal-size tiles within the run of units up to the band / range end (7 units -> 3+2+2, not 3+3+1): a 1-sub-tile
         // remainder tile would stream a full set of weight blocks for a quarter of the MMAs
@@ -213,17 +224,19 @@ struct TileWalkV2 {
 };
 
 // F16 : 16-bit format of activations and weights: 0 bf16 (default) | 1 fp16 (precision mode); same kernel otherwise
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16>
-__global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16, int NS>
+__global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tmo,
                                                                      const __grid_constant__ CUtensorMap tmw) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;       // CTA pair: rank 0 is the leader (issues the MMAs)
     constexpr int N_ENT = C::N_ENT;
     constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
     constexpr int W_X = 4 * EW + 3;                                      // XF: four transform warps W_X .. W_X+3
+    constexpr int W_MMA1 = 4 * EW + 3 + 4 * XF;                          // NS = 2: the second stream's MMA warp
+    constexpr int SAQ = C::SAQ, SLQ = C::SLQ, SBQ = C::SBQ, EWQ = C::EWQ;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
     uint8_t* smem = smem_raw + (s_base - smem_u32(smem_raw));
@@ -298,10 +311,12 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
         // =========================================================== activation halo tiles (TMA), one elected thread
         if (elect_one()) {
             int it = 0;
+            int itq[2] = {0, 0};                      // stage uses per tile stream (tiles are produced in walk order, each into its stream's ring)
             long long tw = 0, t00 = clock64();
             while (walk.next<MSUB, CG>(p, t)) {
                 const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;          // halo origin; OOB -> zero fill
                 const int st_rot = rot_of(t);
+                const int q = (NS == 2) ? (walk.k & 1) : 0;
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                     if constexpr (XF != 0) {   // raw coarse tile of chunk st into the staging ring; the transform warps fill the A stage
@@ -311,9 +326,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         tma_load_4d(s_base + C::OFF_RAW + rs * C::RAW_STRIDE, &tm0, st * 64, t.sx0 * 4 - 1, t.ty * (kTileH / 2) - 1, t.n, raw_full(rs));
                         continue;
                     } else {
-                    const int stage = it % SA;
+                    const int stage = q * SAQ + itq[q] % SAQ;
                     const long long c0 = prof ? clock64() : 0;
-                    mbar_wait(a_empty(stage), ((it / SA) & 1) ^ 1);
+                    mbar_wait(a_empty(stage), ((itq[q] / SAQ) & 1) ^ 1);
+                    ++itq[q];
                     if (prof) tw += clock64() - c0;
                     if (dbg & 1) { mbar_arrive(a_full(stage)); continue; }
                     const bool first = st < p.c0_chunks;
@@ -364,18 +380,20 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                         bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.wpack) + off, (uint32_t)min(gran, total - off));
                     }
                 }
-                int cnt = 0;
+                int cntq[2] = {0, 0};
                 while (walk.next<MSUB, CG>(p, t)) {
                     const __nv_bfloat16* wsrc = p.wpack + (size_t)t.nt * nblk * (NT * KB);
                     const int st_rot = rot_of(t);
-                    for (int bi = 0; bi < nblk; ++bi, ++cnt) {
-                        const int slot = cnt % SB;
+                    const int q = (NS == 2) ? (walk.k & 1) : 0;
+                    for (int bi = 0; bi < nblk; ++bi) {
+                        const int cnt = cntq[q]++;
+                        const int slot = q * SBQ + cnt % SBQ;
                         const int si = bi / N_ENT, e = bi - si * N_ENT;
                         const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                         const int b = st * N_ENT + e;
                         uint32_t bytes = C::B_BLOCK;
                         if (C::HALF && ((st & 1) ? (e < 4) : (e >= 4))) bytes = C::B_BLOCK / 2;
-                        mbar_wait(b_empty(slot), ((cnt / SB) & 1) ^ 1);
+                        mbar_wait(b_empty(slot), ((cnt / SBQ) & 1) ^ 1);
                         if (dbg & 2) { mbar_arrive(b_full(slot)); continue; }
                         if (CG == 2) {
                             // this CTA's half (N/2 rows) of block b, as a 64-row x 128-byte box of the packed weights viewed
@@ -392,7 +410,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
             }
         }
         __syncwarp();
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA || (NS == 2 && warp == W_MMA1)) {
+        const int q = (NS == 2 && warp == W_MMA1) ? 1 : 0;              // tile stream of this issuer
         // =========================================================== MMA issuer: ONE elected thread runs the whole role
         // (no per-entry warp re-convergence; entries, K steps and their descriptor offsets are compile-time)
         // CTA pairs: only the leader issues (M = 256 over both CTAs); its commits arrive on both CTAs' barriers.
@@ -429,15 +448,15 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                     if (RES) {
                         b_e = (hf ? b_lo0h : b_lo0) + b_st + (uint32_t)(C::res_off(PAR, e) >> 4);
                     } else {
-                        slot = cnt % SB;
+                        slot = q * SBQ + cnt % SBQ;
                         if (!b_rdy) {
                             const long long c0 = prof ? clock64() : 0;
-                            mbar_wait(b_full(slot), (cnt / SB) & 1);
+                            mbar_wait(b_full(slot), (cnt / SBQ) & 1);
                             if (prof) twb += clock64() - c0;
                         }
                         tc_fence_after();
                         ++cnt;
-                        b_rdy = mbar_test(b_full(cnt % SB), (cnt / SB) & 1);  // next block: polled while this entry's MMAs issue
+                        b_rdy = mbar_test(b_full(q * SBQ + cnt % SBQ), (cnt / SBQ) & 1);  // next block: polled while this entry's MMAs issue
                         b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
                     }
                     const uint32_t a_e = a_st + C::ent_off(PAR, e);
@@ -447,7 +466,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                     const long long cm0 = prof ? clock64() : 0;
 #pragma unroll
                     for (int j = 0; j < M; ++j) {
-                        const int ts = (slot0 + j) % C::SLOTS;                // accumulator slots are used round-robin
+                        const int ts = q * SLQ + (slot0 + j) % SLQ;           // accumulator slots (of this stream) are used round-robin
                         if (e == 0 && first_stage) {    // first write into this slot: the epilogue must have drained its previous use
                             const long long c0 = prof ? clock64() : 0;
                             mbar_wait(acc_empty(ts), ((use_bits >> ts) & 1) ^ 1);
@@ -474,33 +493,34 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
             };
             if (CG == 2 && RES) mbar_wait(w_ready, 0);      // pairs with resident weights: both CTAs' halves are in place
             while (walk.next<MSUB, CG>(p, t)) {
+                if (NS == 2 && (walk.k & 1) != q) continue;                  // the other stream's tile
                 const int m = t.m;
                 const int st_rot = rot_of(t);
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
-                    const int stage = it % SA;
+                    const int stage = q * SAQ + it % SAQ;
                     if (!a_rdy) {
                         const long long c0 = prof ? clock64() : 0;
-                        mbar_wait(a_full(stage), (it / SA) & 1);
+                        mbar_wait(a_full(stage), (it / SAQ) & 1);
                         if (prof) twa += clock64() - c0;
                     }
                     if (RES && ntile == 0)                                    // resident weights: first use of this stage's blocks
                         for (int e = 0; e < N_ENT; ++e) mbar_wait(b_full(st * N_ENT + e), 0);
                     tc_fence_after();
-                    a_rdy = mbar_test(a_full((it + 1) % SA), ((it + 1) / SA) & 1);   // next stage: polled while this one issues
+                    a_rdy = mbar_test(a_full(q * SAQ + (it + 1) % SAQ), ((it + 1) / SAQ) & 1);   // next stage: polled while this one issues
                     if (SCHED == 2 && (st & 1)) run_m(std::integral_constant<int, 1>{}, m, st, si == 0, stage);
                     else run_m(std::integral_constant<int, 0>{}, m, st, si == 0, stage);
                 }
                 for (int j = 0; j < m; ++j) {
-                    const int ts = (slot0 + j) % C::SLOTS;
+                    const int ts = q * SLQ + (slot0 + j) % SLQ;
                     commit(acc_full(ts));
                     use_bits ^= 1u << ts;
                 }
-                slot0 = (slot0 + m) % C::SLOTS;
+                slot0 = (slot0 + m) % SLQ;
                 ++ntile;
             }
-            if (prof) { pprof[3] = twa; pprof[4] = twb; pprof[5] = twc; pprof[6] = clock64() - t00; pprof[7] = ntile; pprof[10] = tmma; pprof[11] = tcom; }
-            if (pprof) { pprof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; pprof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
+            if (prof && q == 0) { pprof[3] = twa; pprof[4] = twb; pprof[5] = twc; pprof[6] = clock64() - t00; pprof[7] = ntile; pprof[10] = tmma; pprof[11] = tcom; }
+            if (pprof && q == 0) { pprof[16 + 4 * blockIdx.x + 0] = t00 - t_begin; pprof[16 + 4 * blockIdx.x + 1] = clock64() - t_begin; }   // roles start, MMA role end
         }
         __syncwarp();
     } else if (XF && warp >= W_X) {
@@ -560,19 +580,23 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
       }
     } else if (warp < 4 * EW) {
         // =========================================================== epilogue: EW groups of 4 warps (quadrant = warp % 4)
-        const int quad = warp & 3, grp = warp >> 2;
+        // (two tile streams: group g drains stream g % 2)
+        const int quad = warp & 3;
+        const int q = (NS == 2) ? ((warp >> 2) & 1) : 0;                // tile stream this group drains
+        const int grp = (warp >> 2) / NS;                               // group number within the stream
         const int mrow = quad * 32 + lane;              // accumulator row == TMEM lane
         const int ly = mrow >> 3, lx = mrow & 7;
         int slot0 = 0, seq = 0;                         // seq: running sub-tile number; group grp drains seq % EW == grp
         uint32_t use_bits = 0;
         long long twf = 0, t00 = clock64();
         while (walk.next<MSUB, CG>(p, t)) {
+            if (NS == 2 && (walk.k & 1) != q) continue;                  // the other stream's tile
             const int gy = t.ty * kTileH + ly;
             const float* bsrc = bias_s + t.nt * NT;
 #pragma unroll 1
             for (int j = 0; j < t.m; ++j) {
-                if (EW > 1 && ((seq + j) % EW) != grp) continue;
-                const int ts = (slot0 + j) % C::SLOTS;
+                if (EWQ > 1 && ((seq + j) % EWQ) != grp) continue;
+                const int ts = q * SLQ + (slot0 + j) % SLQ;
                 { const long long c0 = prof ? clock64() : 0;
                   mbar_wait(acc_full(ts), (use_bits >> ts) & 1);
                   if (prof) twf += clock64() - c0; }
@@ -586,7 +610,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 // SLOTS - MSUB free slots): the slot goes back to the MMA thread as soon as its last column is in registers,
                 // before the bias / activation / staging / store of that data.  (Measured: -4 % on the level-0 cat conv;
                 // with double-buffered slots the earlier hand-back only adds contention: +5 % on the head convs.)
-                constexpr bool EARLY = 2 * MSUB > C::SLOTS;
+                constexpr bool EARLY = 2 * MSUB > SLQ;
                 auto release_slot = [&]() {
                     tc_fence_before();
                     if (CG == 2) mbar_arrive_cluster(leader_bar(acc_empty(ts))); else mbar_arrive(acc_empty(ts));
@@ -767,8 +791,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF), 1) conv3x3_tma_kernel(cons
                 }
                 if (!released) release_slot();                  // (CTA pairs: the leader's MMA thread waits for both CTAs)
             }
-            for (int j = 0; j < t.m; ++j) use_bits ^= 1u << ((slot0 + j) % C::SLOTS);
-            slot0 = (slot0 + t.m) % C::SLOTS;
+            for (int j = 0; j < t.m; ++j) use_bits ^= 1u << (q * SLQ + (slot0 + j) % SLQ);
+            slot0 = (slot0 + t.m) % SLQ;
             seq += t.m;
         }
         if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed

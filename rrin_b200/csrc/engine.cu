@@ -80,7 +80,7 @@ static int up_cfg() {
 // level-1 block.0 conv on the pooled 32-channel level-0 tensor: TMA config 21 (RRIN_POOL1_CFG=3: the cp.async-fed v1 kernel)
 static int pool1_cfg() {
     static const int c = getenv("RRIN_POOL1_CFG") ? atoi(getenv("RRIN_POOL1_CFG")) : 21;
-    return c == 3 ? 3 : 21;
+    return (c == 3 || c == 39) ? c : 21;
 }
 
 // level-1 plain / cat convs on CTA pairs (config 22): experimental, RRIN_L1_PAIR=1
@@ -88,17 +88,18 @@ static bool l1_pair() {
     static const bool on = getenv("RRIN_L1_PAIR") && atoi(getenv("RRIN_L1_PAIR")) != 0;
     return on;
 }
-// level-1 64->64 / cat(64+64)->64 config ids: RRIN_L1_CFG=<a>,<b> with a in {14, 28, 30}, b in {15, 29, 31} (28-31: CTA pairs
-// with resident half-blocks)
+// level-1 64->64 / cat(64+64)->64 config ids.  64->64: two tile streams per CTA on 16 x 8 tiles (config 36; N = 64 MMAs run 48
+// cycles, one thread issues one per ~39: 0.21 -> 0.18 ms against the single-issuer config 14).  RRIN_L1_CFG=<a>,<b> with a in
+// {14, 28, 30, 36, 43}, b in {15, 22, 29, 31, 41, 42} (22, 28-31: CTA pairs; 36, 41-43: two tile streams)
 static void l1_cfgs(int& c64, int& ccat) {
     static int a = -1, b = -1;
     if (a < 0) {
-        a = 14; b = 15;
+        a = 36; b = 15;
         const char* e = getenv("RRIN_L1_CFG");
         int x = 0, y = 0;
         if (e && sscanf(e, "%d,%d", &x, &y) == 2) {
-            if (x == 14 || x == 28 || x == 30) a = x;
-            if (y == 15 || y == 29 || y == 31) b = y;
+            if (x == 14 || x == 28 || x == 30 || x == 36 || x == 43) a = x;
+            if (y == 15 || y == 22 || y == 29 || y == 31 || y == 41 || y == 42) b = y;
         }
     }
     c64 = a; ccat = b;
@@ -106,18 +107,19 @@ static void l1_cfgs(int& c64, int& ccat) {
 
 // Level-0 cat(32+32)->32 conv: CTA pairs that keep the layer's 192 KB of space-to-depth weights resident as two 96 KB halves
 // (config 25; measured 0.44 -> 0.33 ms per 4-pair launch against the single-CTA config 12, which re-streams them per tile).
-// The 32->32 conv stays on the single-CTA config 11 (its 96 KB fit one SM; the pair variants 23 / 26 / 27 measured slower).
-// RRIN_L0_PAIR=0 selects 11 / 12; RRIN_L0_PAIR=<a>,<b> picks explicit ids (A/B runs: a in {11,23,26,27}, b in {12,24,25}).
+// Level-0 32->32 conv: its 96 KB of weights fit one SM; two tile streams per CTA (config 35: two MMA-issuing warps; 0.27 / 0.25 ->
+// 0.24 / 0.21 ms against the single-issuer config 11; the pair variants 23 / 26 / 27 measured slower).
+// RRIN_L0_PAIR=0 selects 11 / 12; RRIN_L0_PAIR=<a>,<b> picks explicit ids (A/B runs: a in {11,23,26,27,35}, b in {12,24,25}).
 static void l0_pair_cfgs(int& c32, int& ccat) {
     static int a = -1, b = -1;
     if (a < 0) {
-        a = 11; b = 25;
+        a = 35; b = 25;
         const char* e = getenv("RRIN_L0_PAIR");
         if (e) {
             int x = 0, y = 0;
             const int n = sscanf(e, "%d,%d", &x, &y);
             if (n == 1 && x == 0) { a = 11; b = 12; }
-            else if (n == 2) { a = (x == 23 || x == 26 || x == 27 || x == 11) ? x : 23; b = (y == 24 || y == 25 || y == 12) ? y : 24; }
+            else if (n == 2) { a = (x == 23 || x == 26 || x == 27 || x == 11 || x == 35) ? x : 35; b = (y == 24 || y == 25 || y == 12) ? y : 25; }
         }
     }
     c32 = a; ccat = b;
@@ -141,12 +143,13 @@ static Schedule build_schedule() {
         // configs 10..16: TMA-fed kernel (conv3x3_v2.cuh: every source that is a stored tensor as-is)
         if (level == 0) {                       // space-to-depth: 4 phases x cout columns on the half-res grid
             m.n_cols = is_last ? 16 : 128;
-            if (src == K_HEAD) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 10; m.n_stages = 1; }
+            static const int head_cfg = [] { const char* e = getenv("RRIN_HEAD_CFG"); return (e && atoi(e) == 38) ? 38 : 10; }();
+            if (src == K_HEAD) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = head_cfg; m.n_stages = 1; }
             else if (src == K_UP) { m.kind = PACK_S2D; m.sched = SCHED_S2D16; m.cfg = 1; m.n_stages = cin / 32; }   // exact bilinear (ring / small frames)
             else {
                 int c32, ccat;
                 l0_pair_cfgs(c32, ccat);
-                static const int last_cfg = [] { const char* e = getenv("RRIN_LAST_CFG"); const int v = e ? atoi(e) : 13; return (v >= 32 && v <= 34) ? v : 13; }();
+                static const int last_cfg = [] { const char* e = getenv("RRIN_LAST_CFG"); const int v = e ? atoi(e) : 37; return (v == 13 || (v >= 32 && v <= 34) || v == 37 || v == 40) ? v : 37; }();
                 m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? last_cfg : (cin == 32 ? c32 : ccat); m.n_stages = 2 * (cin / 32);
                 if (m.cfg >= 23 && m.cfg <= 27) m.kind = PACK_S2D8_CG2;
             }
@@ -160,7 +163,7 @@ static Schedule build_schedule() {
                     l1_cfgs(c64, ccat);
                     m.cfg = (src == K_UP) ? 4 : (cin == 64 ? c64 : ccat); m.n_stages = cin / 64;
                     if (src != K_UP && l1_pair()) m.cfg = 22;
-                    if (m.cfg == 22 || m.cfg >= 28) m.kind = PACK_NORMAL_CG2;
+                    if (m.cfg == 22 || (m.cfg >= 28 && m.cfg <= 31)) m.kind = PACK_NORMAL_CG2;
                 }
             } else {
                 m.cfg = (src == K_UP) ? up_cfg() : big_cfg(); m.n_stages = cin / 64;

@@ -70,12 +70,12 @@ def test_conv_config_table_is_consistent():
     l = lib()
     v = [C.c_int() for _ in range(4)]
     valid = {}
-    for cfg in range(-1, 40):
+    for cfg in range(-1, 64):
         if l.rrin_conv_config_info(cfg, *map(C.byref, v)) == 0:
             valid[cfg] = tuple(x.value for x in v)                       # kcs, kb, nt, msub
-    assert set(valid) == set(range(0, 9)) | set(range(10, 35)), sorted(valid)
+    assert set(valid) == set(range(0, 9)) | set(range(10, 44)), sorted(valid)
     for cfg, (kcs, kb, nt, msub) in valid.items():
-        assert kcs in (32, 64, 128) and kb in (16, 32, 64) and kb <= kcs and nt in (16, 64, 128) and 1 <= msub <= 4
+        assert kcs in (32, 64, 128) and kb in (16, 32, 64) and kb <= kcs and nt in (16, 64, 128) and 1 <= msub <= 4, (cfg, kcs, kb, nt, msub)
         if cfg >= 10:
             assert msub * nt <= 512, "a tile's accumulators fit TMEM"
     assert valid[21][:3] == (32, 32, 64) and valid[22][:3] == (64, 64, 64)
