@@ -115,8 +115,10 @@ RRIN_API int rrin_engine_tap(const rrin_engine* e, const void* workspace, int wh
  *   sched 2  : half-phase schedule of the TMA-fed kernel for level-0 tensors (pack kind 3)
  *   pool_out : optional second output of the TMA-epilogue configs: F.avg_pool2d(out, 2) (unet.py:46) written by the
  *              same epilogue, bf16 NHWC [N,H/2,W/2,cout_stride] (space-to-depth grid: [N,H,W,cout_stride/4]); or NULL
- *   cfg      : tile configuration: 0..8 transform kernel (pool / bilinear sources, border strips), 10..21 TMA-fed kernel
- *              (rrin_conv_config_info gives KCS, KB, NT, MSUB; 21 = 32 stored channels per pixel).
+ *   cfg      : tile configuration: 0..8 transform kernel (pool / bilinear sources, border strips), 10..44 TMA-fed kernel
+ *              (rrin_conv_config_info gives KCS, KB, NT, MSUB; the table with the CTA-pair, two-tile-stream and
+ *              frame-staging variants is in rrin_b200/csrc/conv3x3_launch.cuh).
+ *   pack kind: ... 4 plain, CTA-pair halves | 5 half-phase space-to-depth, CTA-pair halves
  *   alignment: activation / output / pooled tensors 32-byte aligned (TMA maps and 256-bit stores); a misaligned
  *              pointer is rejected with RRIN_ERR_BAD_ARG. */
 RRIN_API int rrin_conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);

@@ -36,16 +36,16 @@ namespace rrin {
     X(8, 64, 16, 128, 1, 3, 12, 1)
 
 constexpr int kV2Base = 10;
-struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf; };
+struct CfgInfo { int kcs, kb, nt, msub, sa, sb, smem, ps, pw, sched, res, etma, strip, cg, xf, fs; };
 static const CfgInfo kCfg1[] = {
 #define X(id, KCS, KB, NT, MSUB, SA, SB, STRIP) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP, 1, 0},
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::SMEM_BYTES, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PS, ConvCfg<KCS, KB, NT, MSUB, SA, SB, STRIP>::PW, -1, 0, 0, STRIP, 1, 0, 0},
     RRIN_CONV_CONFIGS(X)
 #undef X
 };
 static const CfgInfo kCfg2[] = {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS) \
-    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>::PW, SCHED, RES, ETMA, 0, CG, XF},
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS) \
+    {KCS, KB, NT, MSUB, SA, SB, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS>::SMEM_BYTES, 0, ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS>::PW, SCHED, RES, ETMA, 0, CG, XF, FS},
     RRIN_CONV2_CONFIGS(X)
 #undef X
 };
@@ -344,6 +344,25 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }
     CUtensorMap tmw = tm0;
+    if (c.fs && d.fuse.mode == 2) {
+        // frame staging: tensor maps of the two fp32 NCHW frames [n_pairs,3,H,W], box = the tile's window {8*MSUB*2+20, 2*16+16, 3, 1},
+        // out-of-image elements read as zero (grid_sample's zeros padding, model.py:20); carried in the otherwise unused map slots
+        EncodeTiledFn fn = encode_fn();
+        if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return RRIN_ERR_UNSUPPORTED; }
+        const int FH = d.fuse.H, FW = d.fuse.W, np = d.fuse.pair_mul ? d.fuse.Nt : 1;
+        const cuuint64_t dims[4] = {(cuuint64_t)FW, (cuuint64_t)FH, 3, (cuuint64_t)np};
+        const cuuint64_t strides[3] = {(cuuint64_t)FW * 4, (cuuint64_t)FH * FW * 4, (cuuint64_t)3 * FH * FW * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)(8 * c.msub * 2 + 16 + 4), (cuuint32_t)(2 * kTileH + 16), 3, 1};     // ConvCfgV2::FRM_W x FRM_H
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const float* frames[2] = {d.fuse.in0, d.fuse.in1};
+        CUtensorMap* maps[2] = {&tmo, &tmw};
+        for (int f = 0; f < 2; ++f) {
+            if (reinterpret_cast<uintptr_t>(frames[f]) & 15) { set_error("conv3x3(tma): frames must be 16-byte aligned for frame staging"); return RRIN_ERR_BAD_ARG; }
+            CUresult r = fn(maps[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(frames[f]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for a %dx%d frame", (int)r, FH, FW); return RRIN_ERR_CUDA; }
+        }
+    }
     if (c.cg == 2) {
         // packed weights as a 2-D tensor of 128-byte rows: a CTA's half of a block is a box of (bytes / 128) rows
         EncodeTiledFn fn = encode_fn();

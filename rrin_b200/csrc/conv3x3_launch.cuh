@@ -3,7 +3,7 @@
 #pragma once
 #include "conv3x3_v2.cuh"
 
-// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>  (XF = 0, NS = 1 unless noted)
+// TMA-fed kernel (conv3x3_v2.cuh), ids 10.. : <KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS>  (XF = 0, NS = 1, FS = 0 unless noted)
 // 10 : < 64, 16, 128, 2, 3, 16, S2D16, 1, 1, 2, 1>  level-0 head convs (packed 4 phases x 16 ch), 16 entries, weights resident
 // 11 : < 64, 32, 128, 1, 4, 16, S2D8 , 1, 1, 2, 1>  level-0 32->32, two half-phase stages x 8 entries, weights resident (96 KB)
 // 12 : < 64, 32, 128, 3, 2,  8, S2D8 , 0, 1, 2, 1>  level-0 cat(32+32)->32, four stages x 8 entries, weights streamed
@@ -35,42 +35,45 @@
 //           and its own epilogue group.  35 = config 11 (level-0 32->32), 36 = level-1 64->64 with 16 x 8 tiles, 37 / 40 = level-0
 //           `last` (16 x 16 / 16 x 8 tiles), 38 = level-0 heads with 16 x 8 tiles, 39 = level-1 block.0 on the pooled 32-channel tensor
 //           41 / 42 = level-1 cat(64+64)->64 (16 x 16 / 16 x 32 tiles, one stage per stream), 43 = level-1 64->64 with 16 x 16 tiles
+// 44 : level-0 `last` with FRAME STAGING (FS = 1, last column): refine_flow.last, whose epilogue runs both backward warps -- the 48 x 48
+//      pixel windows of the two source frames are TMA-loaded into shared memory per tile and the bilinear taps are gathered from there
 // 32 / 33 / 34 : level-0 `last` (config 13) with 16 x 8 tiles and four / eight stages, or 16 x 16 tiles and four stages
 #define RRIN_CONV2_CONFIGS(X)                   \
-    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0, 1) \
-    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0, 1) \
-    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1, 0, 1)  \
-    X(13, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0, 1)  \
-    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1, 0, 1)   \
-    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1, 0, 1)   \
-    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0, 1)  \
-    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1, 0, 1)  \
-    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0, 1)  \
-    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0, 1) \
-    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1, 1) \
-    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0, 1) \
-    X(22, 64, 64, 64, 4, 2, 8, 0, 0, 1, 2, 2, 0, 1) \
-    X(23, 64, 32, 128, 2, 3, 16, 2, 1, 1, 2, 2, 0, 1) \
-    X(24, 64, 32, 128, 2, 2, 32, 2, 1, 1, 2, 2, 0, 1) \
-    X(25, 64, 32, 128, 1, 4, 32, 2, 1, 1, 2, 2, 0, 1) \
-    X(26, 64, 32, 128, 3, 2, 16, 2, 1, 1, 2, 2, 0, 1) \
-    X(27, 64, 32, 128, 1, 6, 16, 2, 1, 1, 2, 2, 0, 1) \
-    X(28, 64, 64, 64, 2, 4, 9, 0, 1, 1, 1, 2, 0, 1) \
-    X(29, 64, 64, 64, 2, 3, 18, 0, 1, 1, 1, 2, 0, 1) \
-    X(30, 64, 64, 64, 1, 6, 9, 0, 1, 1, 2, 2, 0, 1) \
-    X(31, 64, 64, 64, 1, 4, 18, 0, 1, 1, 2, 2, 0, 1) \
-    X(32, 64, 32, 16, 1, 4, 16, 2, 1, 0, 2, 1, 0, 1) \
-    X(33, 64, 32, 16, 1, 8, 16, 2, 1, 0, 2, 1, 0, 1) \
-    X(34, 64, 32, 16, 2, 4, 16, 2, 1, 0, 2, 1, 0, 1) \
-    X(35, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0, 2) \
-    X(36, 64, 64, 64, 1, 4, 9, 0, 1, 1, 2, 1, 0, 2) \
-    X(37, 64, 32, 16, 2, 4, 16, 2, 1, 0, 2, 1, 0, 2) \
-    X(38, 64, 16, 128, 1, 4, 16, 1, 1, 1, 2, 1, 0, 2) \
-    X(39, 32, 32, 64, 2, 4, 9, 0, 1, 1, 2, 1, 0, 2) \
-    X(40, 64, 32, 16, 1, 4, 16, 2, 1, 0, 2, 1, 0, 2) \
-    X(41, 64, 64, 64, 2, 2, 8, 0, 0, 1, 2, 1, 0, 2) \
-    X(42, 64, 64, 64, 4, 2, 4, 0, 0, 1, 2, 1, 0, 2) \
-    X(43, 64, 64, 64, 2, 2, 9, 0, 1, 1, 2, 1, 0, 2)
+    X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0, 1, 0) \
+    X(11, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0, 1, 0) \
+    X(12, 64, 32, 128, 3, 2, 8, 2, 0, 1, 2, 1, 0, 1, 0)  \
+    X(13, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0, 1, 0)  \
+    X(14, 64, 64, 64, 2, 3, 9, 0, 1, 1, 1, 1, 0, 1, 0)   \
+    X(15, 64, 64, 64, 4, 2, 6, 0, 0, 1, 1, 1, 0, 1, 0)   \
+    X(16, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0, 1, 0)  \
+    X(17, 64, 64, 128, 3, 2, 4, 0, 0, 0, 2, 1, 0, 1, 0)  \
+    X(18, 64, 64, 128, 3, 2, 4, 0, 0, 1, 2, 1, 0, 1, 0)  \
+    X(19, 64, 64, 128, 3, 2, 6, 0, 0, 1, 2, 2, 0, 1, 0) \
+    X(20, 64, 64, 128, 2, 2, 4, 0, 0, 1, 2, 1, 1, 1, 0) \
+    X(21, 32, 32, 64, 4, 3, 9, 0, 1, 1, 1, 1, 0, 1, 0) \
+    X(22, 64, 64, 64, 4, 2, 8, 0, 0, 1, 2, 2, 0, 1, 0) \
+    X(23, 64, 32, 128, 2, 3, 16, 2, 1, 1, 2, 2, 0, 1, 0) \
+    X(24, 64, 32, 128, 2, 2, 32, 2, 1, 1, 2, 2, 0, 1, 0) \
+    X(25, 64, 32, 128, 1, 4, 32, 2, 1, 1, 2, 2, 0, 1, 0) \
+    X(26, 64, 32, 128, 3, 2, 16, 2, 1, 1, 2, 2, 0, 1, 0) \
+    X(27, 64, 32, 128, 1, 6, 16, 2, 1, 1, 2, 2, 0, 1, 0) \
+    X(28, 64, 64, 64, 2, 4, 9, 0, 1, 1, 1, 2, 0, 1, 0) \
+    X(29, 64, 64, 64, 2, 3, 18, 0, 1, 1, 1, 2, 0, 1, 0) \
+    X(30, 64, 64, 64, 1, 6, 9, 0, 1, 1, 2, 2, 0, 1, 0) \
+    X(31, 64, 64, 64, 1, 4, 18, 0, 1, 1, 2, 2, 0, 1, 0) \
+    X(32, 64, 32, 16, 1, 4, 16, 2, 1, 0, 2, 1, 0, 1, 0) \
+    X(33, 64, 32, 16, 1, 8, 16, 2, 1, 0, 2, 1, 0, 1, 0) \
+    X(34, 64, 32, 16, 2, 4, 16, 2, 1, 0, 2, 1, 0, 1, 0) \
+    X(35, 64, 32, 128, 1, 4, 16, 2, 1, 1, 2, 1, 0, 2, 0) \
+    X(36, 64, 64, 64, 1, 4, 9, 0, 1, 1, 2, 1, 0, 2, 0) \
+    X(37, 64, 32, 16, 2, 4, 16, 2, 1, 0, 2, 1, 0, 2, 0) \
+    X(38, 64, 16, 128, 1, 4, 16, 1, 1, 1, 2, 1, 0, 2, 0) \
+    X(39, 32, 32, 64, 2, 4, 9, 0, 1, 1, 2, 1, 0, 2, 0) \
+    X(40, 64, 32, 16, 1, 4, 16, 2, 1, 0, 2, 1, 0, 2, 0) \
+    X(41, 64, 64, 64, 2, 2, 8, 0, 0, 1, 2, 1, 0, 2, 0) \
+    X(42, 64, 64, 64, 4, 2, 4, 0, 0, 1, 2, 1, 0, 2, 0) \
+    X(43, 64, 64, 64, 2, 2, 9, 0, 1, 1, 2, 1, 0, 2, 0) \
+    X(44, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0, 1, 1)
 
 
 namespace rrin {
@@ -86,11 +89,11 @@ namespace {
 constexpr int kLaunchMaxDevices = 64, kLaunchMaxCfg = 64;
 bool g_v2_attr_set[kLaunchMaxDevices][kLaunchMaxCfg] = {};
 
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16, int NS>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16, int NS, int FS>
 int launch_cfg2(int id, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
                 const CUtensorMap& tmw, int grid, cudaStream_t stream) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>;
-    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, F16, NS>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS>;
+    auto kern = conv3x3_tma_kernel<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, F16, NS, FS>;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kLaunchMaxDevices || id < 0 || id >= kLaunchMaxCfg) { set_error("conv3x3: no current CUDA device"); return RRIN_ERR_CUDA; }
     if (!g_v2_attr_set[dev][id]) {
@@ -105,8 +108,8 @@ template <int F16>
 int launch_v2_impl(int cfg, const ConvParamsV2& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo,
                    const CUtensorMap& tmw, int grid, cudaStream_t stream) {
     switch (cfg) {
-#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS) \
-    case id: return launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, F16, NS>(id, p, tm0, tm1, tmo, tmw, grid, stream);
+#define X(id, KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS) \
+    case id: return launch_cfg2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, F16, NS, FS>(id, p, tm0, tm1, tmo, tmw, grid, stream);
         RRIN_CONV2_CONFIGS(X)
 #undef X
     }

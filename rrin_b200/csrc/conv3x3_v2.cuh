@@ -109,7 +109,11 @@ constexpr int v2_threads(int ew, int xf = 0, int ns = 1) { return (4 * ew + 3 + 
 //        group(s); the TMA producers and resident weights are shared.  A single thread issues one tcgen05.mma per ~39 cycles
 //        (tools/umma_queue_probe.cu) next to its barrier traffic, which is as long as an N = 64 MMA runs (48 cycles) and not
 //        far from the half-phase mix of level 0: two issuers keep the tensor pipe fed where one cannot.
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0, int NS = 1>
+// FS   : 1 = frame staging for the fused backward warps (refine_flow.last, FuseParams::mode 2): per tile, TMA loads the 48 x 48-pixel
+//        window (tile + 8-pixel halo, zero-filled outside the image = grid_sample's zeros padding) of all three planes of both
+//        source frames into shared memory; the epilogue gathers its 96 bilinear taps per block pixel from there and falls back to
+//        global loads only for samples whose flow leaves the window.
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG = 1, int XF = 0, int NS = 1, int FS = 0>
 struct ConvCfgV2 {
     static constexpr int BOXES = 1;                    // TMA boxes per stage
     static constexpr int BOX_CH = KCS;                 // channels per box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte, SWIZZLE_64B)
@@ -129,6 +133,15 @@ struct ConvCfgV2 {
     static constexpr int RAW_BYTES = RAW_H * RAW_W * 128;
     static constexpr int RAW_STRIDE = (RAW_BYTES + 1023) / 1024 * 1024;
     static constexpr int RAW_SLOTS = XF ? 2 : 0;
+    // staged frame window: tile width / height in pixels + 8 each side; 4 more columns on the right make the row pitch 52 floats, so the
+    // four block-pixel rows a warp gathers for (2 * 52 floats apart) start 8 banks apart instead of on the same bank (pitch 48)
+    static constexpr int FRM_W = 8 * MSUB * 2 + 16 + 4;
+    static constexpr int FRM_H = kTileH * 2 + 16;
+    static constexpr int FRM_PLANE = FRM_W * FRM_H * 4;                 // one fp32 plane of the window
+    static constexpr int FRM_BYTES = 2 * 3 * FRM_PLANE;                 // both frames, three planes each
+    static constexpr int FRM_STRIDE = (FRM_BYTES + 1023) / 1024 * 1024;
+    static constexpr int FRM_SLOTS = FS ? 2 : 0;
+    static_assert(!FS || (NT == 16 && !ETMA && CG == 1 && NS == 1 && !XF && SCHED == 2), "frame staging: the fp32 `last` epilogue, one tile stream");
     static_assert(!XF || (CG == 1 && SCHED == 0), "transform stage: single CTA, 9-tap schedule");
     static_assert(!XF || ((8 * MSUB + 2) % 2 == 0 && (kTileH + 2) % 2 == 0), "transform stage works on 2x2 cells of the halo tile");
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
@@ -141,9 +154,10 @@ struct ConvCfgV2 {
     static constexpr int EPI_STAGE = ETMA ? 4 * EW * 4096 : 0;         // per warp: 32 pixels x 64 channels bf16, SWIZZLE_128B
     static constexpr int OFF_EPI = OFF_B + B_BYTES;                     // 1024-byte aligned (A stages and weight blocks are)
     static constexpr int OFF_RAW = OFF_EPI + EPI_STAGE;                 // 1024-byte aligned
-    static constexpr int OFF_BIAS = OFF_RAW + RAW_SLOTS * RAW_STRIDE;
+    static constexpr int OFF_FRM = OFF_RAW + RAW_SLOTS * RAW_STRIDE;     // 1024-byte aligned
+    static constexpr int OFF_BIAS = OFF_FRM + FRM_SLOTS * FRM_STRIDE;
     static constexpr int OFF_BAR = OFF_BIAS + BIAS_MAX * 4;
-    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS + 1;   // + "resident weights of both CTAs have landed" (pairs)
+    static constexpr int NBAR = 2 * SA + 2 * SB + 2 * SLOTS + 2 * RAW_SLOTS + 2 * FRM_SLOTS + 1;   // + "resident weights of both CTAs have landed" (pairs)
     static constexpr int SMEM_BYTES = OFF_BAR + NBAR * 8 + 16 + 1024;   // +1024: manual alignment of the base
     static_assert(KCS == 64 || (KCS == 32 && SCHED == 0 && CG == 1 && !XF), "one 64-channel TMA box per stage (32: a 32-channel NHWC source)");
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
@@ -224,13 +238,13 @@ struct TileWalkV2 {
 };
 
 // F16 : 16-bit format of activations and weights: 0 bf16 (default) | 1 fp16 (precision mode); same kernel otherwise
-template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16, int NS>
+template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int SCHED, int RES, int ETMA, int EW, int CG, int XF, int F16, int NS, int FS>
 __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(const __grid_constant__ ConvParamsV2 p,
                                                                      const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tmo,
                                                                      const __grid_constant__ CUtensorMap tmw) {
-    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS>;
+    using C = ConvCfgV2<KCS, KB, NT, MSUB, SA, SB, SCHED, RES, ETMA, EW, CG, XF, NS, FS>;
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;       // CTA pair: rank 0 is the leader (issues the MMAs)
     constexpr int N_ENT = C::N_ENT;
     constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
@@ -252,6 +266,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
     auto acc_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + C::SLOTS + i); };
     auto raw_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + i); };
     auto raw_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + C::RAW_SLOTS + i); };
+    auto frm_full = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + 2 * C::RAW_SLOTS + i); };
+    auto frm_empty = [&](int i) { return s_bar + 8u * (2 * SA + 2 * SB + 2 * C::SLOTS + 2 * C::RAW_SLOTS + C::FRM_SLOTS + i); };
     const uint32_t w_ready = s_bar + 8u * (C::NBAR - 1);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + C::NBAR * 8);
 
@@ -276,9 +292,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), CG * kEpiWarps * 32); }   // both CTAs' epilogues
         mbar_init(w_ready, CG);
+        for (int i = 0; i < C::FRM_SLOTS; ++i) { mbar_init(frm_full(i), 1); mbar_init(frm_empty(i), 4 * EW); }   // one arrival per epilogue warp
         mbar_fence_init();
     }
-    if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA) tma_prefetch_desc(&tmo); if (CG == 2) tma_prefetch_desc(&tmw); }
+    if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA || FS) tma_prefetch_desc(&tmo); if (CG == 2 || FS) tma_prefetch_desc(&tmw); }
     for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
     if (warp == W_MMA) {
         if (CG == 2) { tmem_alloc_cg2(smem_u32(tmem_slot), 512); tmem_relinquish_cg2(); }
@@ -317,6 +334,18 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                 const int x0 = t.sx0 * 8 - 1, y0 = t.ty * kTileH - 1;          // halo origin; OOB -> zero fill
                 const int st_rot = rot_of(t);
                 const int q = (NS == 2) ? (walk.k & 1) : 0;
+                if constexpr (FS != 0) {
+                    // frame windows of this tile (tmo / tmw carry the tensor maps of the two fp32 frames): [frame][plane][FRM_H][FRM_W]
+                    if (p.fz.mode == 2) {
+                        const int fb = walk.k & 1;
+                        mbar_wait(frm_empty(fb), ((walk.k >> 1) & 1) ^ 1);
+                        mbar_arrive_expect_tx(frm_full(fb), C::FRM_BYTES);
+                        const uint32_t dst = s_base + C::OFF_FRM + fb * C::FRM_STRIDE;
+                        const int fx = t.sx0 * 16 - 8, fy = t.ty * (2 * kTileH) - 8, pn = t.n * p.fz.pair_mul;
+                        tma_load_4d(dst, &tmo, fx, fy, 0, pn, frm_full(fb));
+                        tma_load_4d(dst + 3 * C::FRM_PLANE, &tmw, fx, fy, 0, pn, frm_full(fb));
+                    }
+                }
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
                     if constexpr (XF != 0) {   // raw coarse tile of chunk st into the staging ring; the transform warps fill the A stage
@@ -593,6 +622,9 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
             if (NS == 2 && (walk.k & 1) != q) continue;                  // the other stream's tile
             const int gy = t.ty * kTileH + ly;
             const float* bsrc = bias_s + t.nt * NT;
+            const bool staged = (FS != 0) && p.fz.mode == 2;
+            const int fb = walk.k & 1;
+            if (staged) mbar_wait(frm_full(fb), (walk.k >> 1) & 1);      // this tile's frame windows have landed
 #pragma unroll 1
             for (int j = 0; j < t.m; ++j) {
                 if (EWQ > 1 && ((seq + j) % EWQ) != grp) continue;
@@ -736,8 +768,16 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                             float4 f[4];
 #pragma unroll
                             for (int ph = 0; ph < 4; ++ph) f[ph] = fz.aux[(pn * nb + q) * 4 + ph];
-                            glue_warp_block<F16>(f, v, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
-                                            fz.h16 + ((long)t.n * nb + q) * 64, reinterpret_cast<float4*>(fz.dst) + ((long)t.n * nb + q) * 8);
+                            if constexpr (FS != 0) {
+                                FrameWindow fw;
+                                fw.smem = s_base + C::OFF_FRM + fb * C::FRM_STRIDE;
+                                fw.x0 = t.sx0 * 16 - 8; fw.y0 = t.ty * (2 * kTileH) - 8; fw.w = C::FRM_W; fw.h = C::FRM_H;
+                                glue_warp_block_staged<F16>(f, v, fw, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
+                                                            fz.h16 + ((long)t.n * nb + q) * 64, reinterpret_cast<float4*>(fz.dst) + ((long)t.n * nb + q) * 8);
+                            } else {
+                                glue_warp_block<F16>(f, v, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef + t.n * 6, HW, fz.H, fz.W, gy, gx,
+                                                fz.h16 + ((long)t.n * nb + q) * 64, reinterpret_cast<float4*>(fz.dst) + ((long)t.n * nb + q) * 8);
+                            }
                         } else if (fz.mode == 3) {
                             const long pn = (long)t.n * fz.pair_mul, i = (long)t.n * nb + q;
                             glue_blend_block<F16>(v, fz.aux + i * 8, fz.in0 + pn * 3 * HW, fz.in1 + pn * 3 * HW, fz.coef[t.n * 6 + 4], fz.coef[t.n * 6 + 5],
@@ -790,6 +830,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                     }
                 }
                 if (!released) release_slot();                  // (CTA pairs: the leader's MMA thread waits for both CTAs)
+            }
+            if (staged) {                                 // every epilogue warp hands the window back, also one without a sub-tile in this tile
+                __syncwarp();
+                if (lane == 0) mbar_arrive(frm_empty(fb));
             }
             for (int j = 0; j < t.m; ++j) use_bits ^= 1u << (q * SLQ + (slot0 + j) % SLQ);
             slot0 = (slot0 + t.m) % SLQ;

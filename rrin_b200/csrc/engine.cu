@@ -89,12 +89,14 @@ static bool l1_pair() {
     return on;
 }
 // level-1 64->64 / cat(64+64)->64 config ids.  64->64: two tile streams per CTA on 16 x 8 tiles (config 36; N = 64 MMAs run 48
-// cycles, one thread issues one per ~39: 0.21 -> 0.18 ms against the single-issuer config 14).  RRIN_L1_CFG=<a>,<b> with a in
+// cycles, one thread issues one per ~39: 0.21 -> 0.18 ms against the single-issuer config 14).  cat(64+64)->64: CTA pairs with
+// streamed weights (config 22: one issuer drives two SMs, half of every weight block per SM; 0.35 -> 0.31 ms against config 15).
+// RRIN_L1_CFG=<a>,<b> with a in
 // {14, 28, 30, 36, 43}, b in {15, 22, 29, 31, 41, 42} (22, 28-31: CTA pairs; 36, 41-43: two tile streams)
 static void l1_cfgs(int& c64, int& ccat) {
     static int a = -1, b = -1;
     if (a < 0) {
-        a = 36; b = 15;
+        a = 36; b = 22;
         const char* e = getenv("RRIN_L1_CFG");
         int x = 0, y = 0;
         if (e && sscanf(e, "%d,%d", &x, &y) == 2) {
@@ -123,6 +125,13 @@ static void l0_pair_cfgs(int& c32, int& ccat) {
         }
     }
     c32 = a; ccat = b;
+}
+
+// refine_flow.last + fused backward warps: config 44 stages the frames' tile windows in shared memory (RRIN_WARP_STAGE=0: gather
+// from global memory like the other `last` epilogues)
+static bool warp_staging() {
+    static const bool on = [] { const char* e = getenv("RRIN_WARP_STAGE"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 static Schedule build_schedule() {
@@ -289,7 +298,7 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
         int kcs, kb, nt, msub;
         conv_config_info(ln.cd.cfg, &kcs, &kb, &nt, &msub);
         char b[128];
-        snprintf(b, sizeof b, "conv3x3_%s<KCS%d,KB%d,NT%d,MSUB%d>%s", ln.cd.cfg >= 10 ? "tma" : "umma", kcs, kb, nt, msub, tag);
+        snprintf(b, sizeof b, "conv3x3_%s#%d<KCS%d,KB%d,NT%d,MSUB%d>%s", ln.cd.cfg >= 10 ? "tma" : "umma", ln.cd.cfg, kcs, kb, nt, msub, tag);
         ln.name = b;
         const double lp = (double)B * (H >> L.level) * (W >> L.level);      // output pixels of the reference conv
         if (counts_flops) {
@@ -474,6 +483,10 @@ int rrin_engine_create_ex(int n_pairs, int n_samples, int H, int W, int precisio
         if (fuse) {
             Launch& last = e->launches.back();
             last.fuse_mode = u + 1;
+            if (u == 1 && warp_staging()) {             // refine_flow.last runs both backward warps: frame windows staged in shared memory
+                last.cd.cfg = 44;                       // (same packed weights and tensor-map geometry as the other `last` configs with 16 x 16 tiles)
+                last.name = "conv3x3_tma#44<KCS64,KB32,NT16,MSUB2>";
+            }
             last.name += " +glue";
             last.bytes += glue_bytes_px[u + 1] * (double)H * W * n_samples - 16.0 * H * W * n_samples;   // the fp32 hand-over tensor is not materialised
         } else {

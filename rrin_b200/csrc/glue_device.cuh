@@ -52,9 +52,18 @@ __device__ __forceinline__ void tscale(const float4 f, const float* __restrict__
 // warp() of model.py:8-21: sample img at (x+u-0.5, y+v-0.5), bilinear, zeros padding
 // (F.grid_sample defaults, align_corners=False).  The normalise/un-normalise round trip is
 // reproduced in the reference's fp32 op order (model.py:15-18, GridSampler.h:27-36).
-__device__ __forceinline__ float warp_coord(int g, float d, float size) {
+// x / size, correctly rounded, from the correctly rounded reciprocal rs = RN(1 / size) (Markstein: q0 = RN(x * rs), exact residual
+// r = x - q0 * size by FMA, q = RN(q0 + r * rs) == RN(x / size); size is a small integer, so its significand is never all ones).
+// Three FP32 instructions instead of the ~15 of an IEEE division; 16 of them per block pixel.  Non-finite x: the residual is NaN and
+// q0 (= x * rs, the value the division gives) is kept.
+__device__ __forceinline__ float div_by_size(float x, float size, float rs) {
+    const float q0 = __fmul_rn(x, rs);
+    const float r = __fmaf_rn(-q0, size, x);
+    return (r != r) ? q0 : __fmaf_rn(r, rs, q0);
+}
+__device__ __forceinline__ float warp_coord(int g, float d, float size, float rs) {
     const float x = __fadd_rn((float)g, d);
-    const float nrm = __fmul_rn(2.f, __fsub_rn(__fdiv_rn(x, size), 0.5f));
+    const float nrm = __fmul_rn(2.f, __fsub_rn(div_by_size(x, size, rs), 0.5f));
     return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(nrm, 1.f), size), 1.f), 0.5f);
 }
 __device__ __forceinline__ void bilinear_gather3(const float* __restrict__ img, long HW, int H, int W, float ix, float iy, float (&o)[3]) {
@@ -102,7 +111,7 @@ template <int F16>
 __device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const float4 (&res)[4], const float* __restrict__ i0,
                                                 const float* __restrict__ i1, const float* __restrict__ cf, long HW, int H, int W, int by,
                                                 int bx, __nv_bfloat16* __restrict__ m16, float4* __restrict__ xt8) {
-    const float fW = (float)W, fH = (float)H;
+    const float fW = (float)W, fH = (float)H, rW = __frcp_rn(fW), rH = __frcp_rn(fH);
     float a[3][4], b[3][4];
     load_block3(i0, HW, W, by, bx, a);
     load_block3(i1, HW, W, by, bx, b);
@@ -115,8 +124,85 @@ __device__ __forceinline__ void glue_warp_block(const float4 (&flow)[4], const f
         a0 = __fadd_rn(a0, r.x); a1 = __fadd_rn(a1, r.y);       // model.py:44
         b0 = __fadd_rn(b0, r.z); b1 = __fadd_rn(b1, r.w);       // model.py:45
         float xt1[3], xt2[3];
-        bilinear_gather3(i0, HW, H, W, warp_coord(gx, a0, fW), warp_coord(gy, a1, fH), xt1);   // model.py:47
-        bilinear_gather3(i1, HW, H, W, warp_coord(gx, b0, fW), warp_coord(gy, b1, fH), xt2);   // model.py:48
+        bilinear_gather3(i0, HW, H, W, warp_coord(gx, a0, fW, rW), warp_coord(gy, a1, fH, rH), xt1);   // model.py:47
+        bilinear_gather3(i1, HW, H, W, warp_coord(gx, b0, fW, rW), warp_coord(gy, b1, fH, rH), xt2);   // model.py:48
+        float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph],
+                       xt1[0], xt1[1], xt1[2], xt2[0], xt2[1], xt2[2]};                          // model.py:50
+        store_x16<F16>(m16 + ph * 16, v);
+        stg256(xt8 + ph * 2, __float_as_uint(xt1[0]), __float_as_uint(xt1[1]), __float_as_uint(xt1[2]), __float_as_uint(xt2[0]),
+               __float_as_uint(xt2[1]), __float_as_uint(xt2[2]), 0u, 0u);
+    }
+}
+
+// ---- K3 with the frames staged in shared memory (conv3x3_v2.cuh, FS configs): the window [frame 2][plane 3][h][w] fp32 holds
+// pixels [x0, x0 + w) x [y0, y0 + h) of both frames, zero outside the image (TMA fill == grid_sample's zeros padding).
+struct FrameWindow { uint32_t smem; int x0, y0, w, h; };
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+// one bilinear sample: taps from the window when its 2 x 2 footprint lies inside, else the global path (identical arithmetic:
+// the in-range flags and the accumulate order of bilinear_gather3; an in-window tap outside the image is never added)
+__device__ __forceinline__ void bilinear_gather3_staged(const FrameWindow& fw, int frame, const float* __restrict__ img, long HW, int H, int W,
+                                                        float ix, float iy, float (&o)[3]) {
+    const float xw = floorf(ix), yn = floorf(iy);
+    const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
+    const int x0 = min(max((int)xw, -2), W), y0 = min(max((int)yn, -2), H);
+    const int lx = x0 - fw.x0, ly = y0 - fw.y0;
+    if ((unsigned)lx < (unsigned)(fw.w - 1) && (unsigned)ly < (unsigned)(fw.h - 1)) {
+        const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
+        const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
+        const float wnw = s * e, wne = s * w, wsw = nn * e, wse = nn * w;
+        const uint32_t a = fw.smem + (uint32_t)(((frame * 3) * fw.h + ly) * fw.w + lx) * 4u;
+        const uint32_t plane = (uint32_t)(fw.w * fw.h) * 4u, row = (uint32_t)fw.w * 4u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t0 = lds_f32(a + c * plane), t1 = lds_f32(a + c * plane + 4), t2 = lds_f32(a + c * plane + row), t3 = lds_f32(a + c * plane + row + 4);
+            float acc = 0.f;
+            if (yin0 && xin0) acc += t0 * wnw;
+            if (yin0 && xin1) acc += t1 * wne;
+            if (yin1 && xin0) acc += t2 * wsw;
+            if (yin1 && xin1) acc += t3 * wse;
+            o[c] = acc;
+        }
+    } else {
+        bilinear_gather3(img, HW, H, W, ix, iy, o);
+    }
+}
+template <int F16>
+__device__ __forceinline__ void glue_warp_block_staged(const float4 (&flow)[4], const float4 (&res)[4], const FrameWindow& fw,
+                                                       const float* __restrict__ i0, const float* __restrict__ i1, const float* __restrict__ cf,
+                                                       long HW, int H, int W, int by, int bx, __nv_bfloat16* __restrict__ m16, float4* __restrict__ xt8) {
+    const float fW = (float)W, fH = (float)H, rW = __frcp_rn(fW), rH = __frcp_rn(fH);
+    float a[3][4], b[3][4];
+    {   // the block's own 2 x 2 pixels of both frames: always inside the window
+        const uint32_t base = fw.smem + (uint32_t)((2 * by - fw.y0) * fw.w + (2 * bx - fw.x0)) * 4u;
+        const uint32_t plane = (uint32_t)(fw.w * fw.h) * 4u, row = (uint32_t)fw.w * 4u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 r0 = lds_f32x2(base + c * plane), r1 = lds_f32x2(base + c * plane + row);
+            a[c][0] = r0.x; a[c][1] = r0.y; a[c][2] = r1.x; a[c][3] = r1.y;
+            const float2 s0 = lds_f32x2(base + (3 + c) * plane), s1 = lds_f32x2(base + (3 + c) * plane + row);
+            b[c][0] = s0.x; b[c][1] = s0.y; b[c][2] = s1.x; b[c][3] = s1.y;
+        }
+    }
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        const int gy = 2 * by + (ph >> 1), gx = 2 * bx + (ph & 1);
+        const float4 r = res[ph];
+        float a0, a1, b0, b1;
+        tscale(flow[ph], cf, a0, a1, b0, b1);
+        a0 = __fadd_rn(a0, r.x); a1 = __fadd_rn(a1, r.y);       // model.py:44
+        b0 = __fadd_rn(b0, r.z); b1 = __fadd_rn(b1, r.w);       // model.py:45
+        float xt1[3], xt2[3];
+        bilinear_gather3_staged(fw, 0, i0, HW, H, W, warp_coord(gx, a0, fW, rW), warp_coord(gy, a1, fH, rH), xt1);   // model.py:47
+        bilinear_gather3_staged(fw, 1, i1, HW, H, W, warp_coord(gx, b0, fW, rW), warp_coord(gy, b1, fH, rH), xt2);   // model.py:48
         float v[16] = {a0, a1, b0, b1, a[0][ph], a[1][ph], a[2][ph], b[0][ph], b[1][ph], b[2][ph],
                        xt1[0], xt1[1], xt1[2], xt2[0], xt2[1], xt2[2]};                          // model.py:50
         store_x16<F16>(m16 + ph * 16, v);

@@ -189,6 +189,7 @@ S2D_CASES = [
     ("ns2_head_many", 38, "plain", 10, 16, 32, True, 1, 368, 368),
     ("last_sa4", 34, "plain", 32, 32, 4, False, 1, 368, 368),
     ("last_msub1", 32, "plain", 32, 32, 2, False, 1, 176, 208),
+    ("last_sa8", 33, "plain", 32, 32, 4, False, 2, 80, 208),
 ]
 
 

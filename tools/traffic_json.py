@@ -16,14 +16,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = 1088 * 1920
 # i: (class, layer, algorithmic bytes per frame pair: bf16 activations in + out, + packed weights once)
 LAUNCHES = {
-    5: ("conv3x3_tma<KCS64,KB64,NT128,MSUB3>", "Flow.down_path.2.block.2 (128->128, level 2)", (128 + 128) * 2 * P / 16, 9 * 128 * 128 * 2),
-    12: ("conv3x3_tma<KCS64,KB64,NT128,MSUB3> (cat)", "Flow.up_path.0.conv_block.block.0 (cat 256+256->256, level 3)", (512 + 256) * 2 * P / 64, 9 * 512 * 256 * 2),
-    2: ("conv3x3_tma<KCS32,KB32,NT64,MSUB4>", "Flow.down_path.1.block.0 (pooled 32->64, level 1)", (32 + 64) * 2 * P / 4, 9 * 32 * 64 * 2),
-    1: ("conv3x3_tma<KCS64,KB32,NT128,MSUB1>", "Flow.down_path.0.block.2 (32->32, level 0, + pooled output)", (32 + 32 + 8) * 2 * P, 96 * 1024),
-    3: ("conv3x3_tma<KCS64,KB64,NT64,MSUB2>", "Flow.down_path.1.block.2 (64->64, level 1, + pooled output)", (64 + 64 + 16) * 2 * P / 4, 9 * 64 * 64 * 2),
-    23: ("conv3x3_tma<KCS64,KB32,NT128,MSUB3>", "Flow.up_path.3.conv_block.block.0 (cat 32+32->32, level 0)", (64 + 32) * 2 * P, 192 * 1024),
-    25: ("conv3x3_tma<KCS64,KB32,NT16,MSUB2> +glue", "Flow.last (32->4, level 0) + fused t-scale / head packing", (32 * 2 + 16 + 32 + 24) * P, 16 * 1024),
-    11: ("conv3x3_tma<KCS64,KB64,NT128,MSUB2> up", "Flow.up_path.0.up.1 (bilinear x2 + 512->256, level 3)", (512 * 2 / 4 + 256 * 2) * P / 64, 9 * 512 * 256 * 2),
+    5: ("conv3x3_tma#16<KCS64,KB64,NT128,MSUB3>", "Flow.down_path.2.block.2 (128->128, level 2)", (128 + 128) * 2 * P / 16, 9 * 128 * 128 * 2),
+    12: ("conv3x3_tma#16<KCS64,KB64,NT128,MSUB3> (cat)", "Flow.up_path.0.conv_block.block.0 (cat 256+256->256, level 3)", (512 + 256) * 2 * P / 64, 9 * 512 * 256 * 2),
+    2: ("conv3x3_tma#21<KCS32,KB32,NT64,MSUB4>", "Flow.down_path.1.block.0 (pooled 32->64, level 1)", (32 + 64) * 2 * P / 4, 9 * 32 * 64 * 2),
+    1: ("conv3x3_tma#35<KCS64,KB32,NT128,MSUB1>", "Flow.down_path.0.block.2 (32->32, level 0, + pooled output; two tile streams)", (32 + 32 + 8) * 2 * P, 96 * 1024),
+    3: ("conv3x3_tma#36<KCS64,KB64,NT64,MSUB1>", "Flow.down_path.1.block.2 (64->64, level 1, + pooled output; two tile streams)", (64 + 64 + 16) * 2 * P / 4, 9 * 64 * 64 * 2),
+    20: ("conv3x3_tma#22<KCS64,KB64,NT64,MSUB4>", "Flow.up_path.2.conv_block.block.0 (cat 64+64->64, level 1; CTA pairs)", (128 + 64) * 2 * P / 4, 9 * 128 * 64 * 2),
+    23: ("conv3x3_tma#25<KCS64,KB32,NT128,MSUB1>", "Flow.up_path.3.conv_block.block.0 (cat 32+32->32, level 0; CTA pairs, resident half-blocks)", (64 + 32) * 2 * P, 192 * 1024),
+    25: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue", "Flow.last (32->4, level 0) + fused t-scale / refine_flow head packing", (32 * 2 + 16 + 32 + 24) * P, 16 * 1024),
+    46: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue (warp)", "refine_flow.last (32->4) + fused residue add, both backward warps, Mask head packing (model.py:44-50)", (32 * 2 + 16 + 24 + 32 + 32) * P, 16 * 1024),
+    67: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue (blend)", "Mask.last (32->2) + fused sigmoid, blend, final head packing (model.py:52-55,61)", (32 * 2 + 32 + 24 + 16 + 32) * P, 16 * 1024),
+    88: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue (clamp)", "final.last (32->3) + fused residue add, clamp, NCHW store (model.py:62-63)", (32 * 2 + 16 + 12) * P, 16 * 1024),
+    11: ("conv3x3_tma#20<KCS64,KB64,NT128,MSUB2> up", "Flow.up_path.0.up.1 (bilinear x2 + 512->256, level 3)", (512 * 2 / 4 + 256 * 2) * P / 64, 9 * 512 * 256 * 2),
 }
 
 
