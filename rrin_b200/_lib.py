@@ -9,7 +9,7 @@ import os
 import re
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "librrin_b200.so")
+LIB_PATH = os.environ.get("RRIN_LIB") or os.path.join(PKG, "librrin_b200.so")      # RRIN_LIB: an alternative build (A/B timing)
 HEADER = os.path.join(os.path.dirname(PKG), "include", "rrin_b200.h")
 
 _lib = None

@@ -322,6 +322,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100: FADD2 / FMUL2, one issue slot per two lanes)
+// The conv epilogues are issue-bound (about 900 instructions per thread and sub-tile on 8 warps): bias add and LeakyReLU on
+// register pairs halve their arithmetic instruction count.  IEEE round-to-nearest like the scalar forms: identical results.
+#ifdef RRIN_NO_F32X2            // A/B builds only: scalar forms
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#else
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+#endif
+// LeakyReLU(0.1) (unet.py:47,60,63): max(v, 0.1 v) == (v >= 0 ? v : 0.1 v) for every v, NaN included
+__device__ __forceinline__ float2 lrelu2(float2 v) {
+    const float2 u = f2mul(v, make_float2(0.1f, 0.1f));
+    return make_float2(fmaxf(v.x, u.x), fmaxf(v.y, u.y));
+}
+
 // ---------------------------------------------------------------- 16-bit operand format as a template parameter
 // F16 = 0: bf16 (fp32 range, 8-bit significand; the default path) | 1: fp16 (11-bit significand, max 65504; the
 // "fp32-accumulate within 1e-3" precision mode).  Storage size, TMA boxes, swizzles and MMA rate are identical.

@@ -79,9 +79,11 @@ constexpr int kTileH = 16;
 // 16 x 8 tile: halo = 3 lines x (L+2) positions, accumulator row m = position m along the strip.  Used to recompute the
 // outermost ring after a weight-folded upsample conv: only those pixels differ (zero padding vs folded halo).
 // A strip covers kStripLen positions; the accumulator still has 128 rows (rows >= kStripLen read past the 3 halo lines and
-// are discarded): shorter strips spread the latency-bound halo construction over more CTAs than 128-pixel ones, longer ones
-// re-stream the weight blocks less often; 64 measured best at batch 1 and 4 (32: +0.4 %, 128: +1 % at batch 1).
-constexpr int kStripLen = 64;
+// are discarded).  Strips are latency-bound (halo construction from global loads, streamed weight blocks), so what matters is
+// how many rounds of them a launch needs on 148 CTAs: at 1080p, batch 4, 64-pixel strips are 192 (level 0) / 208 (level 1) work
+// items = two rounds, 96-pixel strips 128 / 128 = one (rings 0.39 -> 0.32 ms per step; 128-pixel strips: 0.37 ms and slower at
+// batch 1, where every length fits one round).
+constexpr int kStripLen = 96;
 template <int KCS, int KB, int NT, int MSUB, int SA, int SB, int STRIP = 0>
 struct ConvCfg {
     static constexpr int CH8 = KCS / 8;                // 16-byte channel groups (planes) per stage

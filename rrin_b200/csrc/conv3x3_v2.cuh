@@ -668,18 +668,16 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const float4 ba = b4[i], bb = b4[4 + i];
-                                float v[8] = {__uint_as_float(ra[4 * i]) + ba.x, __uint_as_float(ra[4 * i + 1]) + ba.y,
-                                              __uint_as_float(ra[4 * i + 2]) + ba.z, __uint_as_float(ra[4 * i + 3]) + ba.w,
-                                              __uint_as_float(rb[4 * i]) + bb.x, __uint_as_float(rb[4 * i + 1]) + bb.y,
-                                              __uint_as_float(rb[4 * i + 2]) + bb.z, __uint_as_float(rb[4 * i + 3]) + bb.w};
-                                if (p.act) {
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) v[q] = v[q] >= 0.f ? v[q] : 0.1f * v[q];
-                                }
-                                o[16 * h + 2 * i] = pack2<F16>(v[0], v[1]);
-                                o[16 * h + 2 * i + 1] = pack2<F16>(v[2], v[3]);
-                                o[16 * h + 8 + 2 * i] = pack2<F16>(v[4], v[5]);
-                                o[16 * h + 8 + 2 * i + 1] = pack2<F16>(v[6], v[7]);
+                                // bias add and LeakyReLU on register pairs (FADD2 / FMUL2)
+                                float2 v0 = f2add(make_float2(__uint_as_float(ra[4 * i]), __uint_as_float(ra[4 * i + 1])), make_float2(ba.x, ba.y));
+                                float2 v1 = f2add(make_float2(__uint_as_float(ra[4 * i + 2]), __uint_as_float(ra[4 * i + 3])), make_float2(ba.z, ba.w));
+                                float2 v2 = f2add(make_float2(__uint_as_float(rb[4 * i]), __uint_as_float(rb[4 * i + 1])), make_float2(bb.x, bb.y));
+                                float2 v3 = f2add(make_float2(__uint_as_float(rb[4 * i + 2]), __uint_as_float(rb[4 * i + 3])), make_float2(bb.z, bb.w));
+                                if (p.act) { v0 = lrelu2(v0); v1 = lrelu2(v1); v2 = lrelu2(v2); v3 = lrelu2(v3); }
+                                o[16 * h + 2 * i] = pack2<F16>(v0.x, v0.y);
+                                o[16 * h + 2 * i + 1] = pack2<F16>(v1.x, v1.y);
+                                o[16 * h + 8 + 2 * i] = pack2<F16>(v2.x, v2.y);
+                                o[16 * h + 8 + 2 * i + 1] = pack2<F16>(v3.x, v3.y);
                             }
                         }
                         if (lane == 0) bulk_wait_group_read<0>();       // the previous store has finished reading the buffer
@@ -701,8 +699,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) {
                                     const float2 a = unpack2<F16>(o[i]), b = unpack2<F16>(o[16 + i]);
-                                    if (c == 0) { pacc[2 * i] = a.x + b.x; pacc[2 * i + 1] = a.y + b.y; }
-                                    else { pacc[2 * i] = (pacc[2 * i] + a.x) + b.x; pacc[2 * i + 1] = (pacc[2 * i + 1] + a.y) + b.y; }
+                                    float2 s2;
+                                    if (c == 0) s2 = f2add(a, b);
+                                    else s2 = f2add(f2add(make_float2(pacc[2 * i], pacc[2 * i + 1]), a), b);
+                                    pacc[2 * i] = s2.x; pacc[2 * i + 1] = s2.y;
                                 }
                                 if (c == NT - 64 && ok) {
                                     __nv_bfloat16* d = p.pool_out + pix * (size_t)(NT / 4);        // 64 bytes per pooled pixel
@@ -801,17 +801,15 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float v0 = __uint_as_float(ra[2 * i]) + bsrc[c + 2 * i];
-                            float v1 = __uint_as_float(ra[2 * i + 1]) + bsrc[c + 2 * i + 1];
-                            if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                            o[i] = pack2<F16>(v0, v1);
+                            float2 v = f2add(make_float2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1])), make_float2(bsrc[c + 2 * i], bsrc[c + 2 * i + 1]));
+                            if (p.act) v = lrelu2(v);
+                            o[i] = pack2<F16>(v.x, v.y);
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            float v0 = __uint_as_float(rb[2 * i]) + bsrc[c + 16 + 2 * i];
-                            float v1 = __uint_as_float(rb[2 * i + 1]) + bsrc[c + 16 + 2 * i + 1];
-                            if (p.act) { v0 = v0 >= 0.f ? v0 : 0.1f * v0; v1 = v1 >= 0.f ? v1 : 0.1f * v1; }
-                            o[8 + i] = pack2<F16>(v0, v1);
+                            float2 v = f2add(make_float2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1])), make_float2(bsrc[c + 16 + 2 * i], bsrc[c + 16 + 2 * i + 1]));
+                            if (p.act) v = lrelu2(v);
+                            o[8 + i] = pack2<F16>(v.x, v.y);
                         }
                         if (ok) {
                             __nv_bfloat16* op;
