@@ -80,7 +80,7 @@ static int up_cfg() {
 // level-1 block.0 conv on the pooled 32-channel level-0 tensor: TMA config 21 (RRIN_POOL1_CFG=3: the cp.async-fed v1 kernel)
 static int pool1_cfg() {
     static const int c = getenv("RRIN_POOL1_CFG") ? atoi(getenv("RRIN_POOL1_CFG")) : 21;
-    return (c == 3 || c == 39) ? c : 21;
+    return (c == 3 || c == 39 || c == 45 || c == 46) ? c : 21;
 }
 
 // level-1 plain / cat convs on CTA pairs (config 22): experimental, RRIN_L1_PAIR=1

@@ -100,6 +100,8 @@ NORMAL_CASES = [
     ("ns2_l1_odd", 36, "plain", 64, 64, False, 3, 40, 72),
     ("ns2_pool32_partial_n2", 39, "plain", 32, 64, False, 2, 36, 52),
     ("ns2_pool32_many_tiles", 39, "plain", 32, 64, True, 1, 184, 328),
+    ("pool32_ew2_many_tiles", 45, "plain", 32, 64, True, 1, 184, 328),
+    ("pool32_ns2m4_many_tiles", 46, "plain", 32, 64, False, 2, 100, 328),
     ("ns2_l1_cat_small", 41, "cat", 64, 64, True, 1, 36, 52),
     ("ns2_l1_cat_many_tiles", 41, "cat", 64, 64, False, 1, 200, 136),
     ("ns2_l1_cat4_many_tiles", 42, "cat", 64, 64, True, 2, 200, 136),
