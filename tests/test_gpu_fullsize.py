@@ -72,8 +72,9 @@ def test_1080p_noise_frames_match_oracle():
 
 
 def test_1080p_stress_flow_matches_oracle():
-    """Multi-pixel flows (|flow| up to ~6 px, out-of-bounds taps along all four edges) at 1080p: bf16-operand path >= 50 dB."""
-    sd = O.seeded_state_dict(stress_flow=100.0)
+    """Multi-pixel flows (out-of-bounds taps along all four edges, samples leaving the staged frame window) at 1080p:
+    bf16-operand path >= 50 dB."""
+    sd = O.seeded_state_dict(stress_flow=800.0)
     net = make_net(sd)
     a, b = O.seeded_frames(1, 1088, 1920, seed=2, smooth=True)
     y = net(a.cuda(), b.cuda(), t=0.5).cpu()
@@ -82,14 +83,14 @@ def test_1080p_stress_flow_matches_oracle():
     fmax = max(taps["ft0"].abs().max().item(), taps["ft1"].abs().max().item())
     p = psnr(y, ref)
     print(f"1080p stress: |flow| max {fmax:.2f} px, psnr {p:.1f} dB, max-abs {(y - ref).abs().max().item():.3e}")
-    assert fmax > 1.0, "the stress weights must produce multi-pixel flows"
+    assert fmax > 8.0, "the stress weights must produce flows beyond the 8-pixel halo of the staged frame window"
     assert p >= 50
 
 
 def test_1080p_stress_flow_fp16_precision_mode():
     """The precision mode (fp16 operands, fp32 accumulation) at 1080p with multi-pixel flows: the 1e-3 bar that the bf16
     path only meets with random-init weights."""
-    sd = O.seeded_state_dict(stress_flow=100.0)
+    sd = O.seeded_state_dict(stress_flow=300.0)
     net = make_net(sd, precision="fp16")
     a, b = O.seeded_frames(1, 1088, 1920, seed=2, smooth=True)
     y = net(a.cuda(), b.cuda(), t=0.5).cpu()
@@ -143,7 +144,7 @@ def test_4k_pair_matches_oracle():
 
 def test_4k_stress_flow_border_strips():
     """4K with multi-pixel flows: PSNR >= 50 dB on the whole frame and on each of the four 64-pixel border strips."""
-    sd = O.seeded_state_dict(stress_flow=100.0)
+    sd = O.seeded_state_dict(stress_flow=400.0)
     net = make_net(sd)
     a, b = O.seeded_frames(1, 2176, 3840, seed=6, smooth=True)
     y = net(a.cuda(), b.cuda(), t=0.5).cpu()

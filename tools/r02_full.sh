@@ -22,4 +22,4 @@ for f in sorted(glob.glob("gpurun_out/${tag}_bench_*.json")):
     except Exception as e:
         print(f, "unreadable", e)
 PY
-tail -2 gpurun_out/${tag}_bench_*.err | head -40
+for f in gpurun_out/${tag}_bench_*.err; do tail -n 2 $f; done | head -40

@@ -16,4 +16,4 @@ for f in ("gpurun_out/${tag}_bench_n${n}.json", "gpurun_out/${tag}_bench_clip_n$
     except Exception as e:
         print(f, "unreadable", e)
 PY
-tail -4 gpurun_out/${tag}_bench_n${n}.err gpurun_out/${tag}_bench_clip_n${n}.err
+for f in gpurun_out/${tag}_bench_n${n}.err gpurun_out/${tag}_bench_clip_n${n}.err; do tail -n 3 $f; done
