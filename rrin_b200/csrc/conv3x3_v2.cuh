@@ -27,7 +27,15 @@
 //
 // Warp roles (1 CTA / SM, persistent): 4*EW epilogue warps (EW groups, one warp per TMEM lane quadrant), then one
 // warp each for MMA issue (a single elected thread), weight blocks (cp.async.bulk) and activation halo tiles
-// (cp.async.bulk.tensor), then -- XF only -- four transform warps.  224 / 352 / 480 threads.
+// (cp.async.bulk.tensor), then -- XF only -- four transform warps, then -- NS = 2 only -- the second tile stream's MMA
+// warp.  224 / 352 / 384 / 480 threads.
+//
+// Round-2 variants of the same kernel (template parameters, see ConvCfgV2 and conv3x3_launch.cuh):
+//   NS = 2  two tile streams per CTA: two MMA-issuing warps, each with half of the stages / accumulator slots and its own
+//           epilogue group(s) (a single thread issues one tcgen05.mma per ~39 cycles, as long as an N = 64 MMA runs);
+//   CG = 2 + RES  CTA pairs keeping a layer's weights resident as two halves (level-0 cat: 2 x 96 KB);
+//   FS = 1  frame windows of the fused backward warps staged in shared memory by TMA;
+//   F16     fp16 instead of bf16 operands (precision mode).
 #pragma once
 #include <cuda.h>
 
