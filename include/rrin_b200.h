@@ -134,7 +134,9 @@ RRIN_API int rrin_pack_conv_raw_ex(int kind, const float* w, const float* b, int
                           void* wpack, float* bias_pack, int precision, void* stream);
 RRIN_API int rrin_conv3x3_ex(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                     int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
-                    int act, int ring_only, int cfg, void* pool_out, int precision, void* stream);
+                    int act, int ring_only, int cfg, void* pool_out, int precision, int transposed, void* stream);
+/* transposed != 0 (streamed 9-tap TMA configs with the TMA-store epilogue, e.g. 16 and 20): the kernel's 16-row bands run along the
+ * image WIDTH (tensor maps with swapped W / H, weight taps swapped) -- same result, less padding when H is not a multiple of 16 */
 
 /* Glue kernels.  Frames are fp32 NCHW; tensors exchanged with the U-Nets are space-to-depth on the half-res
  * grid: head inputs bf16 [N,H/2,W/2,4,16]; U-Net outputs fp32 [N,H/2,W/2,4,4]; xt8 fp32 [N,H/2,W/2,4,8].

@@ -40,7 +40,7 @@ _SIGNATURES = {
     "rrin_pack_conv_raw": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
     "rrin_conv3x3": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
     "rrin_pack_conv_raw_ex": (ci, [ci, vp, vp, ci, ci, ci, ci, vp, vp, ci, vp]),
-    "rrin_conv3x3_ex": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, ci, vp]),
+    "rrin_conv3x3_ex": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp]),
     "rrin_pack_pair": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "rrin_flow_tscale_pack": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_warp_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),

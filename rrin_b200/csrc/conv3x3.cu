@@ -253,7 +253,7 @@ static EncodeTiledFn encode_fn() {
 // Tensor map of a bf16 NHWC tensor [N,H,W,C], SWIZZLE_128B.  which = 0: source of the A operand, box {64 ch, PW pixels,
 // 18 rows, 1 image}, out-of-bounds elements read as zero (the conv's zero padding); which = 1: epilogue destination,
 // box {64 ch, 8 pixels, 4 rows, 1 image} (one epilogue warp's share of a sub-tile), out-of-bounds elements not written.
-int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out) {
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out, int transposed) {
     if (!cfg_valid(cfg) || !cfg_is_v2(cfg)) { set_error("conv_make_tmap: config %d is not a TMA config", cfg); return RRIN_ERR_BAD_ARG; }
     const CfgInfo& c = cfg_info(cfg);
     const int box_ch = (which == 0 && c.kcs == 32) ? 32 : 64;          // input boxes of the 32-channel config: 64-byte rows
@@ -263,8 +263,9 @@ int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int wh
     }
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return RRIN_ERR_UNSUPPORTED; }
-    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    // transposed: dimension 1 (the box's pixel-column extent) walks image rows, dimension 2 (the box's row extent) walks along a row
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)(transposed ? H : W), (cuuint64_t)(transposed ? W : H), (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)(transposed ? W : 1) * C * 2, (cuuint64_t)(transposed ? 1 : W) * C * 2, (cuuint64_t)H * W * C * 2};
     const cuuint32_t box_in[4] = {(cuuint32_t)box_ch, (cuuint32_t)c.pw, (cuuint32_t)(kTileH + 2), 1};
     const cuuint32_t box_out[4] = {64, 8, 4, 1};
     const cuuint32_t box_raw[4] = {64, (cuuint32_t)(4 * c.msub + 2), (cuuint32_t)(kTileH / 2 + 2), 1};   // which = 2: coarse tile of an upsample source
@@ -288,9 +289,15 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     const int ctot = d.c0 + (d.mode == SRC_CAT ? d.c1 : 0);
     const int box_ch = c.kcs < 64 ? c.kcs : 64;
     if (d.c0 % box_ch || (d.mode == SRC_CAT && d.c1 % box_ch) || ctot % c.kcs) { set_error("conv3x3(tma): %d(+%d) stored channels not a multiple of %d / stage width %d", d.c0, d.c1, box_ch, c.kcs); return RRIN_ERR_BAD_SHAPE; }
+    const int tr = d.transposed ? 1 : 0;
+    if (tr && (c.sched != SCHED_TAPS9 || !c.etma || c.res || c.cg != 1 || d.epi != EPI_BF16)) {
+        set_error("conv3x3(tma): transposed launches need the streamed 9-tap schedule with the TMA-store epilogue (config %d)", cfg); return RRIN_ERR_BAD_ARG;
+    }
     ConvParamsV2 p{};
     p.c0_chunks = d.c0 / box_ch;
-    p.N = d.N; p.H = d.H; p.W = d.W;
+    p.N = d.N; p.H = tr ? d.W : d.H; p.W = tr ? d.H : d.W;      // kernel-space grid
+    p.wt_transposed = tr;
+    p.pool_sy = tr ? 1 : (d.W >> 1); p.pool_sx = tr ? (d.W >> 1) : 1;
     p.n_stages = ctot / c.kcs;
     if (d.sched != c.sched) { set_error("conv3x3(tma): config %d runs schedule %d, not %d", cfg, c.sched, d.sched); return RRIN_ERR_BAD_ARG; }
     if (d.sched == SCHED_S2D8 && (p.n_stages & 1)) { set_error("conv3x3(tma): the half-phase schedule needs an even number of 64-channel chunks"); return RRIN_ERR_BAD_SHAPE; }
@@ -320,8 +327,8 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     if (((reinterpret_cast<uintptr_t>(d.out) | reinterpret_cast<uintptr_t>(d.pool_out)) & 31) || (d.epi == EPI_BF16 && d.cout_stride % 16)) {
         set_error("conv3x3(tma): outputs must be 32-byte aligned with a multiple of 16 channels per pixel (256-bit stores)"); return RRIN_ERR_BAD_ARG;
     }
-    p.tiles_y = (d.H + kTileH - 1) / kTileH;
-    p.sx = (d.W + 7) / 8;
+    p.tiles_y = (p.H + kTileH - 1) / kTileH;
+    p.sx = (p.W + 7) / 8;
     const long upn = (long)d.N * p.tiles_y * p.sx, total = upn * p.n_ntiles;
     if (total > 0x7fffffffL) { set_error("conv3x3: too many tiles"); return RRIN_ERR_BAD_SHAPE; }
     p.units_per_nt = (int)upn; p.total_units = (int)total;
@@ -331,15 +338,15 @@ static int conv_launch_v2(const ConvDesc& d, cudaStream_t stream) {
     }
     CUtensorMap tm0, tm1, tmo;
     if (d.tmap0) memcpy(&tm0, d.tmap0, sizeof tm0);
-    else if (int r = c.xf ? conv_make_tmap(d.src0, d.N, d.H / 2, d.W / 2, d.c0, cfg, 2, &tm0) : conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, 0, &tm0)) return r;
+    else if (int r = c.xf ? conv_make_tmap(d.src0, d.N, d.H / 2, d.W / 2, d.c0, cfg, 2, &tm0, tr) : conv_make_tmap(d.src0, d.N, d.H, d.W, d.c0, cfg, 0, &tm0, tr)) return r;
     if (d.mode == SRC_CAT) {
         if (d.tmap1) memcpy(&tm1, d.tmap1, sizeof tm1);
-        else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, 0, &tm1)) return r;
+        else if (int r = conv_make_tmap(d.src1, d.N, d.H, d.W, d.c1, cfg, 0, &tm1, tr)) return r;
     } else tm1 = tm0;
     if (c.etma) {
         if (d.epi != EPI_BF16 || d.cout_stride % 64) { set_error("conv3x3(tma): config %d stores bf16 NHWC with a multiple of 64 channels per pixel", cfg); return RRIN_ERR_BAD_ARG; }
         if (d.tmap_out) memcpy(&tmo, d.tmap_out, sizeof tmo);
-        else if (int r = conv_make_tmap(d.out, d.N, d.H, d.W, d.cout_stride, cfg, 1, &tmo)) return r;
+        else if (int r = conv_make_tmap(d.out, d.N, d.H, d.W, d.cout_stride, cfg, 1, &tmo, tr)) return r;
     } else tmo = tm0;
     const int sms = num_sms();
     if (sms <= 0) { set_error("conv3x3: no CUDA device"); return RRIN_ERR_CUDA; }

@@ -75,6 +75,13 @@ struct ConvParamsV2 {
     // optional second output (TMA-epilogue configs): F.avg_pool2d(out, 2) (unet.py:46) as bf16 NHWC [N, H/2, W/2, cout_stride]
     // on an NHWC grid, or [N, H, W, cout_stride/4] (mean over the 4 phases) on the space-to-depth grid; null = none
     __nv_bfloat16* pool_out;
+    // Transposed launches (conv3x3.cu: ConvDesc::transposed): the kernel's rows run along the image's WIDTH (tensor maps with
+    // swapped W / H dimensions; H and W above are swapped too), so that the 16-row bands cut the dimension with less padding
+    // (1080p: level-2..4 tensors have 136 / 68 / 34 rows, 6 / 18 / 41 % of a 16-row band grid is padding; their widths are
+    // multiples of 16).  Everything that goes through TMA needs nothing else; the pooled second output is stored directly and
+    // takes its strides (in pooled pixels) from here, and the weight producer swaps each tap's (dy, dx).
+    int pool_sy, pool_sx;        // pooled-pixel strides of the kernel's row / column index: {W/2, 1}, transposed {1, H/2}
+    int wt_transposed;           // 9-tap schedule: fetch weight block (dx, dy) for entry (dy, dx)
     int n_ntiles;
     int tiles_y;                 // row bands per image
     int sx;                      // 8-pixel column groups per band
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                         const int slot = q * SBQ + cnt % SBQ;
                         const int si = bi / N_ENT, e = bi - si * N_ENT;
                         const int st = (si + st_rot >= nst) ? si + st_rot - nst : si + st_rot;
-                        const int b = st * N_ENT + e;
+                        const int b = st * N_ENT + ((SCHED == 0 && p.wt_transposed) ? (e % 3) * 3 + e / 3 : e);
                         uint32_t bytes = C::B_BLOCK;
                         if (C::HALF && ((st & 1) ? (e < 4) : (e >= 4))) bytes = C::B_BLOCK / 2;
                         mbar_wait(b_empty(slot), ((cnt / SBQ) & 1) ^ 1);
@@ -741,7 +748,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                                 }
                                 const int py = (t.ty * kTileH + 4 * quad) / 2 + pyl, px = (t.sx0 + j) * 4 + pxl;
                                 if (py < (p.H >> 1) && px < (p.W >> 1)) {
-                                    stg256_x16<F16>(p.pool_out + ((size_t)(t.n * (p.H >> 1) + py) * (p.W >> 1) + px) * p.cout_stride + t.nt * NT + c + 16 * q,
+                                    stg256_x16<F16>(p.pool_out + ((size_t)t.n * (p.H >> 1) * (p.W >> 1) + (size_t)py * p.pool_sy + (size_t)px * p.pool_sx) * p.cout_stride + t.nt * NT + c + 16 * q,
                                                    acc, 0.25f);
                                 }
                             }

@@ -127,6 +127,13 @@ static void l0_pair_cfgs(int& c32, int& ccat) {
     c32 = a; ccat = b;
 }
 
+// transposed launches for levels >= 2 (RRIN_TRANSPOSE=0: never)
+constexpr long kBandRows = 16;          // conv3x3.cuh kTileH
+static bool transpose_ok() {
+    static const bool on = [] { const char* e = getenv("RRIN_TRANSPOSE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // refine_flow.last + fused backward warps: config 44 stages the frames' tile windows in shared memory (RRIN_WARP_STAGE=0: gather
 // from global memory like the other `last` epilogues)
 static bool warp_staging() {
@@ -295,6 +302,12 @@ static void plan_unet(rrin_engine* e, int u, int B, size_t head_off, size_t out_
     };
     auto finish = [&](Launch& ln, const char* tag, bool counts_flops) {
         const Layer& L = s.layers[ln.layer];
+        // Levels >= 2 (streamed 9-tap configs with TMA stores): run the kernel's 16-row bands along whichever image dimension pads
+        // less (1088 = 17 * 64: the level-2..4 tensors have 136 / 68 / 34 rows but widths that are multiples of 16)
+        if ((ln.cd.cfg == 16 || ln.cd.cfg == 20) && ln.cd.epi == EPI_BF16 && transpose_ok()) {
+            auto padded = [](long h, long w) { return ((h + kBandRows - 1) / kBandRows * kBandRows) * ((w + 7) / 8 * 8); };
+            if (padded(ln.cd.W, ln.cd.H) < padded(ln.cd.H, ln.cd.W)) ln.cd.transposed = 1;
+        }
         int kcs, kb, nt, msub;
         conv_config_info(ln.cd.cfg, &kcs, &kb, &nt, &msub);
         char b[128];
@@ -533,10 +546,10 @@ int rrin_engine_forward(rrin_engine* e, const void* blob_, void* workspace, cons
         for (Launch& ln : e->launches) {
             if (ln.glue >= 0 || ln.cd.cfg < 10) continue;
             const ConvDesc& c = ln.cd;
-            int r = (c.mode == SRC_UP) ? conv_make_tmap(dec(c.src0), c.N, c.H / 2, c.W / 2, c.c0, c.cfg, 2, ln.tmap[0])   // raw coarse tile
-                                       : conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, 0, ln.tmap[0]);
-            if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, 0, ln.tmap[1]);
-            if (r == RRIN_OK && conv_config_tma_epilogue(c.cfg)) r = conv_make_tmap(dec(c.out), c.N, c.H, c.W, c.cout_stride, c.cfg, 1, ln.tmap[2]);
+            int r = (c.mode == SRC_UP) ? conv_make_tmap(dec(c.src0), c.N, c.H / 2, c.W / 2, c.c0, c.cfg, 2, ln.tmap[0], c.transposed)   // raw coarse tile
+                                       : conv_make_tmap(dec(c.src0), c.N, c.H, c.W, c.c0, c.cfg, 0, ln.tmap[0], c.transposed);
+            if (r == RRIN_OK && c.mode == SRC_CAT) r = conv_make_tmap(dec(c.src1), c.N, c.H, c.W, c.c1, c.cfg, 0, ln.tmap[1], c.transposed);
+            if (r == RRIN_OK && conv_config_tma_epilogue(c.cfg)) r = conv_make_tmap(dec(c.out), c.N, c.H, c.W, c.cout_stride, c.cfg, 1, ln.tmap[2], c.transposed);
             if (r != RRIN_OK) return r;
         }
         e->tmap_ws = workspace;
@@ -727,14 +740,15 @@ int rrin_conv3x3(const void* src0, const void* src1, int c0, int c1, int src_mod
                  int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
                  int act, int ring_only, int cfg, void* pool_out, void* stream) {
     return rrin_conv3x3_ex(src0, src1, c0, c1, src_mode, pad_clamp, N, H, W, sched, n_cols, wpack, bias_pack, out, epi, cout_stride, act,
-                           ring_only, cfg, pool_out, RRIN_PRECISION_BF16, stream);
+                           ring_only, cfg, pool_out, RRIN_PRECISION_BF16, 0, stream);
 }
 int rrin_conv3x3_ex(const void* src0, const void* src1, int c0, int c1, int src_mode, int pad_clamp, int N, int H, int W,
                     int sched, int n_cols, const void* wpack, const float* bias_pack, void* out, int epi, int cout_stride,
-                    int act, int ring_only, int cfg, void* pool_out, int precision, void* stream) {
+                    int act, int ring_only, int cfg, void* pool_out, int precision, int transposed, void* stream) {
     if (int r = check_precision("rrin_conv3x3_ex", precision)) return r;
     ConvDesc cd;
     cd.f16 = precision == RRIN_PRECISION_FP16;
+    cd.transposed = transposed ? 1 : 0;
     cd.src0 = src0; cd.src1 = src1; cd.c0 = c0; cd.c1 = c1; cd.mode = src_mode; cd.pad_clamp = pad_clamp;
     cd.N = N; cd.H = H; cd.W = W; cd.sched = sched; cd.n_cols = n_cols; cd.wpack = wpack; cd.bias = bias_pack;
     cd.out = out; cd.epi = epi; cd.cout_stride = cout_stride; cd.act = act; cd.ring_only = ring_only; cd.cfg = cfg; cd.pool_out = pool_out;

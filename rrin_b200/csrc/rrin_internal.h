@@ -55,6 +55,7 @@ struct ConvDesc {
     int ring_only = 0;
     int cfg = -1;
     int f16 = 0;                  // operand / activation format: 0 bf16, 1 fp16 (precision mode)
+    int transposed = 0;           // TMA configs, 9-tap schedule, TMA-store epilogue: the kernel's rows run along the image width (see ConvParamsV2)
     const void* tmap0 = nullptr;  // TMA configs: pre-encoded CUtensorMap (128 bytes, host memory) of src0 / src1, or null
     const void* tmap1 = nullptr;
     const void* tmap_out = nullptr; // TMA-epilogue configs: pre-encoded map of `out`, or null
@@ -90,7 +91,7 @@ bool conv_config_valid(int cfg);
 // TMA configs (id >= 10): encode the tensor map of a bf16 NHWC tensor [N,H,W,C] (C % 64 == 0) into tmap_out (128 bytes, host);
 // which = 0: A-operand source (halo box), 1: epilogue destination (one warp's 8x4-pixel box), 2: raw coarse tile of an
 // exact-upsample source (dims are those of the coarse tensor)
-int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out);
+int conv_make_tmap(const void* base, int N, int H, int W, int C, int cfg, int which, void* tmap_out, int transposed = 0);
 bool conv_config_tma_epilogue(int cfg);
 int conv_config_info(int cfg, int* kcs, int* kb, int* nt, int* msub);
 // packed sizes for a layer: n_cols GEMM columns, n_stages*n_ent weight blocks of KB x NT

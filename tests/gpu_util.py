@@ -91,10 +91,13 @@ def pack(kind, cfg, weight, bias, n_stages, sched):
     return wp, bp, n_cols
 
 
+TRANSPOSED = 0       # conv_normal: run the launch transposed (rrin_conv3x3_ex)
+
+
 def launch(src0, src1, c0, c1, mode, pad_clamp, n, gh, gw, sched, n_cols, wp, bp, out, epi, cout_stride, act, ring_only, cfg, pool_out=None):
     check(lib().rrin_conv3x3_ex(src0.data_ptr(), src1.data_ptr() if src1 is not None else None, c0, c1, mode, pad_clamp, n, gh, gw,
                              sched, n_cols, wp.data_ptr(), bp.data_ptr(), out.data_ptr(), epi, cout_stride, int(act), int(ring_only),
-                             cfg, pool_out.data_ptr() if pool_out is not None else None, PREC, stream()), "rrin_conv3x3")
+                             cfg, pool_out.data_ptr() if pool_out is not None else None, PREC, TRANSPOSED, stream()), "rrin_conv3x3")
     torch.cuda.synchronize()
 
 

@@ -170,7 +170,7 @@ y = net(a.cuda(), b.cuda(), t=0.25).cpu()
 torch.save(y, sys.argv[1])
 """
 
-SWITCHES = [("RRIN_FUSE", "0", 0.0), ("RRIN_PDL", "0", 0.0), ("RRIN_GRAPH", "0", 0.0), ("RRIN_WARP_STAGE", "0", 0.0), ("RRIN_BIG_CFG", "19", 2e-3),
+SWITCHES = [("RRIN_FUSE", "0", 0.0), ("RRIN_PDL", "0", 0.0), ("RRIN_GRAPH", "0", 0.0), ("RRIN_WARP_STAGE", "0", 0.0), ("RRIN_TRANSPOSE", "0", 2e-3), ("RRIN_BIG_CFG", "19", 2e-3),
             ("RRIN_L0_PAIR", "0", 2e-3), ("RRIN_L0_PAIR", "26,24", 2e-3), ("RRIN_L1_CFG", "14,15", 2e-3), ("RRIN_L1_CFG", "43,41", 2e-3),
             ("RRIN_LAST_CFG", "13", 2e-3), ("RRIN_HEAD_CFG", "38", 2e-3),
             ("RRIN_L1_PAIR", "1", 2e-3), ("RRIN_UP_CFG", "5", 2e-3), ("RRIN_POOL1_CFG", "3", 2e-3)]

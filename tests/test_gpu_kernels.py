@@ -405,3 +405,30 @@ def test_fp16_pooled_outputs_and_fold_ring():
         test_conv_level0_with_pooled_output(1, 368, 368, 23)
         test_conv_folded_upsample_with_ring(True, 64, 32, 1, 136, 200, "strips")
         test_conv_folded_upsample_with_ring(False, 128, 64, 1, 72, 136, "strips")
+
+
+# ------------------------------------------------------------------ transposed launches (levels >= 2: bands along the image width)
+TRANSPOSED_CASES = ["tma_l2_128_128", "tma_l2_cat", "tma_l3_cat", "tma_l4_512_512", "tma_many_tiles_l2", "tma_many_tiles_l3_ntiles",
+                    "tma_up_l2", "tma_up_l3_ntiles", "tma_up_many_tiles", "tma_up_odd_sizes"]
+
+
+@pytest.mark.parametrize("name", TRANSPOSED_CASES)
+def test_transposed_conv_matches(name):
+    """Same convs with the kernel's rows along the image width (swapped tensor-map dimensions, swapped taps)."""
+    G.TRANSPOSED = 1
+    try:
+        test_conv_levels_ge1(next(c for c in NORMAL_CASES if c[0] == name))
+    finally:
+        G.TRANSPOSED = 0
+
+
+@pytest.mark.parametrize("cfg,cin,cout,n,h,w", [(16, 128, 128, 1, 12, 20), (16, 256, 256, 1, 100, 72), (16, 128, 128, 2, 136, 240), (16, 128, 128, 1, 34, 60)],
+                         ids=["l2", "l3_ntiles", "l2_1080p_like", "l4_1080p_like"])
+def test_transposed_conv_with_pooled_output(cfg, cin, cout, n, h, w):
+    G.TRANSPOSED = 1
+    try:
+        test_conv_with_pooled_output(cfg, cin, cout, n, h, w)
+        with G.precision(1):
+            test_conv_with_pooled_output(cfg, cin, cout, n, h, w)
+    finally:
+        G.TRANSPOSED = 0
