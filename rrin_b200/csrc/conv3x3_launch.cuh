@@ -38,6 +38,7 @@
 // 44 : level-0 `last` with FRAME STAGING (FS = 1, last column): refine_flow.last, whose epilogue runs both backward warps -- the 48 x 48
 //      pixel windows of the two source frames are TMA-loaded into shared memory per tile and the bilinear taps are gathered from there
 // 45 / 46 : config 21 (level-1 block.0 on the pooled 32-channel tensor) with two epilogue groups / two tile streams on 16 x 32 tiles
+// 47 : config 25 (level-0 cat on CTA pairs, resident half-blocks) with two tile streams: two issuing warps in the leader CTA
 // 32 / 33 / 34 : level-0 `last` (config 13) with 16 x 8 tiles and four / eight stages, or 16 x 16 tiles and four stages
 #define RRIN_CONV2_CONFIGS(X)                   \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0, 1, 0) \
@@ -76,7 +77,8 @@
     X(43, 64, 64, 64, 2, 2, 9, 0, 1, 1, 2, 1, 0, 2, 0) \
     X(44, 64, 32, 16, 2, 2, 16, 2, 1, 0, 2, 1, 0, 1, 1) \
     X(45, 32, 32, 64, 4, 3, 9, 0, 1, 1, 2, 1, 0, 1, 0) \
-    X(46, 32, 32, 64, 4, 2, 9, 0, 1, 1, 2, 1, 0, 2, 0)
+    X(46, 32, 32, 64, 4, 2, 9, 0, 1, 1, 2, 1, 0, 2, 0) \
+    X(47, 64, 32, 128, 1, 4, 32, 2, 1, 1, 2, 2, 0, 2, 0)
 
 
 namespace rrin {

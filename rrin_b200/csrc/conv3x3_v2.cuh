@@ -161,8 +161,9 @@ struct ConvCfgV2 {
     static_assert(!XF || ((8 * MSUB + 2) % 2 == 0 && (kTileH + 2) % 2 == 0), "transform stage works on 2x2 cells of the halo tile");
     static constexpr int SLOTS = 512 / NT;             // accumulator slots in TMEM
     static constexpr int SAQ = SA / NS, SLQ = SLOTS / NS, SBQ = SB / NS, EWQ = EW / NS;   // per tile stream
-    static_assert(NS == 1 || (NS == 2 && CG == 1 && !XF && SA % 2 == 0 && SLOTS % 2 == 0 && EW % 2 == 0 && (RES || SB % 2 == 0)),
-                  "two tile streams: single CTA, no transform stage, even stage / slot / epilogue-group counts");
+    static_assert(NS == 1 || (NS == 2 && (CG == 1 || RES) && !XF && SA % 2 == 0 && SLOTS % 2 == 0 && EW % 2 == 0 && (RES || SB % 2 == 0)),
+                  "two tile streams: no transform stage, even stage / slot / epilogue-group counts; on CTA pairs only with resident weights "
+                  "(both issuing warps live in the leader CTA)");
     static constexpr int N_ENT = SCHED == 0 ? 9 : (SCHED == 1 ? 16 : 8);
     static constexpr int BIAS_MAX = 512;
     static constexpr int OFF_B = SA * A_STAGE;

@@ -121,7 +121,7 @@ static void l0_pair_cfgs(int& c32, int& ccat) {
             int x = 0, y = 0;
             const int n = sscanf(e, "%d,%d", &x, &y);
             if (n == 1 && x == 0) { a = 11; b = 12; }
-            else if (n == 2) { a = (x == 23 || x == 26 || x == 27 || x == 11 || x == 35) ? x : 35; b = (y == 24 || y == 25 || y == 12) ? y : 25; }
+            else if (n == 2) { a = (x == 23 || x == 26 || x == 27 || x == 11 || x == 35) ? x : 35; b = (y == 24 || y == 25 || y == 12 || y == 47) ? y : 25; }
         }
     }
     c32 = a; ccat = b;
@@ -167,7 +167,7 @@ static Schedule build_schedule() {
                 l0_pair_cfgs(c32, ccat);
                 static const int last_cfg = [] { const char* e = getenv("RRIN_LAST_CFG"); const int v = e ? atoi(e) : 37; return (v == 13 || (v >= 32 && v <= 34) || v == 37 || v == 40) ? v : 37; }();
                 m.kind = PACK_S2D8; m.sched = SCHED_S2D8; m.cfg = is_last ? last_cfg : (cin == 32 ? c32 : ccat); m.n_stages = 2 * (cin / 32);
-                if (m.cfg >= 23 && m.cfg <= 27) m.kind = PACK_S2D8_CG2;
+                if ((m.cfg >= 23 && m.cfg <= 27) || m.cfg == 47) m.kind = PACK_S2D8_CG2;
             }
         } else {
             m.kind = PACK_NORMAL; m.sched = SCHED_TAPS9; m.n_cols = cout;

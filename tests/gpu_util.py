@@ -122,7 +122,7 @@ def conv_s2d(src0, src1, mode, n, hb, wb, weight, bias, act, cfg, n_stages, ring
     cout = weight.shape[0]
     c0 = src0.shape[-1] * (src0.shape[-2] if src0.dim() == 5 else 1)
     c1 = (src1.shape[-1] * src1.shape[-2]) if src1 is not None else 0
-    pair = cfg in (T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3, T_L0_PAIR1)
+    pair = cfg in (T_L0_PAIR, T_L0CAT_PAIR, T_L0CAT_PAIR1, T_L0_PAIR3, T_L0_PAIR1, 47)
     half = cfg in (T_L0, T_L0CAT, T_LAST, 32, 33, 34, 35, 37, 40) or pair
     kind, sched = ((PACK_S2D8_CG2 if pair else PACK_S2D8), SCHED_S2D8) if half else (PACK_S2D, SCHED_S2D16)
     if half:

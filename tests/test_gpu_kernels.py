@@ -178,6 +178,9 @@ S2D_CASES = [
     ("pair_l0_cat_odd_groups", 24, "cat", 64, 32, 32, False, 2, 80, 208),
     ("pair1_l0_cat", 25, "cat", 64, 32, 32, True, 1, 64, 96),
     ("pair1_l0_cat_many_tiles", 25, "cat", 64, 32, 32, True, 1, 368, 368),
+    ("pair_ns2_l0_cat", 47, "cat", 64, 32, 32, True, 1, 64, 96),
+    ("pair_ns2_l0_cat_many_tiles", 47, "cat", 64, 32, 32, True, 1, 368, 368),
+    ("pair_ns2_l0_cat_odd_groups", 47, "cat", 64, 32, 32, False, 2, 80, 208),
     ("pair6_l0_partial", 27, "plain", 32, 32, 32, True, 2, 48, 80),
     ("pair6_l0_many_tiles", 27, "plain", 32, 32, 32, True, 1, 368, 368),
     # two tile streams per CTA

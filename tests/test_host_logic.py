@@ -73,7 +73,7 @@ def test_conv_config_table_is_consistent():
     for cfg in range(-1, 64):
         if l.rrin_conv_config_info(cfg, *map(C.byref, v)) == 0:
             valid[cfg] = tuple(x.value for x in v)                       # kcs, kb, nt, msub
-    assert set(valid) == set(range(0, 9)) | set(range(10, 47)), sorted(valid)
+    assert set(valid) == set(range(0, 9)) | set(range(10, 48)), sorted(valid)
     for cfg, (kcs, kb, nt, msub) in valid.items():
         assert kcs in (32, 64, 128) and kb in (16, 32, 64) and kb <= kcs and nt in (16, 64, 128) and 1 <= msub <= 4, (cfg, kcs, kb, nt, msub)
         if cfg >= 10:
