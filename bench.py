@@ -11,10 +11,22 @@ K consecutive batches of it; there is no data-path collective (frame pairs are i
 SURVEY.md 8(e)), torch.distributed is used only for the barrier and the max over ranks of the
 device-timed region.  One JSON line is printed by rank 0; ``value`` counts interpolated frames.
 
+The line carries: ``value`` (device-resident inputs), ``e2e`` (the streaming pipeline from pinned host buffers, copies
+inside the timed region), ``roofline`` (dominant kernel class from live per-launch CUDA-event times against
+MEASURED_PEAKS.json; all convs; the whole step against the layer-wise roofline; every fused warp / blend launch against the
+HBM peak, the warp launch also under x200 flow weights), ``launch_gap`` (step time vs the sum of the launches), ``batch1``
+(single-pair calls), ``clocks`` (nvidia-smi samples inside the timed region) and, at N = 1, ``cpu_baseline`` (the oracle
+port on the host cores -- the only place this arm touches oracle/).
+
+``--config`` selects the other named configurations of BASELINE.json through the same contract: ``720p_b8``
+(configs[1]), ``1080p_t7`` (configs[3]: 7 timesteps per pair, Flow U-Net once), ``4k`` (configs[4]) and ``clip``
+(configs[2] as a strong-scaling job: the whole 240-frame clip per step, 239 pairs split over the ranks, frames/s =
+239 / the slowest rank's time).  ``--precision fp16`` runs the precision mode.
+
 ``--impl reference`` times the reference's own CPU path instead: the oracle port
 (oracle/rrin_oracle.py: the same torch CPU operators at the same call sites as the reference,
 which is pure Python and cannot travel to the GPU box) on all host threads, each step a bounded
-strip of the same 1080p workload.
+strip of the same workload.
 
 ``--impl library`` (not part of the driver's contract; context only) times the same oracle
 restatement as torch eager operators on cuda:0 -- cuDNN convolutions in fp32, TF32 and bf16
