@@ -41,7 +41,7 @@ extern "C" {
 
 /* 16-bit operand / activation format of the tensor-core path (accumulation is always fp32; flows, mask logits, the blend
  * and the final residue stay fp32).  BF16: fp32 range, 8-bit significand -- the default, PSNR >= 50 dB path.  FP16: 11-bit
- * significand at the same speed and size -- the "fp32-accumulate path within 1e-3" precision mode; activations above 65504
+ * significand at the same MMA rate and size -- the "fp32-accumulate path within 1e-3" precision mode; activations above 65504
  * would overflow.  The reference computes these convs in fp32 (unet.py:29,38,59,62,78). */
 #define RRIN_PRECISION_BF16 0
 #define RRIN_PRECISION_FP16 1
