@@ -670,9 +670,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                     // at the tensor edges by the TMA unit, so partial tiles need no masks.
                     const uint32_t stg = s_base + C::OFF_EPI + warp * 4096;
                     float pacc[SCHED == 2 ? 32 : 1];     // space-to-depth grid: running sum over the 4 phases (pool_out)
-#pragma unroll 1
-                    for (int c = 0; c < NT; c += 64) {
-                        uint32_t o[32];
+                    // one 64-column chunk: accumulators -> (+bias, LeakyReLU) -> 32 packed 16-bit pairs in registers
+                    auto load_chunk = [&](const int c, uint32_t (&o)[32]) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             uint32_t ra[16], rb[16];
@@ -696,6 +695,9 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                                 o[16 * h + 8 + 2 * i + 1] = pack2<F16>(v3.x, v3.y);
                             }
                         }
+                    };
+                    // ... -> swizzled staging -> TMA tensor store (+ the pooled second output)
+                    auto store_chunk = [&](const int c, uint32_t (&o)[32]) {
                         if (lane == 0) bulk_wait_group_read<0>();       // the previous store has finished reading the buffer
                         __syncwarp();
 #pragma unroll
@@ -753,6 +755,22 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                                                    acc, 0.25f);
                                 }
                             }
+                        }
+                    };
+                    if constexpr (EARLY && NT == 128 && SCHED == 0) {
+                        // The next tile's MMAs wait for this slot: pull BOTH chunks into registers first and hand the slot back
+                        // (inside load_chunk, after the last tcgen05.ld) before any staging / store / pooling work.
+                        uint32_t o0[32], o1[32];
+                        load_chunk(0, o0);
+                        load_chunk(64, o1);
+                        store_chunk(0, o0);
+                        store_chunk(64, o1);
+                    } else {
+#pragma unroll 1
+                        for (int c = 0; c < NT; c += 64) {
+                            uint32_t o[32];
+                            load_chunk(c, o);
+                            store_chunk(c, o);
                         }
                     }
                 } else if (NT == 16) {                   // fp32 [.,16] epilogue of the `last` convs
