@@ -53,11 +53,16 @@ def list_frames(src_dir: str, order: str = "sorted") -> List[str]:
 
 def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str] = None, models_dir: str = "models",
                    net=None, batch: int = 2, resume: bool = False, order: str = "sorted", chunk_pairs: int = 64,
-                   io_workers: int = 4, device: Optional[torch.device] = None) -> List[str]:
+                   io_workers: int = 4, device: Optional[torch.device] = None, rank: int = 0, world: int = 1) -> List[str]:
     """Interpolates ``sf`` frames between consecutive images of ``src_dir`` into ``dst_dir``; returns the written paths in
     output order.  ``net``: a ready ``rrin_b200.Net`` (cuda, eval); otherwise the checkpoint ``models_dir/<model_name>*`` is
     loaded like convert.py:98-111.  ``resume=True`` continues like convert.py:46-53 (the pair index is recomputed from the
-    number of files already in ``dst_dir``)."""
+    number of files already in ``dst_dir``).
+
+    ``rank`` / ``world``: multi-GPU conversion (SURVEY.md 8(e)) -- one process per GPU, each calls this function with its rank;
+    rank r interpolates the contiguous pair range ``sharding.pair_range(n_frames, r, world)`` and writes exactly the files of
+    that range (the original in front of the first pair is written by the rank that owns the pair), so the union over the
+    ranks is the single-process output, file for file.  No communication between the ranks."""
     from .model import Net
     from .pipeline import ClipInterpolator
     if sf < 1:
@@ -66,14 +71,24 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
     if len(names) < 2:
         raise RuntimeError(f"{src_dir}: need at least two frames, found {len(names)}")
     os.makedirs(dst_dir, exist_ok=True)
-    existing = len(os.listdir(dst_dir))
-    if resume:
-        ridx = rio.resume_index(existing, sf)
+    if world > 1:
+        from .sharding import pair_range
+        if resume:
+            raise ValueError("resume is a single-process feature (it counts the files already written)")
+        first_pair, last_pair = pair_range(len(names), rank, world)   # this rank's contiguous shard of pairs
+        if first_pair == last_pair:
+            return []
+        ridx = first_pair + 1
     else:
-        if existing:
-            raise RuntimeError("Folder is already in use! Did you intend to resume the progress? Use resume=True")   # convert.py:57-59
-        ridx = 1
-    first_pair = ridx - 1                                             # ConvertSampler(dataset, resume_index - 1), convert.py:95
+        last_pair = len(names) - 1
+        existing = len(os.listdir(dst_dir))
+        if resume:
+            ridx = rio.resume_index(existing, sf)
+        else:
+            if existing:
+                raise RuntimeError("Folder is already in use! Did you intend to resume the progress? Use resume=True")   # convert.py:57-59
+            ridx = 1
+        first_pair = ridx - 1                                         # ConvertSampler(dataset, resume_index - 1), convert.py:95
     img_count = rio.first_output_number(ridx, sf)                     # convert.py:118
 
     if net is None:
@@ -104,10 +119,10 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
         return p
 
     try:
-        n_pairs = len(names) - 1
+        n_pairs = last_pair
         p0 = first_pair
-        if img_count == 1:                                            # convert.py:121-123: the very first original
-            jobs.append(pool.submit(shutil.copy, paths[p0], out_path(1, exts[p0])))
+        if img_count == 1 or world > 1:                               # convert.py:121-123: the original in front of the first pair
+            jobs.append(pool.submit(shutil.copy, paths[p0], out_path(img_count, exts[p0])))
         carry = first
         while p0 < n_pairs:
             p1 = min(n_pairs, p0 + chunk_pairs)

@@ -90,6 +90,26 @@ def test_convert_folder_resume_like_reference(tmp_path):
     assert {n: open(dst2 / n, "rb").read() for n in sorted(os.listdir(dst2))} == full
 
 
+def test_convert_folder_sharded_over_ranks_equals_single_process(tmp_path):
+    """Multi-GPU conversion: every rank converts its contiguous pair shard on its own (here: one after the other on one GPU);
+    the union of what the ranks write is the single-process output, file for file."""
+    h0, w0, sf = 48, 64, 2
+    src, ref_dst, dst = tmp_path / "frames", tmp_path / "ref", tmp_path / "sharded"
+    _write_frames(str(src), 8, h0, w0)
+    net = Net()
+    net.load_state_dict(O.seeded_state_dict(stress_flow=50.0), strict=True)
+    net = net.cuda().eval()
+    convert_folder(str(src), str(ref_dst), sf, net=net, batch=2)
+    want = {n: open(ref_dst / n, "rb").read() for n in sorted(os.listdir(ref_dst))}
+    written = []
+    for rank in range(3):
+        written += convert_folder(str(src), str(dst), sf, net=net, batch=2, rank=rank, world=3)
+    got = {n: open(dst / n, "rb").read() for n in sorted(os.listdir(dst))}
+    assert got == want
+    assert len(written) == len(want) + 2          # the two shard-boundary originals are written by both neighbours (same bytes)
+    assert convert_folder(str(src), str(tmp_path / "empty"), sf, net=net, rank=9, world=10) == []
+
+
 _REAL_CONVERT = r"""
 import os, sys, argparse
 ROOT, REF, WORK = sys.argv[1:4]
