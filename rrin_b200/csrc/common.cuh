@@ -85,6 +85,11 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Named barrier over a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // Waits for the phase with the given parity to complete (try_wait suspends in HW).
 // A wait that never completes (a pipeline bug) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

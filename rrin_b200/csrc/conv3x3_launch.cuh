@@ -39,6 +39,8 @@
 //      pixel windows of the two source frames are TMA-loaded into shared memory per tile and the bilinear taps are gathered from there
 // 45 / 46 : config 21 (level-1 block.0 on the pooled 32-channel tensor) with two epilogue groups / two tile streams on 16 x 32 tiles
 // 47 : config 25 (level-0 cat on CTA pairs, resident half-blocks) with two tile streams: two issuing warps in the leader CTA
+//      (three / four epilogue groups for this launch -- 480 / 608 threads, 128 / 96 registers -- measured 0.376 -> 0.402 / 0.485 ms: the
+//      gathers are bound by shared-memory wavefronts next to the MMAs' operand reads, not by the number of warps in flight)
 // 32 / 33 / 34 : level-0 `last` (config 13) with 16 x 8 tiles and four / eight stages, or 16 x 16 tiles and four stages
 #define RRIN_CONV2_CONFIGS(X)                   \
     X(10, 64, 16, 128, 2, 3, 16, 1, 1, 1, 2, 1, 0, 1, 0) \

@@ -46,6 +46,12 @@
 #include "glue_device.cuh"
 #include "rrin_internal.h"
 
+// A/B builds (python -m rrin_b200.build -DRRIN_SCATTER_EARLY=0): per-thread-store epilogue of the 3-of-4-slot tiles without the
+// early accumulator-slot hand-back
+#ifndef RRIN_SCATTER_EARLY
+#define RRIN_SCATTER_EARLY 1
+#endif
+
 namespace rrin {
 
 // Glue of Net.process / Net.forward fused into the epilogue of a U-Net's `last` conv (fp32 [.,16] epilogue, one thread per
@@ -179,7 +185,7 @@ struct ConvCfgV2 {
     static_assert(!ETMA || (NT % 64 == 0 && (B_BLOCK % 1024 == 0)), "TMA epilogue: 64-column chunks, aligned staging");
     static_assert(KB % 16 == 0 && KB <= 64 && NT % 16 == 0 && NT <= 256, "UMMA shape");
     static_assert((SCHED == 0 && KB == KCS) || (SCHED == 1 && KB == 16) || (SCHED == 2 && KB == 32), "schedule / K block");
-    static_assert(MSUB >= 1 && MSUB <= SLOTS / NS && SLOTS <= 32 && SLOTS % EW == 0, "accumulator slots");
+    static_assert(MSUB >= 1 && MSUB <= SLOTS / NS && SLOTS <= 32 && EW <= SLOTS, "accumulator slots");
     static_assert(!RES || SB % N_ENT == 0, "resident weights: SB counts whole stages of blocks");
     // half entry? (parity, e) -> 0 full | 1 lower columns [0,64) (a = 0) | 2 upper columns [64,128) (a = 1)
     __host__ __device__ static constexpr int half_of(int parity, int e) {
@@ -312,7 +318,6 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
         mbar_fence_init();
     }
     if (warp == W_A && lane == 0) { tma_prefetch_desc(&tm0); tma_prefetch_desc(&tm1); if (ETMA || FS) tma_prefetch_desc(&tmo); if (CG == 2 || FS) tma_prefetch_desc(&tmw); }
-    for (int i = threadIdx.x; i < p.n_ntiles * NT; i += blockDim.x) bias_s[i] = p.bias[i];
     if (warp == W_MMA) {
         if (CG == 2) { tmem_alloc_cg2(smem_u32(tmem_slot), 512); tmem_relinquish_cg2(); }
         else { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -323,6 +328,13 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
+    if (warp < 4 * EW) {
+        // The bias is read by the epilogue warps only and is constant data: they fetch it here, behind the CTA-wide barrier and in
+        // front of the wait for the previous kernel, so its (cold, DRAM-latency) load overlaps the pipeline fill instead of holding
+        // up every role's start.
+        for (int i = threadIdx.x; i < p.n_ntiles * NT; i += 4 * EW * 32) bias_s[i] = p.bias[i];
+        named_bar_sync(1, 4 * EW * 32);
+    }
     if (warp != W_B) pdl_wait();      // activations (reads and writes) only after the previous kernel has finished; weights are constant
 
     TileWalkV2 walk;
@@ -825,14 +837,12 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                         }
                     }
                 } else {
-#pragma unroll 1
-                    for (int c = 0; c < NT; c += 32) {
+                    // 32 columns: accumulators -> (+bias, activation) -> 16 packed 16-bit pairs
+                    auto load32 = [&](const int c, uint32_t (&o)[16]) {
                         uint32_t ra[16], rb[16];
                         tmem_ld16(t0 + c, ra);
                         tmem_ld16(t0 + c + 16, rb);
                         tmem_ld_wait();
-                        if (EARLY && c == NT - 32) { release_slot(); released = true; }
-                        uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float2 v = f2add(make_float2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1])), make_float2(bsrc[c + 2 * i], bsrc[c + 2 * i + 1]));
@@ -845,23 +855,40 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                             if (p.act) v = lrelu2(v);
                             o[8 + i] = pack2<F16>(v.x, v.y);
                         }
-                        if (ok) {
-                            __nv_bfloat16* op;
-                            if (p.epi == EPI_SCATTER) {
-                                // folded upsample: global column g = (a, b, co); pixel (2y+a, 2x+b) of the hi-res NHWC tensor
-                                const int g = t.nt * NT + c, cs = p.cout_stride;
-                                const int ph = g / cs, co = g - ph * cs;
-                                const size_t hp = ((size_t)(t.n * 2 * p.H + 2 * gy + (ph >> 1)) * (2 * p.W) + 2 * gx + (ph & 1));
-                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + hp * cs + co;
-                            } else {
-                                op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout_stride + t.nt * NT + c;
-                            }
-                            stg256(op, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
-                            stg256(op + 16, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
+                    };
+                    auto store32 = [&](const int c, const uint32_t (&o)[16]) {
+                        if (!ok) return;
+                        __nv_bfloat16* op;
+                        if (p.epi == EPI_SCATTER) {
+                            // folded upsample: global column g = (a, b, co); pixel (2y+a, 2x+b) of the hi-res NHWC tensor
+                            const int g = t.nt * NT + c, cs = p.cout_stride;
+                            const int ph = g / cs, co = g - ph * cs;
+                            const size_t hp = ((size_t)(t.n * 2 * p.H + 2 * gy + (ph >> 1)) * (2 * p.W) + 2 * gx + (ph & 1));
+                            op = reinterpret_cast<__nv_bfloat16*>(p.out) + hp * cs + co;
+                        } else {
+                            op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.cout_stride + t.nt * NT + c;
+                        }
+                        stg256(op, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                        stg256(op + 16, o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
+                    };
+                    if constexpr (EARLY && NT == 128 && RRIN_SCATTER_EARLY) {
+                        // as in the TMA epilogue above: all 128 columns into registers (64 packed words), the slot back to the
+                        // MMA thread, then the address arithmetic and the stores
+                        uint32_t o0[16], o1[16], o2[16], o3[16];
+                        load32(0, o0); load32(32, o1); load32(64, o2); load32(96, o3);
+                        release_slot(); released = true;
+                        store32(0, o0); store32(32, o1); store32(64, o2); store32(96, o3);
+                    } else {
+#pragma unroll 1
+                        for (int c = 0; c < NT; c += 32) {
+                            uint32_t o[16];
+                            load32(c, o);
+                            if (EARLY && c == NT - 32) { release_slot(); released = true; }
+                            store32(c, o);
                         }
                     }
                 }
-                if (!released) release_slot();                  // (CTA pairs: the leader's MMA thread waits for both CTAs)
+                if (!released) release_slot();                 // (CTA pairs: the leader's MMA thread waits for both CTAs)
             }
             if (staged) {                                 // every epilogue warp hands the window back, also one without a sub-tile in this tile
                 __syncwarp();
