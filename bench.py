@@ -89,13 +89,17 @@ class ClockSampler:
         while self.proc is not None and not self.rows and time.time() - t0 < timeout and self.proc.poll() is None:
             time.sleep(0.02)
 
-    def stop(self, t0: float, t1: float):
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0: float, t1: float):
+        """Median SM clock and the throttle reasons seen between the wall-clock times t0 and t1 (the sampler keeps running)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
+        for ts, line in list(self.rows):
             if ts < t0 or ts > t1:
                 continue
             f = [x.strip() for x in line.split(",")]
@@ -343,7 +347,7 @@ def run_gpu(args):
     barrier()
     t_wall1 = time.time()
     ms_max = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop(t_wall0, t_wall1)
+    clk = clocks.window(t_wall0, t_wall1)
     value = K * frames_per_step_job / (ms_max * 1e-3)
 
     # ---------------- end to end with host buffers (`e2e`): the streaming clip pipeline (rrin_b200.ClipInterpolator) over a
@@ -363,11 +367,19 @@ def run_gpu(args):
     pipe = ClipInterpolator(net, H, W, batch=pb, sf=sf)
     nw = min(n_clip_pairs, 4 * pb)                               # four batches: each staging slot is seen twice, so its CUDA graph exists
     pipe.run(host_clip[:nw + 1], out_host[:nw * sf])             # warm-up (engines, graphs, events)
+    # The GPU has idled while the pinned clip was filled, and the timed pipeline run is shorter than the K-step loop above: bring
+    # the chip back under the sustained load (power cap, clocks) of that loop first -- untimed whole-clip runs for about as long
+    # as the K steps took -- so that `e2e` is not a cold-start burst number.
+    for _ in range(1 if clip_mode else max(1, -(-K // ke) - 1)):
+        pipe.run(host_clip, out_host)
     barrier()
+    t_wall2 = time.time()
     e0.record()
     pipe.run(host_clip, out_host)
     e1.record()
     barrier()
+    clk_e2e = clocks.window(t_wall2, time.time())
+    clocks.close()
     t_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_frames_job = (CLIP_FRAMES - 1) if clip_mode else world * n_clip_pairs * sf
     e2e_steps = 1 if clip_mode else ke
@@ -375,7 +387,8 @@ def run_gpu(args):
     h2d_step, d2h_step = pipe.h2d_bytes / e2e_steps, pipe.d2h_bytes / e2e_steps
     e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step, "steps": e2e_steps,
            "api": "rrin_b200.ClipInterpolator.run(pinned host clip) -> pinned host frames: each source frame uploaded once, "
-                  "H2D / forward / D2H of successive batches on three streams, one host sync at the end"}
+                  "H2D / forward / D2H of successive batches on three streams, one host sync at the end",
+           "sm_mhz": clk_e2e.get("sm_mhz")}
     del host_clip, out_host, pipe
     if args.config == "1080p":
         # same pipeline fed with the bytes an image decoder produces (uint8 HWC 1920x1080; Pad + ToTensor and to_pil + crop of

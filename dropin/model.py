@@ -4,9 +4,9 @@
 the reference on ``sys.path`` (``PYTHONPATH=<repo>/dropin:<repo>``) makes the unedited ``convert.py``
 construct the B200-native ``Net`` instead.  Convert (inference) only: the drop-in has no
 backward pass and raises when called the way ``train.py:98`` calls the model.
-``warp`` is not re-exported: in this implementation it exists only fused inside the K3 kernel
-(``rrin_b200/csrc/glue_device.cuh``), and no caller outside ``model.py`` uses it.
+``warp`` (model.py:8-21) is exported too: inside ``Net.forward`` the two warps run fused in the K3 epilogue
+(``rrin_b200/csrc/glue_device.cuh``); the stand-alone function is one CUDA kernel with the same arithmetic (``rrin_warp``).
 """
-from rrin_b200.model import Net  # noqa: F401
+from rrin_b200.model import Net, warp  # noqa: F401
 
-__all__ = ["Net"]
+__all__ = ["Net", "warp"]

@@ -154,6 +154,11 @@ RRIN_API int rrin_warp_pack(const float* flow4, const float* res4, const float* 
  * (model.py:61) -> out4 (fp32 NHWC4) and the `final` head input f16. */
 RRIN_API int rrin_blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef,
                     int n_samples, int pair_mul, int H, int W, float* out4, void* f16, void* stream);
+/* K3b: the reference's public `warp(img, flow)` (model.py:8-21) on its own: img fp32 NCHW [N,C,H,W], flow fp32 [N,2,H,W]
+ * (channel 0 = x displacement, 1 = y displacement, in pixels) -> out fp32 [N,C,H,W].  Grid build in the reference's fp32
+ * op order (model.py:15-18) + F.grid_sample defaults (bilinear, zeros padding, align_corners=False).  Any H, W >= 1.
+ * Net.forward never calls this (its two warps run fused in K3); it exists so that `from model import warp` keeps working. */
+RRIN_API int rrin_warp(const float* img, const float* flow, int N, int C, int H, int W, float* out, void* stream);
 /* K5: final residue add + clamp(0,1) (model.py:62-63) -> fp32 NCHW result. */
 RRIN_API int rrin_residue_clamp(const float* res4, const float* out4, int n_samples, int H, int W, float* out_nchw, void* stream);
 

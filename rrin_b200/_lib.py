@@ -45,6 +45,7 @@ _SIGNATURES = {
     "rrin_flow_tscale_pack": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_warp_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
     "rrin_blend_pack": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp]),
+    "rrin_warp": (ci, [vp, vp, ci, ci, ci, ci, vp, vp]),
     "rrin_residue_clamp": (ci, [vp, vp, ci, ci, ci, vp, vp]),
     "rrin_frame_from_u8": (ci, [vp, ci, ci, ci, ci, ci, vp, vp]),
     "rrin_frame_to_u8": (ci, [vp, ci, ci, ci, ci, vp, vp]),

@@ -775,6 +775,9 @@ int rrin_frame_from_u8(const uint8_t* src_hwc, int H0, int W0, int C, int top_pa
 int rrin_frame_to_u8(const float* src_nchw, int H, int W, int H0, int W0, uint8_t* dst_hwc, void* stream) {
     return frame_to_u8(src_nchw, H, W, H0, W0, dst_hwc, static_cast<cudaStream_t>(stream));
 }
+int rrin_warp(const float* img, const float* flow, int N, int C, int H, int W, float* out, void* stream) {
+    return warp_frames(img, flow, N, C, H, W, out, static_cast<cudaStream_t>(stream));
+}
 int rrin_residue_clamp(const float* res4, const float* out4, int n, int H, int W, float* out_nchw, void* stream) {
     return residue_clamp(res4, out4, n, H, W, out_nchw, static_cast<cudaStream_t>(stream));
 }

@@ -193,6 +193,65 @@ __global__ void __launch_bounds__(kGlueThreads) frame_to_u8_kernel(const float* 
     }
 }
 
+// ------------------------------------------------------------------ K3b: warp(img, flow) of model.py:8-21 on its own
+// img fp32 [N,C,H,W], flow fp32 [N,2,H,W] (u = x displacement, v = y displacement) -> out fp32 [N,C,H,W]:
+// out[n,c,y,x] = bilinear sample of img[n,c] at (x+u-0.5 .. , y+v-0.5 ..) exactly as the reference's grid build +
+// F.grid_sample (zeros padding, align_corners=False) evaluates it -- the coordinate arithmetic and the tap accumulation order
+// are the fused K3's (warp_coord / bilinear_gather3), so both agree bit for bit.  One thread per pixel group of VEC pixels
+// along the row (coalesced flow loads and result stores), all C channels of that group.
+template <int VEC>
+__global__ void __launch_bounds__(kGlueThreads) warp_kernel(const float* __restrict__ img, const float* __restrict__ flow, int N, int C, int H, int W,
+                                                             float* __restrict__ out) {
+    const long HW = (long)H * W;
+    const int Wg = W / VEC;
+    const long groups = (long)N * H * Wg;
+    const float fW = (float)W, fH = (float)H, rW = __frcp_rn(fW), rH = __frcp_rn(fH);
+    for (long g = blockIdx.x * (long)blockDim.x + threadIdx.x; g < groups; g += (long)gridDim.x * blockDim.x) {
+        const long row = g / Wg;
+        const int x0 = (int)(g - row * Wg) * VEC;
+        const int n = (int)(row / H), y = (int)(row - (long)n * H);
+        const float* fl = flow + (long)n * 2 * HW + (long)y * W + x0;
+        float u[VEC], v[VEC];
+        if constexpr (VEC == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(fl), b = *reinterpret_cast<const float4*>(fl + HW);
+            u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; v[0] = b.x; v[1] = b.y; v[2] = b.z; v[3] = b.w;
+        } else {
+            u[0] = fl[0]; v[0] = fl[HW];
+        }
+        // per pixel: tap position, in-range flags and the four weights once; then four loads per channel
+        int base[VEC]; float wnw[VEC], wne[VEC], wsw[VEC], wse[VEC]; unsigned in[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float ix = warp_coord(x0 + k, u[k], fW, rW), iy = warp_coord(y, v[k], fH, rH);
+            const float xw = floorf(ix), yn = floorf(iy);
+            const float w = ix - xw, e = 1.f - w, nn = iy - yn, s = 1.f - nn;
+            const int px = min(max((int)xw, -2), W), py = min(max((int)yn, -2), H);      // saturating casts, see bilinear_gather3
+            const bool xin0 = (unsigned)px < (unsigned)W, xin1 = (unsigned)(px + 1) < (unsigned)W;
+            const bool yin0 = (unsigned)py < (unsigned)H, yin1 = (unsigned)(py + 1) < (unsigned)H;
+            in[k] = (yin0 && xin0 ? 1u : 0u) | (yin0 && xin1 ? 2u : 0u) | (yin1 && xin0 ? 4u : 0u) | (yin1 && xin1 ? 8u : 0u);
+            wnw[k] = s * e; wne[k] = s * w; wsw[k] = nn * e; wse[k] = nn * w;
+            base[k] = py * W + px;               // |py|, |px| <= max(H, W) + 2: fits an int for every frame the engine accepts
+        }
+        for (int c = 0; c < C; ++c) {
+            const float* p = img + ((long)n * C + c) * HW;
+            float o[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const float* q = p + base[k];
+                float acc = 0.f;
+                if (in[k] & 1u) acc += __ldg(q) * wnw[k];
+                if (in[k] & 2u) acc += __ldg(q + 1) * wne[k];
+                if (in[k] & 4u) acc += __ldg(q + W) * wsw[k];
+                if (in[k] & 8u) acc += __ldg(q + W + 1) * wse[k];
+                o[k] = acc;
+            }
+            float* d = out + ((long)n * C + c) * HW + (long)y * W + x0;
+            if constexpr (VEC == 4) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            else d[0] = o[0];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host launchers
 static int check_dims(const char* who, int N, int H, int W) {
     if (N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) { set_error("%s: bad shape N=%d H=%d W=%d (H, W must be even)", who, N, H, W); return RRIN_ERR_BAD_SHAPE; }
@@ -258,6 +317,15 @@ int frame_to_u8(const float* src, int H, int W, int H0, int W0, uint8_t* dst, cu
         frame_to_u8_kernel<4><<<glue_grid((long)H0 * W0 / 4), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
     else
         frame_to_u8_kernel<1><<<glue_grid((long)H0 * W0), kGlueThreads, 0, s>>>(src, H, W, H0, W0, dst);
+    RRIN_CUDA_CHECK(cudaGetLastError());
+    return RRIN_OK;
+}
+int warp_frames(const float* img, const float* flow, int N, int C, int H, int W, float* out, cudaStream_t s) {
+    if (!img || !flow || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("warp: bad argument"); return RRIN_ERR_BAD_ARG; }
+    if ((long)H * W > 0x3fffffffL) { set_error("warp: frame too large"); return RRIN_ERR_BAD_SHAPE; }
+    const bool vec = W % 4 == 0 && !((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(flow) | reinterpret_cast<uintptr_t>(out)) & 15);
+    if (vec) warp_kernel<4><<<glue_grid((long)N * H * (W / 4)), kGlueThreads, 0, s>>>(img, flow, N, C, H, W, out);
+    else warp_kernel<1><<<glue_grid((long)N * H * W), kGlueThreads, 0, s>>>(img, flow, N, C, H, W, out);
     RRIN_CUDA_CHECK(cudaGetLastError());
     return RRIN_OK;
 }

@@ -119,6 +119,7 @@ int warp_pack(const float* flow4, const float* res4, const float* in0, const flo
 int blend_pack(const float* mask4, const float* xt8, const float* in0, const float* in1, const float* coef,
                int Nt, int pair_mul, int H, int W, float* out4, void* f16, cudaStream_t s, int use_f16 = 0);
 int residue_clamp(const float* res4, const float* out4, int Nt, int H, int W, float* out_nchw, cudaStream_t s);
+int warp_frames(const float* img, const float* flow, int N, int C, int H, int W, float* out, cudaStream_t s);
 // uint8 frame I/O of the streaming pipeline: Pad(edge) + ToTensor (dataloader.py:93-118) and to_pil_image + crop (utils.py:51-58)
 int frame_from_u8(const uint8_t* src, int H0, int W0, int C, int top, int bottom, float* dst, cudaStream_t s);
 int frame_to_u8(const float* src, int H, int W, int H0, int W0, uint8_t* dst, cudaStream_t s);

@@ -33,6 +33,33 @@ from torch import nn
 from .unet import UNet
 
 
+def warp(img: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """``warp(img, flow)`` of the reference (model.py:8-21): backward-warps ``img`` ``[N,C,H,W]`` by ``flow`` ``[N,2,H,W]``
+    (channel 0 = x displacement, 1 = y displacement, in pixels) -- the reference's grid build in its fp32 op order followed by
+    ``F.grid_sample`` (bilinear, zeros padding, align_corners=False) -- in one CUDA kernel (``rrin_warp``).  ``Net.forward``
+    does not call it (its two warps run fused into the epilogue of ``refine_flow.last``); it is exported because the
+    reference's ``model`` module exports it.  Inference only, CUDA only, like ``Net``."""
+    from ._lib import check, lib
+    if not (img.is_cuda and flow.is_cuda):
+        raise RuntimeError("rrin_b200.warp runs on CUDA (sm_100a) only; there is no CPU fallback "
+                           "(the reference too hard-codes .cuda(), model.py:11-12)")
+    if torch.is_grad_enabled() and (img.requires_grad or flow.requires_grad):
+        raise RuntimeError("rrin_b200.warp is inference only (no backward pass): call it under torch.no_grad()")
+    if img.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2 or flow.shape[0] != img.shape[0] or flow.shape[2:] != img.shape[2:]:
+        # the reference fails in expand_as / grid_sample with a size mismatch
+        raise RuntimeError(f"Sizes of tensors must match: expected img [N,C,H,W] and flow [N,2,H,W], got "
+                           f"{tuple(img.shape)} and {tuple(flow.shape)}")
+    n, c, h, w = img.shape
+    img = img.detach().to(torch.float32).contiguous()
+    flow = flow.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(img)
+    if out.numel():
+        with torch.cuda.device(img.device):
+            check(lib().rrin_warp(img.data_ptr(), flow.data_ptr(), n, c, h, w, out.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "rrin_warp")
+    return out
+
+
 class Net(nn.Module):
     def __init__(self, level: Optional[int] = None):  # `level` ignored, see module docstring
         super().__init__()

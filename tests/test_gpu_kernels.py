@@ -3,6 +3,8 @@
 conv3x3 (tcgen05) is compared with a float64 torch convolution of the same bf16-rounded
 operands, so the only differences are fp32 accumulation order and the bf16 rounding of the
 stored output; the glue kernels are compared with the CPU oracle's operators."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -435,3 +437,77 @@ def test_transposed_conv_with_pooled_output(cfg, cin, cout, n, h, w):
             test_conv_with_pooled_output(cfg, cin, cout, n, h, w)
     finally:
         G.TRANSPOSED = 0
+
+
+# ------------------------------------------------------------------ stand-alone warp(img, flow) (model.py:8-21)
+WARP_CASES = ["rgb_2x24x40_s6", "c5_1x17x23_s3", "rgb_1x16x32_s01", "rgb_1x8x12_special"]
+
+
+@pytest.mark.parametrize("name", WARP_CASES)
+def test_warp_matches_reference_fixture(name):
+    """``rrin_b200.warp`` against the unmodified reference's ``warp`` (tests/golden/warp_cases.npz, oracle/make_golden_warp.py)
+    and against the oracle restatement.  The fixture was produced by ATen's CPU grid_sample, which multiplies masked-out taps
+    by their (NaN) weights for an INFINITE coordinate and so returns NaN there; ATen's CUDA kernel -- what the reference, with
+    its hard-coded .cuda(), runs -- skips out-of-range taps and returns 0.  Those pixels are checked against 0."""
+    import numpy as np
+    from rrin_b200 import warp
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp_cases.npz"))
+    img, flow, ref = (torch.from_numpy(d[f"{name}/{k}"]) for k in ("img", "flow", "out"))
+    with torch.no_grad():
+        y = warp(img.cuda(), flow.cuda()).cpu()
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    inf_px = torch.isinf(flow).any(1, keepdim=True).expand_as(ref)
+    assert (y[inf_px] == 0).all()
+    nan_ref = torch.isnan(ref) & ~inf_px
+    assert torch.equal(torch.isnan(y), nan_ref)                       # a NaN flow samples NaN, nothing else does
+    ok = ~(nan_ref | inf_px)
+    err = (y[ok] - ref[ok]).abs().max().item()
+    print(f"warp {name}: max-abs {err:.3e} vs the reference's warp")
+    assert err <= 2e-5
+    o = O.warp(img, flow)
+    assert (y[ok] - o[ok]).abs().max().item() <= 2e-5
+    # the second vector path / scalar path agree: a misaligned view forces the scalar kernel
+    if img.shape[-1] % 4 == 0:
+        buf = torch.empty(img.numel() + 1, device="cuda")
+        view = buf[1:].view_as(img)
+        view.copy_(img)
+        with torch.no_grad():
+            y2 = warp(view, flow.cuda()).cpu()
+        assert torch.equal(torch.nan_to_num(y2, nan=-1.0), torch.nan_to_num(y, nan=-1.0))
+
+
+def test_warp_agrees_with_the_fused_warps():
+    """The stand-alone kernel and the K3 warps fused behind refine_flow.last share their coordinate and tap arithmetic: same bits."""
+    from rrin_b200 import warp
+    from rrin_b200._lib import check, lib
+    n, h, w = 1, 32, 48
+    a, b = O.seeded_frames(n, h, w, seed=9, smooth=True)
+    g = torch.Generator().manual_seed(11)
+    flow = torch.randn(n, 4, h, w, generator=g) * 5.0
+    res = torch.zeros(n, 4, h, w)
+    coef = _coef([0.5])
+    tt = 0.5
+    ft0 = -(1 - tt) * tt * flow[:, :2] + tt * tt * flow[:, 2:4]
+    ft1 = (1 - tt) * (1 - tt) * flow[:, :2] - tt * (1 - tt) * flow[:, 2:4]
+    flow4, res4 = _s2d_f32(flow, 4), _s2d_f32(res, 4)
+    m16 = torch.empty(n, h // 2, w // 2, 4, 16, dtype=torch.bfloat16, device="cuda")
+    xt8 = torch.empty(n, h // 2, w // 2, 4, 8, device="cuda")
+    ad, bd = a.cuda(), b.cuda()                      # kept alive across the raw-pointer call
+    check(lib().rrin_warp_pack(flow4.data_ptr(), res4.data_ptr(), ad.data_ptr(), bd.data_ptr(), coef.data_ptr(), n, 1, h, w,
+                               m16.data_ptr(), xt8.data_ptr(), G.stream()))
+    xt = G.from_s2d(xt8).cpu()
+    with torch.no_grad():
+        y1, y2 = warp(ad, (ft0 + res[:, :2]).cuda()).cpu(), warp(bd, (ft1 + res[:, 2:4]).cuda()).cpu()
+    assert torch.equal(xt[:, :3], y1) and torch.equal(xt[:, 3:6], y2)
+
+
+def test_warp_rejects_what_the_reference_rejects():
+    from rrin_b200 import warp
+    img = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        warp(img, torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
+        warp(img.cuda(), torch.zeros(1, 2, 8, 10).cuda())
+    with pytest.raises(RuntimeError, match="inference only"):
+        warp(img.cuda().requires_grad_(), torch.zeros(1, 2, 8, 8).cuda())
+    assert warp(torch.empty(0, 3, 8, 8).cuda(), torch.empty(0, 2, 8, 8).cuda()).shape == (0, 3, 8, 8)

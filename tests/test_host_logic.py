@@ -47,6 +47,9 @@ def test_net_accepts_optional_level_and_rejects_cpu_inputs():
     x = torch.rand(1, 3, 32, 32)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(x, x, 0.5)
+    from rrin_b200 import warp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        warp(x, torch.zeros(1, 2, 32, 32))
 
 
 def test_engine_create_rejects_bad_shapes_without_gpu():
@@ -88,8 +91,8 @@ def test_conv_config_table_is_consistent():
 
 
 def test_dropin_module_is_importable_as_model():
-    code = ("import sys; sys.path[:0] = [%r, %r]; from model import Net; import rrin_b200; "
-            "assert Net is rrin_b200.Net; n = Net(); print(len(n.state_dict()))" % (os.path.join(ROOT, "dropin"), ROOT))
+    code = ("import sys; sys.path[:0] = [%r, %r]; from model import Net, warp; import rrin_b200; "
+            "assert Net is rrin_b200.Net and warp is rrin_b200.warp; n = Net(); print(len(n.state_dict()))" % (os.path.join(ROOT, "dropin"), ROOT))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == "162"

@@ -87,3 +87,15 @@ def test_zero_flow_is_not_identity():
     assert (out - img).abs().max() > 0.1
     ref = rrin_numpy.warp(img.numpy(), np.zeros((1, 2, 16, 16), np.float32))
     assert np.abs(out.numpy() - ref).max() < 1e-6
+
+
+def test_oracle_warp_equals_reference_warp(golden_dir):
+    """``oracle.rrin_oracle.warp`` against the unmodified reference's ``warp`` (model.py:8-21; oracle/make_golden_warp.py):
+    bit-identical, NaN positions included."""
+    d = np.load(os.path.join(golden_dir, "warp_cases.npz"))
+    names = sorted({k.split("/")[0] for k in d.files})
+    assert len(names) == 4
+    for name in names:
+        img, flow, ref = (torch.from_numpy(d[f"{name}/{k}"]) for k in ("img", "flow", "out"))
+        y = O.warp(img, flow)
+        np.testing.assert_array_equal(y.numpy(), ref.numpy())
