@@ -27,6 +27,8 @@ LAUNCHES = {
     46: ("conv3x3_tma#44<KCS64,KB32,NT16,MSUB2> +glue", "refine_flow.last (32->4) + fused residue add, both backward warps, Mask head packing (model.py:44-50)", (32 * 2 + 16 + 24 + 32 + 32) * P, 16 * 1024),      # frames counted once; the staged windows re-read their 8-pixel halo (mostly L2 hits)
     67: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue (blend)", "Mask.last (32->2) + fused sigmoid, blend, final head packing (model.py:52-55,61)", (32 * 2 + 32 + 24 + 16 + 32) * P, 16 * 1024),
     88: ("conv3x3_tma#37<KCS64,KB32,NT16,MSUB2> +glue (clamp)", "final.last (32->3) + fused residue add, clamp, NCHW store (model.py:62-63)", (32 * 2 + 16 + 12) * P, 16 * 1024),
+    17: ("conv3x3_tma#17<KCS64,KB64,NT128,MSUB3> fold", "Flow.up_path.2.up.1 (weight-folded bilinear x2 + 128->64, level 2 -> level 1, scatter stores)", 128 * 2 * P / 16 + 64 * 2 * P / 4, 9 * 128 * 256 * 2),
+    21: ("conv3x3_tma#18<KCS64,KB64,NT128,MSUB3> fold", "Flow.up_path.3.up.1 (weight-folded bilinear x2 + 64->32, level 1 -> level 0)", 64 * 2 * P / 4 + 32 * 2 * P, 9 * 64 * 128 * 2),
     11: ("conv3x3_tma#20<KCS64,KB64,NT128,MSUB2> up", "Flow.up_path.0.up.1 (bilinear x2 + 512->256, level 3)", (512 * 2 / 4 + 256 * 2) * P / 64, 9 * 512 * 256 * 2),
 }
 
