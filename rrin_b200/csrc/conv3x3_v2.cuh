@@ -51,6 +51,10 @@
 #ifndef RRIN_SCATTER_EARLY
 #define RRIN_SCATTER_EARLY 1
 #endif
+// ... -DRRIN_TAIL_FULL_WAIT=1: the epilogue warps wait for their last tensor store's global write before the CTA exits
+#ifndef RRIN_TAIL_FULL_WAIT
+#define RRIN_TAIL_FULL_WAIT 0
+#endif
 
 namespace rrin {
 
@@ -898,7 +902,10 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
             slot0 = (slot0 + t.m) % SLQ;
             seq += t.m;
         }
-        if (ETMA && lane == 0) bulk_wait_group<0>();                   // all tensor stores of this warp have landed
+        // The staging buffer must outlive the tensor stores' shared-memory reads, nothing more: their global writes are complete and
+        // visible when the grid is (what the next kernel's griddepcontrol.wait / stream order waits for), so the CTA's exit does not
+        // have to sit out the last store's write latency.
+        if (ETMA && lane == 0) { if (RRIN_TAIL_FULL_WAIT) bulk_wait_group<0>(); else bulk_wait_group_read<0>(); }
         if (prof && threadIdx.x == 0) { pprof[8] = twf; pprof[9] = clock64() - t00; }
         if (pprof && warp == 4 * EW - 4 && lane == 0) pprof[16 + 4 * blockIdx.x + 2] = clock64() - t_begin;                       // last epilogue group done
     }
