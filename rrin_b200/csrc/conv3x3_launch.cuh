@@ -17,7 +17,7 @@
 // 19 : < 64, 64, 128, 3, 2,  6, TAPS9, 0, 1, 2, 2>  levels >= 2 plain / cat on CTA PAIRS (cta_group::2, M = 256): half of every
 //                                                    weight block per CTA
 // 20 : < 64, 64, 128, 2, 2,  4, TAPS9, 0, 1, 2, 1, XF>  exact bilinear x2 source (up.1 convs of levels >= 2): TMA-staged raw coarse
-//                                                    tile + four transform warps
+//                                                    tile + eight transform warps
 // 21 : < 32, 32,  64, 4, 3,  9, TAPS9, 1, 1, 1, 1>     level-1 block.0 on the pooled 32-channel level-0 tensor: 64-byte pixel rows
 //                                                    (TMA SWIZZLE_64B boxes, 64-byte-swizzle A descriptors), weights resident
 // 22 : < 64, 64,  64, 4, 2,  8, TAPS9, 0, 1, 2, 2>     level 1 on CTA pairs (experimental, RRIN_L1_PAIR=1): M = 256, each CTA holds 32 of the 64

@@ -27,8 +27,8 @@
 //
 // Warp roles (1 CTA / SM, persistent): 4*EW epilogue warps (EW groups, one warp per TMEM lane quadrant), then one
 // warp each for MMA issue (a single elected thread), weight blocks (cp.async.bulk) and activation halo tiles
-// (cp.async.bulk.tensor), then -- XF only -- four transform warps, then -- NS = 2 only -- the second tile stream's MMA
-// warp.  224 / 352 / 384 / 480 threads.
+// (cp.async.bulk.tensor), then -- XF only -- eight transform warps, then -- NS = 2 only -- the second tile stream's MMA
+// warp.  224 / 352 / 384 / 608 threads.
 //
 // Round-2 variants of the same kernel (template parameters, see ConvCfgV2 and conv3x3_launch.cuh):
 //   NS = 2  two tile streams per CTA: two MMA-issuing warps, each with half of the stages / accumulator slots and its own
@@ -105,8 +105,15 @@ struct ConvParamsV2 {
 #endif
 };
 
-// EW epilogue groups of 4 warps + MMA, weights, activations (+ 4 transform warps when the A operand is computed: XF)
-constexpr int v2_threads(int ew, int xf = 0, int ns = 1) { return (4 * ew + 3 + 4 * xf + (ns - 1)) * 32; }
+// EW epilogue groups of 4 warps + MMA, weights, activations (+ kXfWarps transform warps when the A operand is computed: XF)
+// Transform warps of the XF configs.  A stage's transform (81 cells x 8 channel chunks: 4 shared loads, 4 interpolations, 4 shared stores
+// each) on four warps takes about as long as the stage's MMAs; eight warps (608 threads, 96 registers) take the exact-upsample
+// convs from 1.51 to 1.38 ms per step, twelve (80 registers, spills) give it back.  (A/B builds: -DRRIN_XF_WARPS=4)
+#ifndef RRIN_XF_WARPS
+#define RRIN_XF_WARPS 8
+#endif
+constexpr int kXfWarps = RRIN_XF_WARPS;
+constexpr int v2_threads(int ew, int xf = 0, int ns = 1) { return (4 * ew + 3 + kXfWarps * xf + (ns - 1)) * 32; }
 
 // KCS  : stored channels per K stage = channels per TMA box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte rows,
 //        SWIZZLE_64B: the pooled level-0 tensor)
@@ -274,8 +281,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;       // CTA pair: rank 0 is the leader (issues the MMAs)
     constexpr int N_ENT = C::N_ENT;
     constexpr int W_MMA = 4 * EW, W_B = 4 * EW + 1, W_A = 4 * EW + 2;   // warp roles after the epilogue groups
-    constexpr int W_X = 4 * EW + 3;                                      // XF: four transform warps W_X .. W_X+3
-    constexpr int W_MMA1 = 4 * EW + 3 + 4 * XF;                          // NS = 2: the second stream's MMA warp
+    constexpr int W_X = 4 * EW + 3;                                      // XF: transform warps W_X .. W_X+kXfWarps-1
+    constexpr int W_MMA1 = 4 * EW + 3 + kXfWarps * XF;                          // NS = 2: the second stream's MMA warp
     constexpr int SAQ = C::SAQ, SLQ = C::SLQ, SBQ = C::SBQ, EWQ = C::EWQ;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t s_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B tiles want 1024-byte alignment
@@ -313,8 +320,8 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
 
     // ---------------- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), XF ? 128 : 1); mbar_init(a_empty(i), 1); }      // XF: the transform threads fill A
-        for (int i = 0; i < C::RAW_SLOTS; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128); }
+        for (int i = 0; i < SA; ++i) { mbar_init(a_full(i), XF ? kXfWarps * 32 : 1); mbar_init(a_empty(i), 1); }      // XF: the transform threads fill A
+        for (int i = 0; i < C::RAW_SLOTS; ++i) { mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), kXfWarps * 32); }
         for (int i = 0; i < SB; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < C::SLOTS; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), CG * kEpiWarps * 32); }   // both CTAs' epilogues
         mbar_init(w_ready, CG);
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                 // so every output is bit-identical to the per-pixel formulation (a clamped-away tap has weight 0).
                 constexpr int CXN = C::PW / 2, CELLS = ((kTileH + 2) / 2) * CXN;
 #pragma unroll 1
-                for (int cell = px0; cell < CELLS; cell += 16) {
+                for (int cell = px0; cell < CELLS; cell += kXfWarps * 4) {
                     const int cyl = cell / CXN, cxl = cell - cyl * CXN;
                     const int ra = min(max(cy0 + cyl, 0), sh - 1) - cy0, rb = min(max(cy0 + cyl + 1, 0), sh - 1) - cy0;
                     const int ca = min(max(cx0 + cxl, 0), sw - 1) - cx0, cb = min(max(cx0 + cxl + 1, 0), sw - 1) - cx0;
