@@ -70,7 +70,7 @@ struct ConvParams {
 };
 
 constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 8;
+constexpr int kProdWarps = 8;          // (12 / 16 producer warps: border rings 0.31 -> 0.30 ms per step, within noise)
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kConvThreads = (kEpiWarps + 2 + kProdWarps) * 32;
 constexpr int kTileH = 16;
