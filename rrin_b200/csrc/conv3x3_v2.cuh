@@ -108,7 +108,7 @@ struct ConvParamsV2 {
 // EW epilogue groups of 4 warps + MMA, weights, activations (+ kXfWarps transform warps when the A operand is computed: XF)
 // Transform warps of the XF configs.  A stage's transform (81 cells x 8 channel chunks: 4 shared loads, 4 interpolations, 4 shared stores
 // each) on four warps takes about as long as the stage's MMAs; eight warps (608 threads, 96 registers) take the exact-upsample
-// convs from 1.51 to 1.38 ms per step, twelve (80 registers, spills) give it back.  (A/B builds: -DRRIN_XF_WARPS=4)
+// convs from 1.51 to 1.38 ms per step; six / seven warps measured 1.47 / 1.41, twelve (80 registers, spills) 1.48.  (A/B builds: -DRRIN_XF_WARPS=4)
 #ifndef RRIN_XF_WARPS
 #define RRIN_XF_WARPS 8
 #endif
