@@ -66,6 +66,26 @@ def test_engine_create_rejects_bad_shapes_without_gpu():
     l.rrin_engine_destroy(h)
 
 
+def test_c99_consumer_links_and_runs(tmp_path):
+    """include/rrin_b200.h is plain C (no C++ / torch types): a C99 program compiled with -pedantic links the library and
+    drives the host-side entry points (conv table, engine planning, error codes) -- the maintainer-side binding of
+    INTEGRATION.md section 1 in its smallest form."""
+    import shutil
+    from rrin_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    _lib.lib()                                                          # builds the library if it is missing
+    libdir = os.path.join(ROOT, "rrin_b200")
+    exe = str(tmp_path / "consumer")
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "cabi", "consumer.c"), "-o", exe, "-L", libdir, "-l:librrin_b200.so",
+                         "-Wl,-rpath," + libdir], capture_output=True, text=True, timeout=120)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "convs 81 launches 90" in run.stdout, run.stdout
+
+
 def test_conv_config_table_is_consistent():
     """Tile configurations behind rrin_conv3x3 (host-side queries only): ids, K-stage geometry, packed sizes."""
     import ctypes as C
