@@ -144,3 +144,46 @@ def test_public_warp_and_frame_io_respect_their_buffers():
         results.append((f.clone(), u8.clone()))
     assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
     assert torch.equal(results[0][1], src)                       # pad -> ToTensor -> to_pil -> crop is the identity on bytes
+
+
+def test_batch_of_36_pairs_crosses_2_31_elements_per_tensor():
+    """Index arithmetic past 32 bits: 36 pairs of 1088 x 1920 make every level-0 tensor 2.4e9 elements (4.8 GB) and the
+    workspace 34 GB of the 180 GB.  The K-sum order of a pixel depends on its row band and n-tile only (conv3x3_v2.cuh,
+    `rot_of`), so each sample of the large batch must equal the single-pair call bit for bit -- checked on the first, a middle
+    and the last sample (the last one lives entirely above the 2^31-element mark)."""
+    net = _net()
+    n, h, w = 36, 1088, 1920
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.rand(n, 3, h, w, device="cuda", generator=g)
+    b = (a + 0.05 * torch.rand(n, 3, h, w, device="cuda", generator=g)).clamp_(0, 1)
+    with torch.no_grad():
+        y = net(a, b, t=0.5)
+        torch.cuda.synchronize()
+        assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+        for k in (0, 17, 35):
+            yk = net(a[k:k + 1], b[k:k + 1], t=0.5)
+            assert torch.equal(y[k:k + 1], yk), f"sample {k} of the 36-pair batch differs from its single-pair call"
+    net._engines.clear()                     # give the 34 GB workspace back before the next test
+
+
+def test_8k_frame_corner_matches_its_crop():
+    """One 4320 x 7680 pair: level-0 tensors of 2.1 GB (byte offsets past 2^31), 270 x 480 level-0 tiles.  The far corner of the
+    result is compared with a forward over the bottom-right 1024 x 1024 crop, away from the crop's inner edges (the receptive
+    field of the four U-Nets in sequence stays below 256 px at these flow magnitudes); both runs round their 16-bit
+    activations independently, hence the 1e-3 bar of the parity tests rather than equality."""
+    net = _net()
+    h, w, c = 4320, 7680, 1024
+    g = torch.Generator(device="cuda").manual_seed(12)
+    lo = torch.rand(1, 3, h // 16, w // 16, device="cuda", generator=g)
+    a = torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=False)
+    b = torch.roll(a, shifts=(1, 2), dims=(2, 3)).contiguous()
+    with torch.no_grad():
+        y = net(a, b, t=0.5)
+        yc = net(a[:, :, h - c:, w - c:].contiguous(), b[:, :, h - c:, w - c:].contiguous(), t=0.5)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    m = 320                                                       # margin from the crop's inner (top / left) edges
+    err = (y[:, :, h - c + m:, w - c + m:] - yc[:, :, m:, m:]).abs().max().item()
+    print(f"8K corner vs crop: max-abs {err:.3e}")
+    assert err <= 1e-3, err
+    net._engines.clear()
