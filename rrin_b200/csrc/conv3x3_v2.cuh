@@ -113,9 +113,6 @@ struct ConvParamsV2 {
 #define RRIN_XF_WARPS 8
 #endif
 constexpr int kXfWarps = RRIN_XF_WARPS;
-#ifndef RRIN_SKEW_FIRST
-#define RRIN_SKEW_FIRST 0
-#endif
 constexpr int v2_threads(int ew, int xf = 0, int ns = 1) { return (4 * ew + 3 + kXfWarps * xf + (ns - 1)) * 32; }
 
 // KCS  : stored channels per K stage = channels per TMA box: 64 (128-byte pixel rows, SWIZZLE_128B) or 32 (64-byte rows,
@@ -511,31 +508,32 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                 constexpr int PAR = decltype(par_c)::value, M = decltype(m_c)::value;
                 const uint32_t a_st = a_lo0 + ((s_a + stage * C::A_STAGE) >> 4);
                 const uint32_t b_st = RES ? (uint32_t)((st * C::B_STAGE) >> 4) : 0u;
-                // weight block of entry e: resident -> its fixed offset; streamed -> the next ring slot (waited for unless already seen
-                // complete; the block after it is polled while this entry's MMAs issue)
-                auto acquire = [&](const int e, int& slot) -> uint32_t {
-                    const int hf = C::half_of(PAR, e);
-                    if (RES) { slot = 0; return (hf ? b_lo0h : b_lo0) + b_st + (uint32_t)(C::res_off(PAR, e) >> 4); }
-                    slot = q * SBQ + cnt % SBQ;
-                    if (!b_rdy) {
-                        const long long c0 = prof ? clock64() : 0;
-                        mbar_wait(b_full(slot), (cnt / SBQ) & 1);
-                        if (prof) twb += clock64() - c0;
-                    }
-                    tc_fence_after();
-                    ++cnt;
-                    b_rdy = mbar_test(b_full(q * SBQ + cnt % SBQ), (cnt / SBQ) & 1);
-                    return (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
-                };
-                // the MMAs of entry e for sub-tiles [j0, j1)
-                auto issue = [&](const int e, const uint32_t b_e, const int j0, const int j1) {
+#pragma unroll
+                for (int e = 0; e < N_ENT; ++e) {
                     const int hf = C::half_of(PAR, e);                       // 0 full, 1 lower 64 columns, 2 upper
+                    int slot = 0;
+                    uint32_t b_e;
+                    if (RES) {
+                        b_e = (hf ? b_lo0h : b_lo0) + b_st + (uint32_t)(C::res_off(PAR, e) >> 4);
+                    } else {
+                        slot = q * SBQ + cnt % SBQ;
+                        if (!b_rdy) {
+                            const long long c0 = prof ? clock64() : 0;
+                            mbar_wait(b_full(slot), (cnt / SBQ) & 1);
+                            if (prof) twb += clock64() - c0;
+                        }
+                        tc_fence_after();
+                        ++cnt;
+                        b_rdy = mbar_test(b_full(q * SBQ + cnt % SBQ), (cnt / SBQ) & 1);  // next block: polled while this entry's MMAs issue
+                        b_e = (hf ? b_lo0h : b_lo0) + (uint32_t)((slot * C::B_BLOCK) >> 4);
+                    }
                     const uint32_t a_e = a_st + C::ent_off(PAR, e);
                     const uint32_t b_ks = hf ? 2 * (64 / CG) : 2 * (NT / CG);  // descriptor step per K=16: two core-matrix planes
                     const uint32_t id = hf ? idesc_h : idesc;
                     const uint32_t dcol = (hf == 2) ? 64 : 0;
+                    const long long cm0 = prof ? clock64() : 0;
 #pragma unroll
-                    for (int j = j0; j < j1; ++j) {
+                    for (int j = 0; j < M; ++j) {
                         const int ts = q * SLQ + (slot0 + j) % SLQ;           // accumulator slots (of this stream) are used round-robin
                         if (e == 0 && first_stage) {    // first write into this slot: the epilogue must have drained its previous use
                             const long long c0 = prof ? clock64() : 0;
@@ -549,33 +547,6 @@ __global__ void __launch_bounds__(v2_threads(EW, XF, NS), 1) conv3x3_tma_kernel(
                                 mma(tmem_base + ts * NT + dcol, a_e + j * (C::ROWB / 2) + s * 2, a_hi, b_e + s * b_ks, b_hi, id,
                                     (e | s) != 0 || !first_stage);
                     }
-                };
-                // A tile that takes more than half of the accumulator slots starts while the epilogue still drains slots of the
-                // previous tile: only its first sub-tile's slot is free.  RRIN_SKEW_FIRST: the first kSkew entries of such a tile
-                // issue for sub-tile 0 alone (kSkew weight blocks stay held in the ring), then catch up on the other sub-tiles --
-                // kSkew * KB / 16 MMAs of cover for the drain instead of KB / 16.  Every accumulator still sums its entries in the
-                // same order: results are bit-identical.
-                constexpr int kSkew = 3;
-                constexpr bool SKEW = RRIN_SKEW_FIRST && !RES && SCHED == 0 && CG == 1 && NS == 1 && M >= 2 && 2 * MSUB > C::SLOTS && SB > kSkew;
-                int e_first = 0;
-                if constexpr (SKEW) {
-                    if (first_stage) {
-                        int slots[kSkew];
-                        uint32_t b_es[kSkew];
-#pragma unroll
-                        for (int e = 0; e < kSkew; ++e) { b_es[e] = acquire(e, slots[e]); issue(e, b_es[e], 0, 1); }
-#pragma unroll
-                        for (int e = 0; e < kSkew; ++e) { issue(e, b_es[e], 1, M); commit(b_empty(slots[e])); }
-                        e_first = kSkew;
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < N_ENT; ++e) {
-                    if (SKEW && e < e_first) continue;
-                    int slot;
-                    const uint32_t b_e = acquire(e, slot);
-                    const long long cm0 = prof ? clock64() : 0;
-                    issue(e, b_e, 0, M);
                     const long long cm1 = prof ? clock64() : 0;
                     if (!RES) commit(b_empty(slot));
                     if (prof) { tmma += cm1 - cm0; tcom += clock64() - cm1; }
