@@ -13,11 +13,15 @@ ffmpeg encode: it finds the checkpoint the reference would pick (``models/<name>
 
 The pixel path is ``ClipInterpolator(uint8=True)``: frames cross PCIe once, as the bytes PIL decoded; edge pad + ToTensor
 and mul(255).byte() + crop run on the device; for ``sf > 1`` the Flow U-Net runs once per pair.  Decoding, the file copies
-and PNG encoding stay on the host (PIL, a small thread pool like utils.py:36-37).  GPU video decode / encode
+and PNG encoding stay on the host (PIL in thread pools, like the reference's DataLoader workers and Writer threads,
+convert.py:94-97, utils.py:36-37): the next chunk of frames is decoded while the current one is on the GPU, and the writers
+lag at most one chunk behind (bounded memory).  Host PNG encoding (zlib, ~0.1-1 s per 1080p frame and thread) is what bounds
+this entry point, as it bounds the reference's -- the forward pass runs two orders of magnitude faster.  GPU video decode / encode
  is out of scope: there is no ffmpeg / NVDEC / NVENC in the image.
 """
 from __future__ import annotations
 
+import collections
 import os
 import shutil
 from concurrent.futures import ThreadPoolExecutor
@@ -53,11 +57,12 @@ def list_frames(src_dir: str, order: str = "sorted") -> List[str]:
 
 def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str] = None, models_dir: str = "models",
                    net=None, batch: int = 2, resume: bool = False, order: str = "sorted", chunk_pairs: int = 64,
-                   io_workers: int = 4, device: Optional[torch.device] = None, rank: int = 0, world: int = 1) -> List[str]:
+                   io_workers: Optional[int] = None, device: Optional[torch.device] = None, rank: int = 0, world: int = 1) -> List[str]:
     """Interpolates ``sf`` frames between consecutive images of ``src_dir`` into ``dst_dir``; returns the written paths in
     output order.  ``net``: a ready ``rrin_b200.Net`` (cuda, eval); otherwise the checkpoint ``models_dir/<model_name>*`` is
     loaded like convert.py:98-111.  ``resume=True`` continues like convert.py:46-53 (the pair index is recomputed from the
-    number of files already in ``dst_dir``).
+    number of files already in ``dst_dir``).  ``io_workers``: host threads that encode / copy the output files (default: the
+    CPU count, at most 16); a quarter as many decode the next chunk of ``chunk_pairs`` frames ahead of the GPU.
 
     ``rank`` / ``world``: multi-GPU conversion (SURVEY.md 8(e)) -- one process per GPU, each calls this function with its rank;
     rank r interpolates the contiguous pair range ``sharding.pair_range(n_frames, r, world)`` and writes exactly the files of
@@ -106,8 +111,11 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
     rio.padded_shape(h0, w0)                                          # raises like the reference when the padded size cannot run
     pipe = ClipInterpolator(net, h0, w0, batch=batch, sf=sf, device=dev, uint8=True, channels=ch)
     written: List[str] = []
-    pool = ThreadPoolExecutor(max_workers=max(1, io_workers))
-    jobs = []
+    if io_workers is None:
+        io_workers = min(16, os.cpu_count() or 4)
+    pool = ThreadPoolExecutor(max_workers=max(1, io_workers))                 # writers: PNG encode + file copies
+    dec_pool = ThreadPoolExecutor(max_workers=max(1, io_workers // 4))        # readers: PNG decode of the next chunk
+    pending = collections.deque()                                             # write jobs in flight, oldest first
 
     def save_png(arr: np.ndarray, dest: str):
         from PIL import Image
@@ -118,29 +126,43 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
         written.append(p)
         return p
 
+    def drain(limit: int):
+        while len(pending) > limit:
+            pending.popleft().result()                                # re-raises a writer's exception here
+
+    def decode_ahead(lo: int, hi: int):
+        return [dec_pool.submit(_load_rgb, paths[i]) for i in range(lo, hi)]
+
     try:
         n_pairs = last_pair
         p0 = first_pair
         if img_count == 1 or world > 1:                               # convert.py:121-123: the original in front of the first pair
-            jobs.append(pool.submit(shutil.copy, paths[p0], out_path(img_count, exts[p0])))
+            pending.append(pool.submit(shutil.copy, paths[p0], out_path(img_count, exts[p0])))
         carry = first
+        ahead = decode_ahead(p0 + 1, min(n_pairs, p0 + chunk_pairs) + 1)
         while p0 < n_pairs:
             p1 = min(n_pairs, p0 + chunk_pairs)
-            frames = [carry] + [_load_rgb(paths[i]) for i in range(p0 + 1, p1 + 1)]
+            frames = [carry] + [f.result() for f in ahead]
+            ahead = decode_ahead(p1 + 1, min(n_pairs, p1 + chunk_pairs) + 1)   # overlaps this chunk's forward passes
             for i, f in enumerate(frames):
                 if f.shape != (h0, w0, ch):
                     raise RuntimeError(f"{paths[p0 + i]}: frame is {f.shape}, expected {(h0, w0, ch)} like the first frame")
-            clip = torch.from_numpy(np.stack(frames)).pin_memory()
+            clip = torch.from_numpy(np.stack(frames))
+            if torch.cuda.is_available():
+                clip = clip.pin_memory()
             outs = pipe.run(clip).numpy()                             # [(p1-p0)*sf, h0, w0, 3] uint8, cropped like utils.py:56-57
             for k, p in enumerate(range(p0, p1)):
                 for i in range(1, sf + 1):                            # convert.py:127-135
-                    jobs.append(pool.submit(save_png, outs[k * sf + i - 1].copy(), out_path(img_count + i, exts[p])))
-                jobs.append(pool.submit(shutil.copy, paths[p + 1], out_path(img_count + sf + 1, exts[p + 1])))   # convert.py:136-139
+                    pending.append(pool.submit(save_png, outs[k * sf + i - 1].copy(), out_path(img_count + i, exts[p])))
+                pending.append(pool.submit(shutil.copy, paths[p + 1], out_path(img_count + sf + 1, exts[p + 1])))   # convert.py:136-139
                 img_count += sf + 1
             carry = frames[-1]
             p0 = p1
-        for j in jobs:
-            j.result()
+            drain(chunk_pairs * (sf + 1))                             # the writers lag at most one chunk behind the GPU
+        drain(0)
     finally:
+        for f in list(pending):
+            f.cancel()
+        dec_pool.shutdown(wait=True, cancel_futures=True)
         pool.shutdown(wait=True)
     return written

@@ -252,6 +252,77 @@ def test_checkpoint_lookup_and_load(tmp_path):
         rio.find_checkpoint(str(tmp_path), "absent")
 
 
+def test_convert_folder_host_logic_with_a_stand_in_pipeline(tmp_path, monkeypatch):
+    """convert_folder's host side on CPU (decode-ahead pool, bounded writer backlog, numbering, copies, resume, sharding,
+    error propagation) with ClipInterpolator replaced by a stand-in that averages neighbouring frames; the real pipeline is
+    compared file by file in tests/test_gpu_convert.py."""
+    import numpy as np
+    from PIL import Image
+    import rrin_b200.pipeline as pl
+    from rrin_b200 import convert_folder
+
+    class StandIn:
+        def __init__(self, net, h, w, batch=2, sf=1, device=None, uint8=False, channels=3):
+            assert uint8 and channels == 3
+            self.sf = sf
+
+        def run(self, clip):
+            f = clip.numpy().astype(np.float32)
+            outs = [((1 - k / (self.sf + 1)) * f[i] + k / (self.sf + 1) * f[i + 1]).astype(np.uint8)
+                    for i in range(len(f) - 1) for k in range(1, self.sf + 1)]
+            return torch.from_numpy(np.stack(outs))
+
+    monkeypatch.setattr(pl, "ClipInterpolator", StandIn)
+    net = torch.nn.Linear(1, 1)                                           # only .parameters() is touched when `net` is given
+    src = tmp_path / "frames"
+    src.mkdir()
+    rng = np.random.default_rng(1)
+    frames = [rng.integers(0, 256, (40, 32, 3), dtype=np.uint8) for _ in range(11)]
+    for i, a in enumerate(frames):
+        Image.fromarray(a, "RGB").save(src / f"f{i:03d}.png")
+    dev = torch.device("cpu")
+
+    def expect(i, k, sf):
+        return ((1 - k / (sf + 1)) * frames[i].astype(np.float32) + k / (sf + 1) * frames[i + 1]).astype(np.uint8)
+
+    for sf, chunk in ((1, 64), (2, 3), (3, 1)):                           # one chunk; several chunks with decode-ahead; chunk = pair
+        dst = tmp_path / f"out_sf{sf}"
+        written = convert_folder(str(src), str(dst), sf, net=net, device=dev, chunk_pairs=chunk, io_workers=3)
+        assert [os.path.basename(p) for p in written] == [f"{i:09d}.png" for i in range(1, 10 * (sf + 1) + 2)]
+        assert sorted(os.listdir(dst)) == [os.path.basename(p) for p in written]
+        for i in range(11):
+            name = f"{i * (sf + 1) + 1:09d}.png"
+            assert (dst / name).read_bytes() == (src / f"f{i:03d}.png").read_bytes()           # originals are file copies
+            if i < 10:
+                for k in range(1, sf + 1):
+                    got = np.asarray(Image.open(dst / f"{i * (sf + 1) + 1 + k:09d}.png"))
+                    assert np.array_equal(got, expect(i, k, sf)), (sf, i, k)
+    # two ranks write disjoint files whose union is the single-process output
+    dst2 = tmp_path / "out_ranks"
+    w0 = convert_folder(str(src), str(dst2), 2, net=net, device=dev, rank=0, world=2, chunk_pairs=2)
+    w1 = convert_folder(str(src), str(dst2), 2, net=net, device=dev, rank=1, world=2, chunk_pairs=2)
+    assert {os.path.basename(p) for p in set(w0) & set(w1)} == {"000000016.png"}   # the original between the shards: the same copy twice
+    ref = tmp_path / "out_sf2"
+    assert sorted(os.listdir(dst2)) == sorted(os.listdir(ref))
+    for n in os.listdir(ref):
+        assert (dst2 / n).read_bytes() == (ref / n).read_bytes(), n
+    # a non-empty destination is refused like convert.py:57-59; resume continues where the count of files says
+    with pytest.raises(RuntimeError, match="already in use"):
+        convert_folder(str(src), str(ref), 2, net=net, device=dev)
+    part = tmp_path / "out_part"
+    part.mkdir()
+    for n in sorted(os.listdir(ref))[:10]:                                # 10 files = 3 complete pairs + the 4th pair's first frame
+        (part / n).write_bytes((ref / n).read_bytes())
+    convert_folder(str(src), str(part), 2, net=net, device=dev, resume=True, chunk_pairs=4)
+    assert sorted(os.listdir(part)) == sorted(os.listdir(ref))
+    for n in os.listdir(ref):
+        assert np.array_equal(np.asarray(Image.open(part / n)), np.asarray(Image.open(ref / n))), n
+    # a frame of another size stops the conversion with the file's name (decoded ahead on a worker thread)
+    Image.fromarray(rng.integers(0, 256, (24, 32, 3), dtype=np.uint8), "RGB").save(src / "f005.png")
+    with pytest.raises(RuntimeError, match="f005.png"):
+        convert_folder(str(src), str(tmp_path / "out_bad"), 1, net=net, device=dev, chunk_pairs=2)
+
+
 # ----------------------------------------------------------------------------- the reference's own caller on the drop-in
 _CONVERT_SCRIPT = r"""
 import os, sys, argparse
