@@ -57,12 +57,15 @@ def list_frames(src_dir: str, order: str = "sorted") -> List[str]:
 
 def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str] = None, models_dir: str = "models",
                    net=None, batch: int = 2, resume: bool = False, order: str = "sorted", chunk_pairs: int = 64,
-                   io_workers: Optional[int] = None, device: Optional[torch.device] = None, rank: int = 0, world: int = 1) -> List[str]:
+                   io_workers: Optional[int] = None, device: Optional[torch.device] = None, rank: int = 0, world: int = 1,
+                   png_compress_level: Optional[int] = None) -> List[str]:
     """Interpolates ``sf`` frames between consecutive images of ``src_dir`` into ``dst_dir``; returns the written paths in
     output order.  ``net``: a ready ``rrin_b200.Net`` (cuda, eval); otherwise the checkpoint ``models_dir/<model_name>*`` is
     loaded like convert.py:98-111.  ``resume=True`` continues like convert.py:46-53 (the pair index is recomputed from the
     number of files already in ``dst_dir``).  ``io_workers``: host threads that encode / copy the output files (default: the
     CPU count, at most 16); a quarter as many decode the next chunk of ``chunk_pairs`` frames ahead of the GPU.
+    ``png_compress_level``: zlib level for ``.png`` outputs; ``None`` = PIL's default (6), what the reference's
+    ``img.save`` (utils.py:58) uses -- level 1 encodes a 1080p frame 3.5x faster for 16 % larger files, same pixels.
 
     ``rank`` / ``world``: multi-GPU conversion (SURVEY.md 8(e)) -- one process per GPU, each calls this function with its rank;
     rank r interpolates the contiguous pair range ``sharding.pair_range(n_frames, r, world)`` and writes exactly the files of
@@ -119,7 +122,8 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
 
     def save_png(arr: np.ndarray, dest: str):
         from PIL import Image
-        Image.fromarray(arr, "RGB").save(dest)                        # utils.py:58 (to_pil_image gives mode RGB)
+        kw = {"compress_level": png_compress_level} if png_compress_level is not None and dest.lower().endswith(".png") else {}
+        Image.fromarray(arr, "RGB").save(dest, **kw)                  # utils.py:58 (to_pil_image gives mode RGB)
 
     def out_path(number: int, ext: str) -> str:
         p = os.path.join(dst_dir, f"{number:09d}{ext}")               # convert.py:122,135,138

@@ -297,6 +297,10 @@ def test_convert_folder_host_logic_with_a_stand_in_pipeline(tmp_path, monkeypatc
                 for k in range(1, sf + 1):
                     got = np.asarray(Image.open(dst / f"{i * (sf + 1) + 1 + k:09d}.png"))
                     assert np.array_equal(got, expect(i, k, sf)), (sf, i, k)
+    fast = tmp_path / "out_fast"
+    convert_folder(str(src), str(fast), 2, net=net, device=dev, png_compress_level=1)                  # same pixels, other zlib level
+    for n in os.listdir(fast):
+        assert np.array_equal(np.asarray(Image.open(fast / n)), np.asarray(Image.open(tmp_path / "out_sf2" / n))), n
     # two ranks write disjoint files whose union is the single-process output
     dst2 = tmp_path / "out_ranks"
     w0 = convert_folder(str(src), str(dst2), 2, net=net, device=dev, rank=0, world=2, chunk_pairs=2)
