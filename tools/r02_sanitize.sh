@@ -1,5 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over one small run of every launch class (tools/sanitize_step.py); run under gpurun.
+# NOTE: the round-2 GPU pool refuses compute-sanitizer ("closed on this pool"): there the same properties are covered by
+# tests/test_gpu_memory_safety.py (workspace poison, guard bands, >2^31-element tensors).  Kept for pools that allow it.
 # usage: tools/r02_sanitize.sh <tag> [tool ...]      (default tools: memcheck synccheck initcheck)
 tag=${1:-r02}; shift
 tools=${@:-memcheck synccheck initcheck}
