@@ -58,14 +58,17 @@ def list_frames(src_dir: str, order: str = "sorted") -> List[str]:
 def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str] = None, models_dir: str = "models",
                    net=None, batch: int = 2, resume: bool = False, order: str = "sorted", chunk_pairs: int = 64,
                    io_workers: Optional[int] = None, device: Optional[torch.device] = None, rank: int = 0, world: int = 1,
-                   png_compress_level: Optional[int] = None) -> List[str]:
+                   png_compress_level: Optional[int] = None, png_writer: str = "pil") -> List[str]:
     """Interpolates ``sf`` frames between consecutive images of ``src_dir`` into ``dst_dir``; returns the written paths in
     output order.  ``net``: a ready ``rrin_b200.Net`` (cuda, eval); otherwise the checkpoint ``models_dir/<model_name>*`` is
     loaded like convert.py:98-111.  ``resume=True`` continues like convert.py:46-53 (the pair index is recomputed from the
     number of files already in ``dst_dir``).  ``io_workers``: host threads that encode / copy the output files (default: the
-    CPU count, at most 16); a quarter as many decode the next chunk of ``chunk_pairs`` frames ahead of the GPU.
+    CPU count, at most 16); half as many decode the next chunk of ``chunk_pairs`` frames ahead of the GPU.
     ``png_compress_level``: zlib level for ``.png`` outputs; ``None`` = PIL's default (6), what the reference's
     ``img.save`` (utils.py:58) uses -- level 1 encodes a 1080p frame 3.5x faster for 16 % larger files, same pixels.
+    ``png_writer``: ``"pil"`` (default, the reference's encoder) or ``"fast"`` (``rrin_b200.fastpng``: one fixed Sub row filter +
+    one zlib call per frame, level 1 unless ``png_compress_level`` says otherwise; same pixels, another 2x less host time per
+    frame, 7x at level 0); non-PNG destinations always go through PIL.
 
     ``rank`` / ``world``: multi-GPU conversion (SURVEY.md 8(e)) -- one process per GPU, each calls this function with its rank;
     rank r interpolates the contiguous pair range ``sharding.pair_range(n_frames, r, world)`` and writes exactly the files of
@@ -117,10 +120,16 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
     if io_workers is None:
         io_workers = min(16, os.cpu_count() or 4)
     pool = ThreadPoolExecutor(max_workers=max(1, io_workers))                 # writers: PNG encode + file copies
-    dec_pool = ThreadPoolExecutor(max_workers=max(1, io_workers // 4))        # readers: PNG decode of the next chunk
+    dec_pool = ThreadPoolExecutor(max_workers=max(1, io_workers // 2))        # readers: PNG decode of the next chunk
     pending = collections.deque()                                             # write jobs in flight, oldest first
 
+    if png_writer not in ("pil", "fast"):
+        raise ValueError("png_writer must be 'pil' or 'fast'")
+
     def save_png(arr: np.ndarray, dest: str):
+        if png_writer == "fast" and dest.lower().endswith(".png"):
+            from .fastpng import write_png
+            return write_png(arr, dest, 1 if png_compress_level is None else png_compress_level)
         from PIL import Image
         kw = {"compress_level": png_compress_level} if png_compress_level is not None and dest.lower().endswith(".png") else {}
         Image.fromarray(arr, "RGB").save(dest, **kw)                  # utils.py:58 (to_pil_image gives mode RGB)
@@ -134,35 +143,54 @@ def convert_folder(src_dir: str, dst_dir: str, sf: int, model_name: Optional[str
         while len(pending) > limit:
             pending.popleft().result()                                # re-raises a writer's exception here
 
-    def decode_ahead(lo: int, hi: int):
-        return [dec_pool.submit(_load_rgb, paths[i]) for i in range(lo, hi)]
+    # Two pinned input and two pinned output staging buffers, used alternately by successive chunks: while chunk k is on the
+    # GPU the readers decode chunk k + 1 straight into the other input buffer, and the writers encode chunk k - 1 straight from
+    # the other output buffer (no per-chunk allocation, stacking or copies on the main thread).
+    cp = max(1, min(chunk_pairs, last_pair - first_pair))
+
+    def host_buf(*shape):
+        t = torch.empty(shape, dtype=torch.uint8)
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    in_bufs = [host_buf(cp + 1, h0, w0, ch) for _ in range(2)]
+    out_bufs = [host_buf(cp * sf, h0, w0, 3) for _ in range(2)]
+    in_np = [b.numpy() for b in in_bufs]
+
+    def decode_into(which: int, slot: int, path: str):
+        f = _load_rgb(path)
+        if f.shape != (h0, w0, ch):
+            raise RuntimeError(f"{path}: frame is {f.shape}, expected {(h0, w0, ch)} like the first frame")
+        in_np[which][slot] = f
+
+    def decode_ahead(which: int, lo: int, hi: int):
+        return [dec_pool.submit(decode_into, which, i - lo + 1, paths[i]) for i in range(lo, hi)]
 
     try:
         n_pairs = last_pair
         p0 = first_pair
         if img_count == 1 or world > 1:                               # convert.py:121-123: the original in front of the first pair
             pending.append(pool.submit(shutil.copy, paths[p0], out_path(img_count, exts[p0])))
-        carry = first
-        ahead = decode_ahead(p0 + 1, min(n_pairs, p0 + chunk_pairs) + 1)
+        in_np[0][0] = first
+        ahead = decode_ahead(0, p0 + 1, min(n_pairs, p0 + cp) + 1)
+        k = 0
         while p0 < n_pairs:
-            p1 = min(n_pairs, p0 + chunk_pairs)
-            frames = [carry] + [f.result() for f in ahead]
-            ahead = decode_ahead(p1 + 1, min(n_pairs, p1 + chunk_pairs) + 1)   # overlaps this chunk's forward passes
-            for i, f in enumerate(frames):
-                if f.shape != (h0, w0, ch):
-                    raise RuntimeError(f"{paths[p0 + i]}: frame is {f.shape}, expected {(h0, w0, ch)} like the first frame")
-            clip = torch.from_numpy(np.stack(frames))
-            if torch.cuda.is_available():
-                clip = clip.pin_memory()
-            outs = pipe.run(clip).numpy()                             # [(p1-p0)*sf, h0, w0, 3] uint8, cropped like utils.py:56-57
-            for k, p in enumerate(range(p0, p1)):
+            p1 = min(n_pairs, p0 + cp)
+            cur, nxt = k & 1, (k & 1) ^ 1
+            for f in ahead:
+                f.result()                                            # re-raises a reader's exception (wrong size / mode) here
+            in_np[nxt][0] = in_np[cur][p1 - p0]                       # the last frame of this chunk opens the next one
+            ahead = decode_ahead(nxt, p1 + 1, min(n_pairs, p1 + cp) + 1)   # overlaps this chunk's forward passes
+            outs = pipe.run(in_bufs[cur][:p1 - p0 + 1], out_host=out_bufs[cur][:(p1 - p0) * sf]).numpy()
+            # [(p1-p0)*sf, h0, w0, 3] uint8, cropped like utils.py:56-57; the writers read the staging buffer in place: it is
+            # reused two chunks later, after drain() below has seen these jobs finish
+            for j, p in enumerate(range(p0, p1)):
                 for i in range(1, sf + 1):                            # convert.py:127-135
-                    pending.append(pool.submit(save_png, outs[k * sf + i - 1].copy(), out_path(img_count + i, exts[p])))
+                    pending.append(pool.submit(save_png, outs[j * sf + i - 1], out_path(img_count + i, exts[p])))
                 pending.append(pool.submit(shutil.copy, paths[p + 1], out_path(img_count + sf + 1, exts[p + 1])))   # convert.py:136-139
                 img_count += sf + 1
-            carry = frames[-1]
             p0 = p1
-            drain(chunk_pairs * (sf + 1))                             # the writers lag at most one chunk behind the GPU
+            k += 1
+            drain(cp * (sf + 1))                                      # at most this chunk's writes stay in flight
         drain(0)
     finally:
         for f in list(pending):

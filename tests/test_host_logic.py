@@ -252,6 +252,33 @@ def test_checkpoint_lookup_and_load(tmp_path):
         rio.find_checkpoint(str(tmp_path), "absent")
 
 
+def test_fastpng_round_trips_through_pil():
+    """Every (level, row filter) of the lean PNG writer decodes with PIL to the bytes that went in; bad inputs are refused."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from rrin_b200 import fastpng
+    rng = np.random.default_rng(4)
+    ramp = (np.add.outer(np.arange(37), np.arange(53))[:, :, None] * np.array([3, 5, 7])).astype(np.uint8)      # wraps past 255
+    for img in (rng.integers(0, 256, (37, 53, 3), dtype=np.uint8), ramp, np.zeros((1, 1, 3), np.uint8),
+                rng.integers(0, 256, (64, 48, 3), dtype=np.uint8)[::2, ::3]):                                   # a non-contiguous view
+        for level in (0, 1, 6, 9):
+            for flt in ("none", "sub", "up"):
+                data = fastpng.encode_png(img, level, flt)
+                back = Image.open(io.BytesIO(data))
+                assert back.mode == "RGB" and back.size == (img.shape[1], img.shape[0])
+                assert np.array_equal(np.asarray(back), img), (img.shape, level, flt)
+    smooth = np.repeat(np.repeat(rng.integers(0, 256, (8, 8, 3), dtype=np.uint8), 16, 0), 16, 1)
+    assert len(fastpng.encode_png(smooth, 1, "sub")) < len(fastpng.encode_png(smooth, 0)) // 10
+    for bad in (np.zeros((4, 4), np.uint8), np.zeros((4, 4, 4), np.uint8), np.zeros((4, 4, 3), np.float32), np.zeros((0, 4, 3), np.uint8)):
+        with pytest.raises(ValueError):
+            fastpng.encode_png(bad)
+    with pytest.raises(ValueError):
+        fastpng.encode_png(smooth, 10)
+    with pytest.raises(ValueError):
+        fastpng.encode_png(smooth, 1, "paeth")
+
+
 def test_convert_folder_host_logic_with_a_stand_in_pipeline(tmp_path, monkeypatch):
     """convert_folder's host side on CPU (decode-ahead pool, bounded writer backlog, numbering, copies, resume, sharding,
     error propagation) with ClipInterpolator replaced by a stand-in that averages neighbouring frames; the real pipeline is
@@ -266,11 +293,13 @@ def test_convert_folder_host_logic_with_a_stand_in_pipeline(tmp_path, monkeypatc
             assert uint8 and channels == 3
             self.sf = sf
 
-        def run(self, clip):
+        def run(self, clip, out_host=None):
             f = clip.numpy().astype(np.float32)
             outs = [((1 - k / (self.sf + 1)) * f[i] + k / (self.sf + 1) * f[i + 1]).astype(np.uint8)
                     for i in range(len(f) - 1) for k in range(1, self.sf + 1)]
-            return torch.from_numpy(np.stack(outs))
+            assert out_host is not None and tuple(out_host.shape) == (len(outs), *f.shape[1:3], 3)
+            out_host.copy_(torch.from_numpy(np.stack(outs)))
+            return out_host
 
     monkeypatch.setattr(pl, "ClipInterpolator", StandIn)
     net = torch.nn.Linear(1, 1)                                           # only .parameters() is touched when `net` is given
@@ -301,6 +330,10 @@ def test_convert_folder_host_logic_with_a_stand_in_pipeline(tmp_path, monkeypatc
     convert_folder(str(src), str(fast), 2, net=net, device=dev, png_compress_level=1)                  # same pixels, other zlib level
     for n in os.listdir(fast):
         assert np.array_equal(np.asarray(Image.open(fast / n)), np.asarray(Image.open(tmp_path / "out_sf2" / n))), n
+    lean = tmp_path / "out_lean"
+    convert_folder(str(src), str(lean), 2, net=net, device=dev, png_writer="fast")                     # rrin_b200.fastpng
+    for n in os.listdir(lean):
+        assert np.array_equal(np.asarray(Image.open(lean / n)), np.asarray(Image.open(tmp_path / "out_sf2" / n))), n
     # two ranks write disjoint files whose union is the single-process output
     dst2 = tmp_path / "out_ranks"
     w0 = convert_folder(str(src), str(dst2), 2, net=net, device=dev, rank=0, world=2, chunk_pairs=2)

@@ -1,6 +1,7 @@
 """End-to-end rate of convert_folder (PNG folder in -> PNG folder out) at 1080p: usage  python tools/convert_bench.py [frames]
 Synthetic smooth frames with a little noise (PNG-compressible like video frames); random-init weights; prints output frames/s
-(interpolated + copied originals, as the reference counts its progress bar) for PIL's default zlib level and for level 1."""
+(interpolated + copied originals, as the reference counts its progress bar) for PIL at its default zlib level and at level 1,
+and for the lean writer (rrin_b200.fastpng) at levels 1 and 0."""
 import os
 import shutil
 import sys
@@ -37,12 +38,13 @@ with ThreadPoolExecutor(os.cpu_count()) as ex:
 torch.manual_seed(0)
 net = Net().cuda().eval()
 convert_folder(src, os.path.join(root, "warm"), 1, net=net, chunk_pairs=4)      # engine + weights + first-call costs
-for lvl in (None, 1):
-    dst = os.path.join(root, f"out_{lvl}")
+for writer, lvl in (("pil", None), ("pil", 1), ("fast", 1), ("fast", 0)):
+    dst = os.path.join(root, f"out_{writer}_{lvl}")
     torch.cuda.synchronize()
     t0 = time.time()
-    written = convert_folder(src, dst, 1, net=net, batch=4, chunk_pairs=16, png_compress_level=lvl)
+    written = convert_folder(src, dst, 1, net=net, batch=4, chunk_pairs=16, png_compress_level=lvl, png_writer=writer)
     dt = time.time() - t0
-    print(f"convert_folder 1080p, {n} frames -> {len(written)} files, png level {lvl}: {dt:.2f} s = {len(written) / dt:.1f} output frames/s "
-          f"({(n - 1) / dt:.1f} interpolated/s) on {os.cpu_count()} host threads", flush=True)
+    mb = sum(os.path.getsize(p) for p in written[1::2]) / max(1, len(written[1::2])) / 1e6
+    print(f"convert_folder 1080p, {n} frames -> {len(written)} files, writer {writer}, png level {lvl}: {dt:.2f} s = {len(written) / dt:.1f} output frames/s "
+          f"({(n - 1) / dt:.1f} interpolated/s) on {os.cpu_count()} host threads, {mb:.2f} MB per interpolated frame", flush=True)
 shutil.rmtree(root)
