@@ -40,6 +40,21 @@ def test_conv_table_matches_reference_parameter_tree():
         assert act == (0 if key.endswith("up.1") or key.endswith("last") else 1), key   # unet.py:47,60,63 only
 
 
+def test_bench_flop_count_follows_from_the_conv_table():
+    """bench.py's algorithmic FLOP per padded pixel (the roofline numerator) is the sum over the 81 convs of
+    2 * 9 * Cin * Cout at the conv's resolution (level L convolves H * W / 4^L pixels) with the TRUE channel counts -- zero
+    padding of packed tensors and structural zeros of the space-to-depth weights are not credited."""
+    import importlib.util
+    from fractions import Fraction
+    from rrin_b200 import engine
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per_px = sum(Fraction(2 * 9 * cin * cout, 4 ** level) for _key, cin, cout, level, _src, _act in engine.conv_table())
+    assert per_px == bench.FLOP_PER_PX == 1_736_064
+    assert abs(float(per_px) * bench.H * bench.W / 1e12 - 3.62656825344) < 1e-9          # TFLOP per 1080p frame, the bench line's config.tflop_per_frame
+
+
 def test_net_accepts_optional_level_and_rejects_cpu_inputs():
     from rrin_b200 import Net
     Net(3)
